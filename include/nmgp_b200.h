@@ -1,0 +1,124 @@
+/* nmgp_b200.h -- C ABI of the B200-native NMGP log-posterior + gradient library (libnmgp_b200.so).
+ *
+ * The reference (Corleno/Nonstationary_Multivariate_Gaussian_Process) is pure Python and has no FFI;
+ * its plugin surface is the module attribute `Utility.logpos.nlogpos_obj{_S,,_SVC}` called from the
+ * drivers' MAP/HMC loops.  Each entry point below names the reference interface it stands in for.
+ * Conventions: plain pointers and sizes, FP64 everywhere, no C++/torch types; every function returns
+ * 0 on success or a negative NMGP_E* code and never throws; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream); all work is stream-ordered on it; the caller owns every
+ * buffer it passes, the plan owns its caches and workspace; a plan is not thread-safe.
+ *
+ * Layouts (row-major, contiguous):
+ *   x      [S,N]      sorted time stamps per subject            (Utility/logpos.py: argument `x`)
+ *   Y      [S,N,M]    observations                              (argument `Y`, N by M)
+ *   pars   [S,P]      flat parameter vectors, reference order:
+ *            stationary   [tilde_l, tilde_sigma, uL(T), tilde_sigma2_err]           P = T+3     (logpos.py:46-57)
+ *            separable    [tilde_l(N), tilde_sigma(N), uL(T), tilde_sigma2_err]     P = 2N+T+1  (logpos.py:17-29)
+ *            nonseparable [tilde_l(N), uL(N*T) time-major, tilde_sigma2_err]        P = N+N*T+1 (logpos.py:32-43)
+ *          with T = M(M+1)/2 and uL a row-major lower triangle whose diagonal slots are log-scale
+ *          (Utility/utils.py:10-22).
+ *   vals   [S,NMGP_NVALS]  vals[0] = -logpost (what nlogpos_obj* returns), vals[1] = loglik, then the
+ *          prior components in the order of the reference's verbose tuple, zero padded:
+ *            stationary   [., ., lp_tilde_l, lp_uL, lp_sigma2, 0]                   (logpos.py:399-400)
+ *            separable    [., ., lp_tilde_l, lp_tilde_sigma, lp_uL, lp_sigma2]      (logpos.py:231-232)
+ *            nonseparable [., ., lp_tilde_l, lp_uL, lp_sigma2, 0]                   (logpos.py:313-320)
+ *   grad   [S,P]      d(-logpost)/d pars  (what `NegLog.backward()` leaves in the leaves' .grad)
+ *   info   [S]        0 = ok; k>0 = the Cholesky of that subject's covariance failed at pivot k
+ *                     (value and gradient of that subject are NaN; other subjects are unaffected)
+ */
+#ifndef NMGP_B200_H
+#define NMGP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMGP_STATIONARY 0   /* Utility/logpos.py:383-462  nlogpos_obj_S   */
+#define NMGP_SEPARABLE 1    /* Utility/logpos.py:216-296  nlogpos_obj     */
+#define NMGP_NONSEPARABLE 2 /* Utility/logpos.py:299-380  nlogpos_obj_SVC */
+
+#define NMGP_NVALS 6
+#define NMGP_NHYPER 9
+
+#define NMGP_OK 0
+#define NMGP_EINVAL (-1)
+#define NMGP_ECUDA (-2)
+#define NMGP_ENOMEM (-3)
+
+/* hyper[NMGP_NHYPER], host memory, keyword arguments of the objective in signature order:
+ *   stationary   {mu_tilde_l, sigma_tilde_l, a, b, c}                                            (logpos.py:383)
+ *   separable    {mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma,
+ *                 beta_tilde_sigma, a, b, c}                                                     (logpos.py:216)
+ *   nonseparable {mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b}          (logpos.py:299)
+ */
+
+typedef struct nmgp_plan nmgp_plan;
+
+/* Number of parameters P of one subject for (model, N, M); negative on bad arguments.
+ * Mirrors the slicing of vec2pars_S / vec2pars / vec2pars_SVC (logpos.py:17-57). */
+int nmgp_n_params(int model, int N, int M);
+
+/* Create the evaluation plan for S independent subjects of equal shape (N time points, M outputs).
+ * Caches everything that is loop-invariant in the drivers' MAP/HMC loops: copies of x and Y, the
+ * GP-prior covariances of logpos.py:271-281 / :357-365 factored once (the reference re-factors them
+ * 1+T times per call), and the workspace.  x_dev / Y_dev are device pointers.  prior_flag mirrors the
+ * `Prior=` keyword.  workspace_limit_bytes bounds the factorisation workspace (0 = choose from free
+ * memory); subjects are processed in chunks that fit. */
+int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const double* Y_dev,
+                     const double* hyper, int prior_flag, size_t workspace_limit_bytes, void* stream);
+
+int nmgp_plan_destroy(nmgp_plan* plan);
+
+/* One batched evaluation: for every subject the value tuple and (if grad_dev != NULL) the gradient.
+ * Device pointers; stream-ordered; no host synchronisation.  Stands in for
+ * `nlogpos_obj*(pars, Y, x, **hyper, verbose=True)` followed by `.backward()`
+ * (e.g. Nonseparable_Model/Nonseparable_model_mpisim.py:183-186) over S subjects at once. */
+int nmgp_logpost_grad(nmgp_plan* plan, const double* pars_dev, double* vals_dev, double* grad_dev, int* info_dev,
+                      void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies pars host->device, evaluates, copies
+ * vals / grad / info back and synchronises the stream.  This is the call a reference maintainer binds
+ *  and what bench.py times as `e2e`. */
+int nmgp_logpost_grad_host(nmgp_plan* plan, const double* pars_host, double* vals_host, double* grad_host,
+                           int* info_host, void* stream);
+
+/* Number of kernels the plan's last evaluation launched (bench.py's `gpu_launches`). */
+long nmgp_plan_last_launches(const nmgp_plan* plan);
+/* Bytes of device memory owned by the plan. */
+size_t nmgp_plan_device_bytes(const nmgp_plan* plan);
+/* Subjects per chunk and the factorisation block size the plan chose. */
+int nmgp_plan_chunk(const nmgp_plan* plan);
+int nmgp_plan_block(const nmgp_plan* plan);
+
+/* Last error message of the calling thread ("" if none). */
+const char* nmgp_last_error(void);
+
+/* ---------------------------------------------------------------- unit entry points (tests, ncu) ----
+ * Elementwise covariance kernels with the reference's semantics, device pointers:
+ *   nmgp_rbf_cov       Utility/kernels.py:24-43   alpha^2 exp(-0.5 |(x1_i - x2_j)/beta|^2)   (+1e-6 I if x2 == NULL)
+ *   nmgp_gibbs_cov     Utility/kernels.py:46-73   sigma1_i sigma2_j sqrt(2 l1_i l2_j/(l1_i^2+l2_j^2)) exp(-d/(..)) (+1e-6 I)
+ * out is [N1,N2] row-major.  sigma pointers may be NULL (= ones). */
+int nmgp_rbf_cov(const double* x1, int N1, const double* x2, int N2, double alpha, double beta, double* out,
+                 void* stream);
+int nmgp_gibbs_cov(const double* x1, const double* sigma1, const double* ell1, int N1, const double* x2,
+                   const double* sigma2, const double* ell2, int N2, double* out, void* stream);
+
+/* Dense nonseparable covariance K + sigma2_err I of logpos.py:339-352 for `batch` subjects, written in the
+ * REFERENCE's output-major ordering (row (m,i) -> m*N+i), full symmetric [batch, NM, NM].
+ * (The plan itself builds the same matrix time-major and blocked; this entry exists for parity tests.) */
+int nmgp_nonseparable_cov(const double* x, const double* pars, int batch, int N, int M, double* out, void* stream);
+
+/* Batched blocked Cholesky engine on `batch` symmetric positive-definite matrices [batch, n, n] (row-major,
+ * lower triangle referenced).  In place:
+ *   potrf: lower triangle <- L (strict upper untouched), logdet[b] = log det A_b, info[b] as above.
+ *   potri: after potrf, full matrix <- inverse (both triangles).
+ * These wrap the same tile kernels the plan uses (copy into the padded block layout, run, copy out). */
+int nmgp_potrf_batched(double* A, int n, int batch, double* logdet, int* info, void* stream);
+int nmgp_potrf_potri_batched(double* A, int n, int batch, double* logdet, int* info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMGP_B200_H */

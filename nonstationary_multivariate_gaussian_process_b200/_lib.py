@@ -1,0 +1,122 @@
+"""Loader / builder of the C-ABI CUDA library `libnmgp_b200.so` (include/nmgp_b200.h).
+
+There is deliberately no CPU fallback: if the library is missing or no CUDA device is present, every
+compute entry point of this package raises.  `build_library()` compiles the sources in `csrc/` with nvcc for
+sm_100a into the package directory (in-tree, so the built .so travels to the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
+SOURCES = ["engine.cu", "models.cu", "api.cu"]
+HEADERS = ["common.cuh", "engine.cuh", "models.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+NVALS = 6
+NHYPER = 9
+STATIONARY, SEPARABLE, NONSEPARABLE = 0, 1, 2
+
+_lock = threading.Lock()
+_lib = None
+
+
+class NmgpError(RuntimeError):
+    pass
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu -> libnmgp_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NmgpError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+def _declare(lib):
+    c = ctypes
+    dp, ip, vp = c.c_void_p, c.c_void_p, c.c_void_p   # raw device/host addresses
+    lib.nmgp_last_error.restype = c.c_char_p
+    lib.nmgp_last_error.argtypes = []
+    lib.nmgp_n_params.restype = c.c_int
+    lib.nmgp_n_params.argtypes = [c.c_int, c.c_int, c.c_int]
+    lib.nmgp_plan_create.restype = c.c_int
+    lib.nmgp_plan_create.argtypes = [c.POINTER(c.c_void_p), c.c_int, c.c_int, c.c_int, c.c_int, dp, dp,
+                                     c.POINTER(c.c_double), c.c_int, c.c_size_t, vp]
+    lib.nmgp_plan_destroy.restype = c.c_int
+    lib.nmgp_plan_destroy.argtypes = [c.c_void_p]
+    lib.nmgp_logpost_grad.restype = c.c_int
+    lib.nmgp_logpost_grad.argtypes = [c.c_void_p, dp, dp, dp, ip, vp]
+    lib.nmgp_logpost_grad_host.restype = c.c_int
+    lib.nmgp_logpost_grad_host.argtypes = [c.c_void_p, dp, dp, dp, ip, vp]
+    lib.nmgp_plan_last_launches.restype = c.c_long
+    lib.nmgp_plan_last_launches.argtypes = [c.c_void_p]
+    lib.nmgp_plan_device_bytes.restype = c.c_size_t
+    lib.nmgp_plan_device_bytes.argtypes = [c.c_void_p]
+    lib.nmgp_plan_chunk.restype = c.c_int
+    lib.nmgp_plan_chunk.argtypes = [c.c_void_p]
+    lib.nmgp_plan_block.restype = c.c_int
+    lib.nmgp_plan_block.argtypes = [c.c_void_p]
+    lib.nmgp_rbf_cov.restype = c.c_int
+    lib.nmgp_rbf_cov.argtypes = [dp, c.c_int, dp, c.c_int, c.c_double, c.c_double, dp, vp]
+    lib.nmgp_gibbs_cov.restype = c.c_int
+    lib.nmgp_gibbs_cov.argtypes = [dp, dp, dp, c.c_int, dp, dp, dp, c.c_int, dp, vp]
+    lib.nmgp_nonseparable_cov.restype = c.c_int
+    lib.nmgp_nonseparable_cov.argtypes = [dp, dp, c.c_int, c.c_int, c.c_int, dp, vp]
+    lib.nmgp_potrf_batched.restype = c.c_int
+    lib.nmgp_potrf_batched.argtypes = [dp, c.c_int, c.c_int, dp, ip, vp]
+    lib.nmgp_potrf_potri_batched.restype = c.c_int
+    lib.nmgp_potrf_potri_batched.argtypes = [dp, c.c_int, c.c_int, dp, ip, vp]
+    return lib
+
+
+EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
+           "nmgp_logpost_grad_host", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
+           "nmgp_plan_block", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
+           "nmgp_potrf_potri_batched"]
+
+
+def load_library():
+    """dlopen the C-ABI library (no CUDA call is made here).  Raises NmgpError if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NmgpError(
+                    f"{LIB_PATH} is missing: the CUDA library has not been built "
+                    "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+            _lib = _declare(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().nmgp_last_error().decode("utf-8", "replace")
+        raise NmgpError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise NmgpError("no CUDA device is available: this package has no CPU fallback (B200 / sm_100a only)")
+    return torch

@@ -1,0 +1,174 @@
+"""Batched evaluation plans: the host-side handle on `nmgp_plan` (include/nmgp_b200.h).
+
+A plan fixes everything the reference's MAP / HMC loops keep constant between calls -- the model, the subjects'
+time stamps `x` and observations `Y`, the hyper-parameters (`**hyper_pars` of the drivers) -- and evaluates
+`-log posterior`, its components and its gradient for all subjects in one call.  The single-subject functions of
+`logpos.py` (reference signatures) are thin wrappers over a plan with S = 1.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Mapping
+
+import numpy as np
+
+from . import _lib
+
+MODELS = {"stationary": _lib.STATIONARY, "separable": _lib.SEPARABLE, "nonseparable": _lib.NONSEPARABLE}
+
+# keyword order and defaults of the reference signatures (Utility/logpos.py:383, :216, :299)
+HYPER_SPEC = {
+    "stationary": (("mu_tilde_l", None), ("sigma_tilde_l", None), ("a", 1), ("b", 1), ("c", 10)),
+    "separable": (("mu_tilde_l", 0.0), ("alpha_tilde_l", 1.0), ("beta_tilde_l", 1.0), ("mu_tilde_sigma", 0.0),
+                  ("alpha_tilde_sigma", 1.0), ("beta_tilde_sigma", 1.0), ("a", 1), ("b", 1), ("c", 10)),
+    "nonseparable": (("mu_tilde_l", 0.0), ("alpha_tilde_l", 5.0), ("beta_tilde_l", 1.0), ("mu_L", 0.0),
+                     ("alpha_L", 5.0), ("beta_L", 1.0), ("a", 1), ("b", 1)),
+}
+# number of entries of the reference's verbose tuple (value + components)
+N_VERBOSE = {"stationary": 5, "separable": 6, "nonseparable": 5}
+
+
+def hyper_vector(model: str, hyper: Mapping[str, float]) -> np.ndarray:
+    spec = HYPER_SPEC[model]
+    unknown = set(hyper) - {k for k, _ in spec}
+    if unknown:
+        raise TypeError(f"unexpected hyper-parameter(s) for the {model} model: {sorted(unknown)}")
+    out = np.zeros(_lib.NHYPER, dtype=np.float64)
+    for i, (k, default) in enumerate(spec):
+        v = hyper.get(k, default)
+        if v is None:
+            raise TypeError(f"missing required hyper-parameter '{k}' for the {model} model")
+        out[i] = float(v)
+    return out
+
+
+def n_params(model: str, N: int, M: int) -> int:
+    T = M * (M + 1) // 2
+    return {"stationary": T + 3, "separable": 2 * N + T + 1, "nonseparable": N + N * T + 1}[model]
+
+
+class LogPosteriorPlan:
+    """Evaluation plan for S subjects of equal shape (N time points, M outputs) on one GPU."""
+
+    def __init__(self, model: str, x, Y, hyper: Mapping[str, float] | None = None, prior: bool = True,
+                 device=None, workspace_limit_bytes: int = 0):
+        torch = _lib.require_cuda()
+        if model not in MODELS:
+            raise ValueError(f"unknown model '{model}' (expected one of {sorted(MODELS)})")
+        self.model = model
+        self.lib = _lib.load_library()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        x_t = torch.as_tensor(x, dtype=torch.float64)
+        Y_t = torch.as_tensor(Y, dtype=torch.float64)
+        if x_t.dim() == 1:
+            x_t, Y_t = x_t.unsqueeze(0), Y_t.unsqueeze(0)
+        if x_t.dim() != 2 or Y_t.dim() != 3 or Y_t.shape[:2] != x_t.shape:
+            raise ValueError(f"expected x [S,N] and Y [S,N,M]; got {tuple(x_t.shape)} and {tuple(Y_t.shape)}")
+        self.S, self.N, self.M = int(Y_t.shape[0]), int(Y_t.shape[1]), int(Y_t.shape[2])
+        if self.N < 1 or self.M < 1 or self.M > 16:
+            raise ValueError("need N >= 1 and 1 <= M <= 16")
+        self.P = n_params(model, self.N, self.M)
+        self.hyper = dict(hyper or {})
+        self.prior = bool(prior)
+        hv = hyper_vector(model, self.hyper)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            xd = x_t.to(self.device).contiguous()
+            Yd = Y_t.to(self.device).contiguous()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_plan_create(
+                ctypes.byref(self._handle), MODELS[model], self.S, self.N, self.M, xd.data_ptr(), Yd.data_ptr(),
+                hv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(self.prior), int(workspace_limit_bytes),
+                ctypes.c_void_p(stream))
+            _lib.check(rc, "nmgp_plan_create")
+        self._pinned = None
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def chunk(self) -> int:
+        return self.lib.nmgp_plan_chunk(self._handle)
+
+    @property
+    def device_bytes(self) -> int:
+        return self.lib.nmgp_plan_device_bytes(self._handle)
+
+    @property
+    def last_launches(self) -> int:
+        return self.lib.nmgp_plan_last_launches(self._handle)
+
+    # ------------------------------------------------------------------ evaluation
+    def value_and_grad(self, pars, need_grad: bool = True):
+        """Device path: pars [S,P] CUDA float64 -> (vals [S,6], grad [S,P] or None, info [S] int32), all CUDA.
+        Stream-ordered on torch's current stream; no host synchronisation."""
+        torch = _lib.require_cuda()
+        if not (isinstance(pars, torch.Tensor) and pars.is_cuda):
+            raise TypeError("value_and_grad expects a CUDA tensor; use value_and_grad_host for host buffers")
+        p = pars.detach().to(torch.float64).reshape(self.S, self.P).contiguous()
+        vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
+        grad = torch.empty((self.S, self.P), dtype=torch.float64, device=self.device) if need_grad else None
+        info = torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        if self.S == 0:
+            return vals, grad, info
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_logpost_grad(self._handle, p.data_ptr(), vals.data_ptr(),
+                                            grad.data_ptr() if need_grad else None, info.data_ptr(),
+                                            ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_logpost_grad")
+        return vals, grad, info
+
+    def _pinned_buffers(self):
+        torch = _lib.require_cuda()
+        if self._pinned is None:
+            self._pinned = (
+                torch.empty((self.S, self.P), dtype=torch.float64).pin_memory(),
+                torch.empty((self.S, _lib.NVALS), dtype=torch.float64).pin_memory(),
+                torch.empty((self.S, self.P), dtype=torch.float64).pin_memory(),
+                torch.empty((self.S,), dtype=torch.int32).pin_memory(),
+            )
+        return self._pinned
+
+    def value_and_grad_host(self, pars, need_grad: bool = True, pinned_io: bool = False):
+        """Host path (what the reference's drivers see): pars [S,P] CPU float64 -> CPU (vals, grad, info).
+        Host->device copy of pars, evaluation, device->host copy of the results and a stream synchronise all
+        happen inside the C call `nmgp_logpost_grad_host`.  With pinned_io=True `pars` is staged through (and the
+        results are returned in) the plan's pinned buffers, which are reused by the next call."""
+        torch = _lib.require_cuda()
+        p = torch.as_tensor(pars, dtype=torch.float64).detach().reshape(self.S, self.P)
+        if p.is_cuda:
+            raise TypeError("value_and_grad_host expects host memory")
+        if pinned_io:
+            pin_p, vals, grad, info = self._pinned_buffers()
+            if p.data_ptr() != pin_p.data_ptr():
+                pin_p.copy_(p)
+            p = pin_p
+        else:
+            p = p.contiguous()
+            vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64)
+            grad = torch.empty((self.S, self.P), dtype=torch.float64)
+            info = torch.empty((self.S,), dtype=torch.int32)
+        if self.S == 0:
+            return vals, (grad if need_grad else None), info
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_logpost_grad_host(self._handle, p.data_ptr(), vals.data_ptr(),
+                                                 grad.data_ptr() if need_grad else None, info.data_ptr(),
+                                                 ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_logpost_grad_host")
+        return vals, (grad if need_grad else None), info
+
+    def pinned_pars(self):
+        """The plan's pinned staging buffer for `pars` ([S,P]); fill it in place and call
+        value_and_grad_host(buf, pinned_io=True) to avoid an extra host copy."""
+        return self._pinned_buffers()[0]
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.nmgp_plan_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

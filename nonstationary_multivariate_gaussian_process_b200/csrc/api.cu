@@ -1,0 +1,416 @@
+// C ABI of libnmgp_b200.so (include/nmgp_b200.h): plan = cached loop-invariant state + workspace; one call =
+// one batched log-posterior + gradient evaluation.  No torch types, no exceptions across the boundary.
+#include "../../include/nmgp_b200.h"
+
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "models.cuh"
+
+namespace nmgp {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace nmgp
+
+using namespace nmgp;
+
+struct nmgp_plan {
+  int model = 0, S = 0, N = 0, M = 0, T = 0, P = 0;
+  int nmat = 1;   // matrices per subject (1 nonseparable, M separable/stationary)
+  int n = 0;      // dimension of each matrix
+  int nP = 0, Kt = 0;
+  int chunk = 0;  // subjects per pass
+  int nprior = 0; // GP-prior covariance matrices per subject (0 stationary, 2 otherwise)
+  int nv1 = 1;    // right-hand sides for prior 1
+  double hyper[NMGP_NHYPER] = {0};
+  HyperConst hc{};
+  std::vector<void*> allocs;
+  size_t dev_bytes = 0;
+  long last_launches = 0;
+  // persistent
+  double *x = nullptr, *Y = nullptr;
+  double *Wp0 = nullptr, *Wp1 = nullptr;    // [S][N][N] lower Cholesky factors of the prior covariances
+  double *hld0 = nullptr, *hld1 = nullptr;  // [S] half log-determinants
+  // chunk workspace
+  BlockBatch bb;
+  Scratch w{};
+  // staging for the host-buffer call
+  double *pars_d = nullptr, *vals_d = nullptr, *grad_d = nullptr;
+  int* info_d = nullptr;
+};
+
+namespace {
+
+template <typename Tp>
+int dev_alloc(nmgp_plan* pl, Tp** out, size_t count) {
+  *out = nullptr;
+  if (count == 0) count = 1;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, count * sizeof(Tp));
+  if (e != cudaSuccess) {
+    set_last_error(std::string("cudaMalloc of ") + std::to_string(count * sizeof(Tp)) + " bytes failed: " +
+                   cudaGetErrorString(e));
+    cudaGetLastError();
+    return NMGP_ENOMEM;
+  }
+  pl->allocs.push_back(p);
+  pl->dev_bytes += count * sizeof(Tp);
+  *out = reinterpret_cast<Tp*>(p);
+  return 0;
+}
+
+HyperConst make_hyper_const(int model, const double* hy, int prior) {
+  HyperConst h{};
+  h.prior = prior ? 1 : 0;
+  h.half_log2pi = std::log(std::sqrt(2.0 * M_PI));
+  double a = 1, b = 1, c = 10;
+  if (model == NMGP_STATIONARY) {
+    const float loc = (float)hy[0], sc = (float)hy[1];     // Normal(mu_tilde_l, sigma_tilde_l), logpos.py:446
+    h.s_loc = (double)loc;
+    h.s_var = (double)(sc * sc);
+    h.s_logscale = (double)logf(sc);
+    a = hy[2]; b = hy[3]; c = hy[4];
+  } else if (model == NMGP_SEPARABLE) {
+    h.mu0 = hy[0]; h.mu1 = hy[3];
+    a = hy[6]; b = hy[7]; c = hy[8];
+  } else {
+    h.mu0 = hy[0]; h.mu1 = hy[3];
+    a = hy[6]; b = hy[7];
+  }
+  const float c32 = (float)c;                               // Normal(0, c), logpos.py:283,450
+  h.n_loc = 0.0;
+  h.n_var = (double)(c32 * c32);
+  h.n_logscale = (double)logf(c32);
+  h.ig_a = a; h.ig_b = b;
+  h.ig_alogb = a * std::log(b);
+  h.ig_lgamma = std::lgamma(a);
+  return h;
+}
+
+size_t per_subject_bytes(const nmgp_plan* pl) {
+  const size_t N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat, nP = pl->nP, Kt = pl->Kt;
+  const size_t MT = pl->model == NMGP_NONSEPARABLE ? padded_M(pl->M) : 0;
+  size_t d = 0;
+  d += nm * nP * nP;            // A
+  d += nm * Kt * kNB * kNB;     // Dinv
+  d += nm;                      // logdet
+  d += 2 * N + 1;               // ell, sig, s2
+  d += pl->model == NMGP_NONSEPARABLE ? n * MT : M * M;  // Lst
+  d += 2 * N * N;               // Kx, CK
+  d += 2 * nm * n;              // alpha, yv
+  d += pl->model == NMGP_NONSEPARABLE ? 2 * n * MT : 2 * N * M;  // Wout, Vout
+  d += 2 * N + M + M * M;       // gl, gs, lam, Vec
+  d += 3 * (N + N * (size_t)pl->nv1);  // R, Z, G
+  return d * sizeof(double) + nm * sizeof(int);
+}
+
+int alloc_workspace(nmgp_plan* pl) {
+  const size_t cs = pl->chunk, N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat;
+  const bool svc = pl->model == NMGP_NONSEPARABLE;
+  const size_t MT = svc ? padded_M(pl->M) : 0;
+  BlockBatch& b = pl->bb;
+  b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
+  NMGP_TRY(dev_alloc(pl, &b.A, cs * nm * (size_t)pl->nP * pl->nP));
+  NMGP_TRY(dev_alloc(pl, &b.Dinv, cs * nm * (size_t)pl->Kt * kNB * kNB));
+  NMGP_TRY(dev_alloc(pl, &b.logdet, cs * nm));
+  NMGP_TRY(dev_alloc(pl, &b.info, cs * nm));
+  Scratch& w = pl->w;
+  NMGP_TRY(dev_alloc(pl, &w.ell, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.sig, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.s2, cs));
+  NMGP_TRY(dev_alloc(pl, &w.Lst, svc ? cs * n * MT : cs * M * M));
+  NMGP_TRY(dev_alloc(pl, &w.Kx, cs * N * N));
+  NMGP_TRY(dev_alloc(pl, &w.CK, cs * N * N));
+  NMGP_TRY(dev_alloc(pl, &w.alpha, cs * nm * n));
+  NMGP_TRY(dev_alloc(pl, &w.yv, svc ? 1 : cs * nm * n));
+  NMGP_TRY(dev_alloc(pl, &w.Wout, svc ? cs * n * MT : cs * N * M));
+  NMGP_TRY(dev_alloc(pl, &w.Vout, svc ? cs * n * MT : cs * N * M));
+  NMGP_TRY(dev_alloc(pl, &w.gl, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.gs, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.lam, cs * M));
+  NMGP_TRY(dev_alloc(pl, &w.Vec, cs * M * M));
+  const size_t nv1 = pl->nv1;
+  NMGP_TRY(dev_alloc(pl, &w.R0, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.R1, cs * N * nv1));
+  NMGP_TRY(dev_alloc(pl, &w.Z0, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.Z1, cs * N * nv1));
+  NMGP_TRY(dev_alloc(pl, &w.G0, cs * N));
+  NMGP_TRY(dev_alloc(pl, &w.G1, cs * N * nv1));
+  return 0;
+}
+
+// Factor the GP-prior covariance alpha^2 exp(-0.5 d/beta^2) + 1e-6 I of every subject once (the reference rebuilds and
+// re-factors it on every call, logpos.py:271-281, 357-365): L = chol(Sigma_p) and 0.5 log det.
+int factor_prior(nmgp_plan* pl, double alpha, double beta, double* Wp, double* hld, cudaStream_t st) {
+  BlockBatch pb = pl->bb;  // reuse the likelihood workspace
+  pb.n = pl->N;
+  pb.nP = padded_dim(pl->N);
+  pb.Kt = pb.nP / kNB;
+  const size_t capA = (size_t)pl->bb.batch * pl->bb.strideA();
+  const size_t capD = (size_t)pl->bb.batch * pl->bb.strideD();
+  size_t cap = capA / (size_t)pb.strideA();
+  if (capD / (size_t)pb.strideD() < cap) cap = capD / (size_t)pb.strideD();
+  if ((size_t)pl->bb.batch < cap) cap = pl->bb.batch;   // logdet / info arrays
+  if (cap > 65535) cap = 65535;
+  if (cap == 0) { set_last_error("factor_prior: workspace too small"); return NMGP_ENOMEM; }
+  for (int s0 = 0; s0 < pl->S; s0 += (int)cap) {
+    const int cs = pl->S - s0 < (int)cap ? pl->S - s0 : (int)cap;
+    pb.batch = cs;
+    NMGP_TRY(launch_prior_cov_blocks(pl->x + (size_t)s0 * pl->N, cs, pl->N, alpha, beta, pb, st, nullptr));
+    NMGP_TRY(engine_potrf(pb, st, nullptr, /*stable_panel=*/true));
+    NMGP_TRY(launch_extract_factor(pb, pl->N, Wp + (size_t)s0 * pl->N * pl->N, hld + s0, st, nullptr));
+  }
+  return 0;
+}
+
+__global__ void pack_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, long strideA, int ld) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  const int b = blockIdx.z;
+  if (q >= ld) return;
+  double v;
+  if (p < n && q < n) v = (q <= p) ? src[((long)b * n + p) * n + q] : src[((long)b * n + q) * n + p];
+  else v = (p == q) ? 1.0 : 0.0;
+  dst[(long)b * strideA + (long)p * ld + q] = v;
+}
+
+__global__ void unpack_kernel(const double* __restrict__ src, long strideA, int ld, int n, double* __restrict__ dst,
+                              int lower_only) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  const int b = blockIdx.z;
+  if (q >= n) return;
+  if (lower_only && q > p) return;
+  dst[((long)b * n + p) * n + q] = src[(long)b * strideA + (long)p * ld + q];
+}
+
+int potrf_unit(double* A, int n, int batch, double* logdet, int* info, int invert, cudaStream_t st) {
+  if (n <= 0 || batch < 0 || !A) { set_last_error("potrf: bad arguments"); return NMGP_EINVAL; }
+  if (batch == 0) return 0;
+  BlockBatch b;
+  b.n = n; b.nP = padded_dim(n); b.Kt = b.nP / kNB; b.NB = kNB;
+  long step = (long)((8ull << 30) / ((size_t)b.strideA() * sizeof(double)));
+  if (step < 1) step = 1;
+  if (step > 4096) step = 4096;
+  if (step > batch) step = batch;
+  double *ws = nullptr, *dinv = nullptr, *ld = nullptr;
+  int* inf = nullptr;
+  NMGP_CUDA_TRY(cudaMalloc(&ws, (size_t)step * b.strideA() * sizeof(double)));
+  cudaError_t e1 = cudaMalloc(&dinv, (size_t)step * b.strideD() * sizeof(double));
+  cudaError_t e2 = cudaMalloc(&ld, (size_t)step * sizeof(double));
+  cudaError_t e3 = cudaMalloc(&inf, (size_t)step * sizeof(int));
+  int rc = 0;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { set_last_error("potrf: out of memory"); rc = NMGP_ENOMEM; }
+  for (int b0 = 0; rc == 0 && b0 < batch; b0 += (int)step) {
+    const int cs = batch - b0 < step ? batch - b0 : (int)step;
+    b.A = ws; b.Dinv = dinv; b.logdet = ld; b.info = inf; b.batch = cs;
+    dim3 grid((b.nP + 127) / 128, b.nP, cs);
+    pack_kernel<<<grid, 128, 0, st>>>(A + (size_t)b0 * n * n, n, ws, b.strideA(), b.nP);
+    rc = engine_potrf(b, st, nullptr);
+    if (rc == 0 && invert) rc = engine_potri(b, st, nullptr);
+    if (rc != 0) break;
+    dim3 g2((n + 127) / 128, n, cs);
+    unpack_kernel<<<g2, 128, 0, st>>>(ws, b.strideA(), b.nP, n, A + (size_t)b0 * n * n, invert ? 0 : 1);
+    if (logdet) cudaMemcpyAsync(logdet + b0, ld, cs * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (info) cudaMemcpyAsync(info + b0, inf, cs * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (cudaGetLastError() != cudaSuccess) { set_last_error("potrf: launch failed"); rc = NMGP_ECUDA; }
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(ws); cudaFree(dinv); cudaFree(ld); cudaFree(inf);
+  return rc;
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* nmgp_last_error(void) { return g_last_error.c_str(); }
+
+int nmgp_n_params(int model, int N, int M) {
+  if (N <= 0 || M <= 0) return NMGP_EINVAL;
+  const int T = M * (M + 1) / 2;
+  switch (model) {
+    case NMGP_STATIONARY: return T + 3;
+    case NMGP_SEPARABLE: return 2 * N + T + 1;
+    case NMGP_NONSEPARABLE: return N + N * T + 1;
+    default: return NMGP_EINVAL;
+  }
+}
+
+int nmgp_plan_destroy(nmgp_plan* pl) {
+  if (!pl) return 0;
+  for (void* p : pl->allocs) cudaFree(p);
+  delete pl;
+  return 0;
+}
+
+int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const double* Y_dev,
+                     const double* hyper, int prior_flag, size_t workspace_limit_bytes, void* stream) {
+  if (!out) return NMGP_EINVAL;
+  *out = nullptr;
+  if (model < 0 || model > 2 || S < 0 || N <= 0 || M <= 0 || M > 16 || !hyper || (S > 0 && (!x_dev || !Y_dev))) {
+    set_last_error("nmgp_plan_create: bad arguments (need 0<=model<=2, S>=0, N>=1, 1<=M<=16, non-null x/Y/hyper)");
+    return NMGP_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  nmgp_plan* pl = new (std::nothrow) nmgp_plan();
+  if (!pl) return NMGP_ENOMEM;
+  pl->model = model; pl->S = S; pl->N = N; pl->M = M;
+  pl->T = M * (M + 1) / 2;
+  pl->P = nmgp_n_params(model, N, M);
+  std::memcpy(pl->hyper, hyper, sizeof(pl->hyper));
+  pl->hc = make_hyper_const(model, hyper, prior_flag);
+  const bool svc = model == NMGP_NONSEPARABLE;
+  pl->nmat = svc ? 1 : M;
+  pl->n = svc ? N * M : N;
+  pl->nP = padded_dim(pl->n);
+  pl->Kt = pl->nP / kNB;
+  pl->nprior = model == NMGP_STATIONARY ? 0 : 2;
+  pl->nv1 = svc ? pl->T : 1;
+  int rc = 0;
+  do {
+    if (S == 0) { pl->chunk = 0; break; }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { set_last_error("cudaMemGetInfo failed (no CUDA device?)"); rc = NMGP_ECUDA; break; }
+    // persistent state
+    const size_t SN = (size_t)S * N;
+    if ((rc = dev_alloc(pl, &pl->x, SN))) break;
+    if ((rc = dev_alloc(pl, &pl->Y, SN * M))) break;
+    if (cudaMemcpyAsync(pl->x, x_dev, SN * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(pl->Y, Y_dev, SN * M * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_last_error("nmgp_plan_create: copying x/Y failed"); rc = NMGP_ECUDA; break;
+    }
+    if (pl->nprior) {
+      if ((rc = dev_alloc(pl, &pl->Wp0, SN * N))) break;
+      if ((rc = dev_alloc(pl, &pl->Wp1, SN * N))) break;
+      if ((rc = dev_alloc(pl, &pl->hld0, (size_t)S))) break;
+      if ((rc = dev_alloc(pl, &pl->hld1, (size_t)S))) break;
+    }
+    if ((rc = dev_alloc(pl, &pl->pars_d, (size_t)S * pl->P))) break;
+    if ((rc = dev_alloc(pl, &pl->grad_d, (size_t)S * pl->P))) break;
+    if ((rc = dev_alloc(pl, &pl->vals_d, (size_t)S * NMGP_NVALS))) break;
+    if ((rc = dev_alloc(pl, &pl->info_d, (size_t)S))) break;
+    // chunking
+    size_t limit = workspace_limit_bytes;
+    if (limit == 0) {
+      const size_t used = pl->dev_bytes;
+      const size_t avail = free_b > used ? free_b - used : 0;
+      limit = (size_t)(0.7 * (double)avail);
+      const size_t cap = 96ull << 30;
+      if (limit > cap) limit = cap;
+    }
+    const size_t per = per_subject_bytes(pl);
+    long chunk = (long)(limit / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > S) chunk = S;
+    const long maxc = 65535 / pl->nmat;
+    if (chunk > maxc) chunk = maxc;
+    pl->chunk = (int)chunk;
+    if ((rc = alloc_workspace(pl))) break;
+    if (pl->nprior) {
+      const double a0 = hyper[1], b0 = hyper[2], a1 = hyper[4], b1 = hyper[5];
+      if ((rc = factor_prior(pl, a0, b0, pl->Wp0, pl->hld0, st))) break;
+      if ((rc = factor_prior(pl, a1, b1, pl->Wp1, pl->hld1, st))) break;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+      set_last_error(std::string("nmgp_plan_create: ") + cudaGetErrorString(cudaGetLastError())); rc = NMGP_ECUDA; break;
+    }
+  } while (0);
+  if (rc != 0) { nmgp_plan_destroy(pl); return rc; }
+  *out = pl;
+  return 0;
+}
+
+int nmgp_logpost_grad(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, void* stream) {
+  if (!pl || (pl->S > 0 && (!pars || !vals || !info))) { set_last_error("nmgp_logpost_grad: null argument"); return NMGP_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  long launches = 0;
+  const int N = pl->N, M = pl->M, P = pl->P;
+  for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
+    const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
+    BlockBatch b = pl->bb;
+    b.batch = cs * pl->nmat;
+    const double* xs = pl->x + (size_t)s0 * N;
+    const double* Ys = pl->Y + (size_t)s0 * N * M;
+    const double* ps = pars + (size_t)s0 * P;
+    double* vs = vals + (size_t)s0 * NMGP_NVALS;
+    double* gs = grad ? grad + (size_t)s0 * P : nullptr;
+    int* is = info + s0;
+    if (pl->model == NMGP_NONSEPARABLE) {
+      NMGP_TRY(svc_forward(cs, N, M, xs, ps, P, pl->hc, pl->w, b, st, &launches));
+    } else {
+      NMGP_TRY(sep_forward(pl->model, cs, N, M, xs, Ys, ps, P, pl->hc, pl->w, b, st, &launches));
+    }
+    NMGP_TRY(engine_potrf(b, st, &launches));
+    NMGP_TRY(engine_potri(b, st, &launches));
+    if (pl->nprior) {
+      const double* W0 = pl->Wp0 + (size_t)s0 * N * N;
+      const double* W1 = pl->Wp1 + (size_t)s0 * N * N;
+      NMGP_TRY(launch_prior_solve(W0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
+      NMGP_TRY(launch_prior_solve(W1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, st, &launches));
+      if (grad) {
+        NMGP_TRY(launch_prior_solve(W0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, st, &launches));
+        NMGP_TRY(launch_prior_solve(W1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, st, &launches));
+      }
+    }
+    const double* h0 = pl->hld0 ? pl->hld0 + s0 : nullptr;
+    const double* h1 = pl->hld1 ? pl->hld1 + s0 : nullptr;
+    if (pl->model == NMGP_NONSEPARABLE) {
+      NMGP_TRY(svc_backward(cs, N, M, Ys, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
+    } else {
+      NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
+    }
+  }
+  pl->last_launches = launches;
+  return 0;
+}
+
+int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, double* grad_h, int* info_h,
+                           void* stream) {
+  if (!pl || (pl->S > 0 && (!pars_h || !vals_h))) { set_last_error("nmgp_logpost_grad_host: null argument"); return NMGP_EINVAL; }
+  if (pl->S == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t SP = (size_t)pl->S * pl->P;
+  NMGP_CUDA_TRY(cudaMemcpyAsync(pl->pars_d, pars_h, SP * sizeof(double), cudaMemcpyHostToDevice, st));
+  NMGP_TRY(nmgp_logpost_grad(pl, pl->pars_d, pl->vals_d, grad_h ? pl->grad_d : nullptr, pl->info_d, stream));
+  NMGP_CUDA_TRY(cudaMemcpyAsync(vals_h, pl->vals_d, (size_t)pl->S * NMGP_NVALS * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (grad_h) NMGP_CUDA_TRY(cudaMemcpyAsync(grad_h, pl->grad_d, SP * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (info_h) NMGP_CUDA_TRY(cudaMemcpyAsync(info_h, pl->info_d, (size_t)pl->S * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NMGP_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+long nmgp_plan_last_launches(const nmgp_plan* pl) { return pl ? pl->last_launches : 0; }
+size_t nmgp_plan_device_bytes(const nmgp_plan* pl) { return pl ? pl->dev_bytes : 0; }
+int nmgp_plan_chunk(const nmgp_plan* pl) { return pl ? pl->chunk : 0; }
+int nmgp_plan_block(const nmgp_plan* pl) { return pl ? pl->bb.NB : 0; }
+
+int nmgp_rbf_cov(const double* x1, int N1, const double* x2, int N2, double alpha, double beta, double* out, void* stream) {
+  if (!x1 || !out || N1 < 0 || (x2 && N2 < 0)) { set_last_error("nmgp_rbf_cov: bad arguments"); return NMGP_EINVAL; }
+  return launch_rbf_cov(x1, N1, x2, N2, alpha, beta, out, (cudaStream_t)stream);
+}
+
+int nmgp_gibbs_cov(const double* x1, const double* sigma1, const double* ell1, int N1, const double* x2,
+                   const double* sigma2, const double* ell2, int N2, double* out, void* stream) {
+  if (!x1 || !ell1 || !out || N1 < 0 || (x2 && (!ell2 || N2 < 0))) { set_last_error("nmgp_gibbs_cov: bad arguments"); return NMGP_EINVAL; }
+  return launch_gibbs_cov(x1, sigma1, ell1, N1, x2, sigma2, ell2, N2, out, (cudaStream_t)stream);
+}
+
+int nmgp_nonseparable_cov(const double* x, const double* pars, int batch, int N, int M, double* out, void* stream) {
+  if (!x || !pars || !out || batch < 0 || N <= 0 || M <= 0 || M > 16) { set_last_error("nmgp_nonseparable_cov: bad arguments"); return NMGP_EINVAL; }
+  return launch_nonseparable_cov_reference_order(x, pars, batch, N, M, out, (cudaStream_t)stream);
+}
+
+int nmgp_potrf_batched(double* A, int n, int batch, double* logdet, int* info, void* stream) {
+  return potrf_unit(A, n, batch, logdet, info, 0, (cudaStream_t)stream);
+}
+
+int nmgp_potrf_potri_batched(double* A, int n, int batch, double* logdet, int* info, void* stream) {
+  return potrf_unit(A, n, batch, logdet, info, 1, (cudaStream_t)stream);
+}
+
+}  // extern "C"

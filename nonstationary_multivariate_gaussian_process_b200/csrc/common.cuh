@@ -1,0 +1,65 @@
+// Shared helpers for the NMGP B200 kernels (sm_100a, FP64).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace nmgp {
+
+// -------------------------------------------------------------------------------- errors
+void set_last_error(const std::string& msg);  // api.cu
+
+#define NMGP_CUDA_TRY(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::nmgp::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +    \
+                             __FILE__ + ":" + std::to_string(__LINE__));                      \
+      return -2;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+#define NMGP_TRY(expr)            \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != 0) return _r;       \
+  } while (0)
+
+constexpr double kJitter = 1e-6;  // Utility/settings.py:3
+
+__host__ __device__ inline int tril_size(int M) { return M * (M + 1) / 2; }
+__host__ __device__ inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+// -------------------------------------------------------------------------------- FP64 tensor core
+// One DMMA.8x8x4 (mma.sync m8n8k4, f64): D(8x8) += A(8x4, row) * B(4x8, col).
+// Lane l holds  A[l>>2][l&3],  B[l&3][l>>2],  C[l>>2][2*(l&3) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024; result valid in every thread.
+__device__ __forceinline__ double block_sum(double v, double* scratch /* >= 33 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nw ? scratch[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+}  // namespace nmgp

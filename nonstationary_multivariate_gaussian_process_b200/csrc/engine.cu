@@ -1,0 +1,387 @@
+// Batched blocked FP64 Cholesky + inverse on B200, written as "tile tasks".
+//
+// Every O(n^3) step of potrf / trtri / lauum is a rank-NB update  C(i,j) = beta*C(i,j) + alpha * opA * opB
+// on NB x NB tiles of the padded matrix, one CTA per (tile, matrix), computed with DMMA.8x8x4
+// (mma.sync m8n8k4 f64 -- the FP64 tensor-core instruction of sm_100a; tcgen05 has no f64 kind).
+// A launch covers the tiles of ONE block step for ALL matrices of the batch, so a 10 000-subject
+// sweep costs the same number of launches as one subject.  The only non-GEMM work is the NB x NB
+// diagonal block (factor + inverse in shared memory).
+//
+// Replaces, for the whole batch at once: torch.inverse + torch.logdet (LU) at Utility/logpos.py:352-353,
+// torch.symeig at Utility/distributions.py:37,40 (block formulation) and the Cholesky
+// inside MultivariateNormal at logpos.py:274,279,358,365.
+#include "engine.cuh"
+
+namespace nmgp {
+
+namespace {
+
+constexpr int NB = kNB;          // 64
+constexpr int LDS = NB + 4;      // shared tile stride (doubles): == 4 mod 16 -> conflict-free DMMA fragment loads
+constexpr int TILE_THREADS = 128;
+constexpr size_t TILE_SMEM = 2ull * NB * LDS * sizeof(double);
+
+enum Mode : int {
+  POTRF_PANEL = 0,  // A(i,k)  <- A(i,k) * W_kk^T                      i > k
+  POTRF_SYRK = 1,   // A(i,j) -= A(i,k) * A(j,k)^T                     k < j <= i
+  TRTRI_ROW = 2,    // A(c,j)  <- -W_cc * A(c,j)                       j < c
+  TRTRI_UPD = 3,    // A(i,j) += A(i,c) * A(c,j)                       i > c, j < c
+  TRTRI_PANEL = 4,  // A(i,c)  <- A(i,c) * W_cc                        i > c
+  LAUUM_UPD = 5,    // A(i,j) += A(r,i)^T * A(r,j)                     j <= i < r
+  LAUUM_ROW = 6,    // A(r,j)  <- W_rr^T * A(r,j) (j<r);  A(r,r) <- W_rr^T W_rr
+};
+
+struct EngineArgs {
+  double* A;
+  double* Dinv;
+  long strideA, strideD;
+  int ld, Kt, batch, step;
+};
+
+__device__ __forceinline__ void tri_decode(int t, int& a, int& b) {
+  // t = a(a+1)/2 + b, 0 <= b <= a
+  a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long)a * (a + 1) / 2 > t) --a;
+  while ((long)(a + 1) * (a + 2) / 2 <= t) ++a;
+  b = t - a * (a + 1) / 2;
+}
+
+// straight copy of one NB x NB tile (row stride ld) into shared [NB][LDS]
+__device__ __forceinline__ void load_tile(double* __restrict__ S, const double* __restrict__ src, int ld) {
+  constexpr int V2 = NB / 2;  // double2 per row
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < NB * V2; idx += TILE_THREADS) {
+    const int r = idx / V2, c2 = idx % V2;
+    const double2 v = *reinterpret_cast<const double2*>(src + (long)r * ld + 2 * c2);
+    *reinterpret_cast<double2*>(S + r * LDS + 2 * c2) = v;
+  }
+}
+
+// acc(32x32 per warp) += opA(32 x NB) * opB(32 x NB)^T.   KM: S[row][k],  MM: S[k][row].
+template <bool A_KM, bool B_KM>
+__device__ __forceinline__ void warp_mma(const double* __restrict__ SA, const double* __restrict__ SB, int m0, int n0,
+                                         double (&acc)[4][4][2]) {
+  const int lane = threadIdx.x & 31;
+  const int lr = lane >> 2, lk = lane & 3;
+  const double* pa = A_KM ? SA + (m0 + lr) * LDS + lk : SA + lk * LDS + m0 + lr;
+  const double* pb = B_KM ? SB + (n0 + lr) * LDS + lk : SB + lk * LDS + n0 + lr;
+  constexpr int a_sub = A_KM ? 8 * LDS : 8;  // next 8-row subtile
+  constexpr int b_sub = B_KM ? 8 * LDS : 8;
+  constexpr int a_k = A_KM ? 4 : 4 * LDS;    // next k-step of 4
+  constexpr int b_k = B_KM ? 4 : 4 * LDS;
+#pragma unroll 4
+  for (int k = 0; k < NB; k += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = pa[i * a_sub];
+      b[i] = pb[i * b_sub];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    pa += a_k;
+    pb += b_k;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  double* SA = smem;
+  double* SB = smem + NB * LDS;
+
+  const int s = g.step;
+  const int t = blockIdx.x;
+  int i, j;          // output block coordinates
+  int ai, aj;        // block coordinates of operand A inside the matrix (or -1: Dinv[step])
+  int bi, bj;        // same for operand B
+  if (MODE == POTRF_PANEL) {
+    i = s + 1 + t; j = s; ai = i; aj = s; bi = -1; bj = -1;
+  } else if (MODE == POTRF_SYRK) {
+    int a, b; tri_decode(t, a, b);
+    i = s + 1 + a; j = s + 1 + b; ai = i; aj = s; bi = j; bj = s;
+  } else if (MODE == TRTRI_ROW) {
+    i = s; j = t; ai = -1; aj = -1; bi = s; bj = j;
+  } else if (MODE == TRTRI_UPD) {
+    const int a = t / s, b = t % s;
+    i = s + 1 + a; j = b; ai = i; aj = s; bi = s; bj = j;
+  } else if (MODE == TRTRI_PANEL) {
+    i = s + 1 + t; j = s; ai = i; aj = s; bi = -1; bj = -1;
+  } else if (MODE == LAUUM_UPD) {
+    int a, b; tri_decode(t, a, b);
+    i = a; j = b; ai = s; aj = i; bi = s; bj = j;
+  } else {  // LAUUM_ROW
+    i = s; j = t; ai = -1; aj = -1;
+    if (j < s) { bi = s; bj = j; } else { bi = -1; bj = -1; }
+  }
+  constexpr bool A_KM = (MODE == POTRF_PANEL || MODE == POTRF_SYRK || MODE == TRTRI_ROW || MODE == TRTRI_UPD ||
+                         MODE == TRTRI_PANEL);
+  constexpr bool B_KM = (MODE == POTRF_PANEL || MODE == POTRF_SYRK);
+  constexpr double alpha = (MODE == POTRF_SYRK || MODE == TRTRI_ROW) ? -1.0 : 1.0;
+  constexpr bool accumulate = (MODE == POTRF_SYRK || MODE == TRTRI_UPD || MODE == LAUUM_UPD);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
+
+  for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
+    double* Am = g.A + (long)mat * g.strideA;
+    const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * NB * NB;
+    const double* srcA = (ai < 0) ? Dm : Am + ((long)ai * NB) * g.ld + (long)aj * NB;
+    const double* srcB = (bi < 0) ? Dm : Am + ((long)bi * NB) * g.ld + (long)bj * NB;
+    load_tile(SA, srcA, ai < 0 ? NB : g.ld);
+    load_tile(SB, srcB, bi < 0 ? NB : g.ld);
+    __syncthreads();
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    warp_mma<A_KM, B_KM>(SA, SB, m0, n0, acc);
+
+    double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
+    const int r = lane >> 2, c = 2 * (lane & 3);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double2* p = reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * g.ld + n0 + 8 * b + c);
+        double2 v;
+        if (accumulate) {
+          v = *p;
+          v.x += alpha * acc[a][b][0];
+          v.y += alpha * acc[a][b][1];
+        } else {
+          v.x = alpha * acc[a][b][0];
+          v.y = alpha * acc[a][b][1];
+        }
+        *p = v;
+      }
+    __syncthreads();  // shared tiles are reused by the next matrix
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Diagonal block: factor A(k,k) = L L^T in shared memory, W = L^-1, accumulate log det, report failures.
+constexpr int DIAG_THREADS = 256;
+constexpr int LDD = NB + 1;
+constexpr size_t DIAG_SMEM = (2ull * NB * LDD + NB) * sizeof(double);
+
+__global__ void __launch_bounds__(DIAG_THREADS) diag_kernel(EngineArgs g, double* __restrict__ logdet,
+                                                            int* __restrict__ info) {
+  extern __shared__ __align__(16) double smem[];
+  double* L = smem;                 // [NB][LDD]
+  double* W = smem + NB * LDD;      // [NB][LDD]
+  double* rinv = W + NB * LDD;      // [NB]
+  __shared__ int fail;
+  const int k = g.step;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int mat = blockIdx.x; mat < g.batch; mat += gridDim.x) {
+    double* Akk = g.A + (long)mat * g.strideA + ((long)k * NB) * g.ld + (long)k * NB;
+    if (tid == 0) fail = 0;
+    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+      const int r = idx / NB, c = idx % NB;
+      L[r * LDD + c] = (c <= r) ? Akk[(long)r * g.ld + c] : 0.0;
+      W[r * LDD + c] = 0.0;
+    }
+    __syncthreads();
+    // right-looking unblocked Cholesky
+    for (int j = 0; j < NB; ++j) {
+      const double d = L[j * LDD + j];
+      if (!(d > 0.0) && tid == 0 && fail == 0) fail = k * NB + j + 1;
+      const double rj = sqrt(d);          // NaN on failure: propagates in-band
+      const double ri = 1.0 / rj;
+      __syncthreads();
+      for (int r = j + 1 + tid; r < NB; r += DIAG_THREADS) L[r * LDD + j] *= ri;
+      if (tid == 0) { L[j * LDD + j] = rj; rinv[j] = ri; }
+      __syncthreads();
+      for (int r = j + 1 + warp; r < NB; r += DIAG_THREADS / 32) {
+        const double lrj = L[r * LDD + j];
+        for (int c = j + 1 + lane; c <= r; c += 32) L[r * LDD + c] -= lrj * L[c * LDD + j];
+      }
+      __syncthreads();
+    }
+    // W = L^-1 by column-parallel forward substitution (column t owned by thread t)
+    if (tid < NB) {
+      const int t = tid;
+      W[t * LDD + t] = rinv[t];
+      for (int r = t + 1; r < NB; ++r) {
+        double sacc = 0.0;
+        for (int c = t; c < r; ++c) sacc += L[r * LDD + c] * W[c * LDD + t];
+        W[r * LDD + t] = -sacc * rinv[r];
+      }
+    }
+    __syncthreads();
+    double* Dk = g.Dinv + (long)mat * g.strideD + (long)k * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+      const int r = idx / NB, c = idx % NB;
+      if (c <= r) Akk[(long)r * g.ld + c] = L[r * LDD + c];
+      Dk[idx] = W[r * LDD + c];
+    }
+    if (tid == 0) {
+      double sld = 0.0;
+      for (int j = 0; j < NB; ++j) sld += log(L[j * LDD + j]);
+      sld *= 2.0;
+      logdet[mat] = (k == 0 ? 0.0 : logdet[mat]) + sld;
+      if (k == 0) info[mat] = fail;
+      else if (fail != 0 && info[mat] == 0) info[mat] = fail;
+    }
+    __syncthreads();
+  }
+}
+
+// Mirror the lower block triangle into the upper one: A(j,i) = A(i,j)^T for i > j.
+__global__ void __launch_bounds__(256) symmetrize_kernel(EngineArgs g) {
+  __shared__ double T[NB][NB + 1];
+  int a, b;
+  tri_decode(blockIdx.x, a, b);
+  const int i = a + 1, j = b;  // strictly lower blocks
+  for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
+    double* Am = g.A + (long)mat * g.strideA;
+    const double* src = Am + ((long)i * NB) * g.ld + (long)j * NB;
+    double* dst = Am + ((long)j * NB) * g.ld + (long)i * NB;
+    for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+      const int r = idx / NB, c = idx % NB;
+      T[r][c] = src[(long)r * g.ld + c];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+      const int r = idx / NB, c = idx % NB;
+      dst[(long)r * g.ld + c] = T[c][r];
+    }
+    __syncthreads();
+  }
+}
+
+// Backward-stable panel solve  X L_kk^T = A(i,k)  by substitution (one thread per row), used instead of the
+// multiply-by-inverse POTRF_PANEL when the matrix is ill-conditioned (GP-prior covariances, cond ~ 1e10):
+// multiplying by an explicit inverse of the diagonal block inflates the backward error by cond(L_kk).
+__global__ void __launch_bounds__(NB) trsm_panel_kernel(EngineArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem);
+  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem + NB * (NB + 1));
+  const int k = g.step;
+  const int i = k + 1 + blockIdx.x;
+  const int r = threadIdx.x;
+  for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
+    double* Am = g.A + (long)mat * g.strideA;
+    const double* Lkk = Am + ((long)k * NB) * g.ld + (long)k * NB;
+    double* X = Am + ((long)i * NB) * g.ld + (long)k * NB;
+    for (int idx = threadIdx.x; idx < NB * NB; idx += NB) {
+      const int rr = idx / NB, cc = idx % NB;
+      Ls[rr][cc] = Lkk[(long)rr * g.ld + cc];
+      Xs[rr][cc] = X[(long)rr * g.ld + cc];
+    }
+    __syncthreads();
+    for (int c = 0; c < NB; ++c) {
+      double sacc = Xs[r][c];
+      for (int c2 = 0; c2 < c; ++c2) sacc -= Xs[r][c2] * Ls[c][c2];
+      Xs[r][c] = sacc / Ls[c][c];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NB * NB; idx += NB) {
+      const int rr = idx / NB, cc = idx % NB;
+      X[(long)rr * g.ld + cc] = Xs[rr][cc];
+    }
+    __syncthreads();
+  }
+}
+
+template <int MODE>
+int launch_tiles(const EngineArgs& g, int ntiles, cudaStream_t st, long* launches) {
+  if (ntiles <= 0 || g.batch <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    NMGP_CUDA_TRY(cudaFuncSetAttribute(tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    configured = true;
+  }
+  dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
+  tile_kernel<MODE><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+EngineArgs make_args(const BlockBatch& b) {
+  EngineArgs g;
+  g.A = b.A; g.Dinv = b.Dinv; g.strideA = b.strideA(); g.strideD = b.strideD();
+  g.ld = b.nP; g.Kt = b.Kt; g.batch = b.batch; g.step = 0;
+  return g;
+}
+
+}  // namespace
+
+int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
+  if (b.batch <= 0) return 0;
+  if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine_potrf: bad block layout"); return -1; }
+  static bool configured = false;
+  if (!configured) {
+    NMGP_CUDA_TRY(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+    configured = true;
+  }
+  EngineArgs g = make_args(b);
+  const int dgrid = b.batch < 148 * 8 ? b.batch : 148 * 8;
+  for (int k = 0; k < b.Kt; ++k) {
+    g.step = k;
+    diag_kernel<<<dgrid, DIAG_THREADS, DIAG_SMEM, st>>>(g, b.logdet, b.info);
+    NMGP_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    const int r = b.Kt - k - 1;
+    if (stable_panel) {
+      if (r > 0) {
+        dim3 pg(r, b.batch < 65535 ? b.batch : 65535);
+        constexpr size_t kTrsmSmem = 2ull * NB * (NB + 1) * sizeof(double);
+        static bool trsm_configured = false;
+        if (!trsm_configured) {
+          NMGP_CUDA_TRY(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+          trsm_configured = true;
+        }
+        trsm_panel_kernel<<<pg, NB, kTrsmSmem, st>>>(g);
+        NMGP_CUDA_TRY(cudaGetLastError());
+        if (launches) ++*launches;
+      }
+    } else {
+      NMGP_TRY(launch_tiles<POTRF_PANEL>(g, r, st, launches));
+    }
+    NMGP_TRY(launch_tiles<POTRF_SYRK>(g, r * (r + 1) / 2, st, launches));
+  }
+  return 0;
+}
+
+int engine_trtri(const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (b.batch <= 0) return 0;
+  EngineArgs g = make_args(b);
+  // W = L^-1 (strictly-lower blocks in A, diagonal blocks stay in Dinv)
+  for (int c = 0; c < b.Kt; ++c) {
+    g.step = c;
+    const int below = b.Kt - c - 1;
+    NMGP_TRY(launch_tiles<TRTRI_ROW>(g, c, st, launches));
+    NMGP_TRY(launch_tiles<TRTRI_UPD>(g, below * c, st, launches));
+    NMGP_TRY(launch_tiles<TRTRI_PANEL>(g, below, st, launches));
+  }
+  return 0;
+}
+
+int engine_potri(const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (b.batch <= 0) return 0;
+  NMGP_TRY(engine_trtri(b, st, launches));
+  EngineArgs g = make_args(b);
+  // A = W^T W (lower block triangle, diagonal blocks complete)
+  for (int r = 0; r < b.Kt; ++r) {
+    g.step = r;
+    NMGP_TRY(launch_tiles<LAUUM_UPD>(g, r * (r + 1) / 2, st, launches));
+    NMGP_TRY(launch_tiles<LAUUM_ROW>(g, r + 1, st, launches));
+  }
+  if (b.Kt > 1) {
+    dim3 grid(b.Kt * (b.Kt - 1) / 2, b.batch < 65535 ? b.batch : 65535);
+    symmetrize_kernel<<<grid, 256, 0, st>>>(g);
+    NMGP_CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+  }
+  return 0;
+}
+
+}  // namespace nmgp

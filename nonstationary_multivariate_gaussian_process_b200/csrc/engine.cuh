@@ -1,0 +1,39 @@
+// Batched blocked FP64 Cholesky / inverse engine (tile-task kernels on DMMA).  See engine.cu.
+#pragma once
+#include "common.cuh"
+
+namespace nmgp {
+
+// A batch of symmetric matrices in the engine's padded block layout:
+//   A      [batch][nP][nP] row-major, nP = Kt*NB >= n; rows/cols >= n hold the identity, so the padded
+//          matrix is diag(Sigma, I): its factor is diag(L, I), its inverse diag(Sigma^-1, I), and no kernel
+//          needs edge predication.
+//   Dinv   [batch][Kt][NB*NB]  inverses of the diagonal blocks of L (full tiles, zero upper), written by potrf.
+struct BlockBatch {
+  double* A = nullptr;
+  double* Dinv = nullptr;
+  double* logdet = nullptr;  // [batch]
+  int* info = nullptr;       // [batch]
+  int n = 0;                 // logical dimension
+  int nP = 0;                // padded dimension (multiple of NB)
+  int Kt = 0;                // blocks per side
+  int NB = 64;
+  int batch = 0;
+  long strideA() const { return (long)nP * nP; }
+  long strideD() const { return (long)Kt * NB * NB; }
+};
+
+constexpr int kNB = 64;
+
+inline int padded_dim(int n, int NB = kNB) { return (int)round_up(n, NB); }
+
+// In place: lower triangle of every A <- L;  logdet <- log det;  info <- 0 or failing pivot (1-based).
+// stable_panel: solve the panel by substitution instead of multiplying by the inverse of the diagonal block
+// (slower; for matrices with cond >> 1e6 such as the GP-prior covariances).
+int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel = false);
+// After potrf: strictly-lower blocks of A <- blocks of W = L^-1 (its diagonal blocks are already in Dinv).
+int engine_trtri(const BlockBatch& b, cudaStream_t st, long* launches);
+// After potrf: A <- inverse (both triangles filled).  trtri + lauum + symmetrize.
+int engine_potri(const BlockBatch& b, cudaStream_t st, long* launches);
+
+}  // namespace nmgp

@@ -1,0 +1,869 @@
+// Model kernels of the NMGP hot path (FP64, sm_100a): everything between the flat parameter vector and the
+// factorisation engine, and between the inverse and the gradient.  All kernels are batched over subjects.
+//
+// Internal ordering of the nonseparable covariance is TIME-major (row (i,m) -> i*M+m) -- a symmetric permutation
+// of the reference's output-major ordering (Utility/logpos.py:347-348) that leaves log det, the quadratic form
+// and (after un-permuting) the gradient unchanged, and makes the M x M cross-output blocks contiguous.
+#include "models.cuh"
+
+#include <cmath>
+
+namespace nmgp {
+
+namespace {
+
+constexpr int NB = kNB;
+
+// squared distance exactly as Utility/kernels.py:13-20 forms it: (x_i^2 + x_j^2) - 2.0*(x_i*x_j), no FMA contraction
+__device__ __forceinline__ double ref_sqdist(double xi, double xj) {
+  const double s = __dadd_rn(__dmul_rn(xi, xi), __dmul_rn(xj, xj));
+  return __dsub_rn(s, __dmul_rn(2.0, __dmul_rn(xi, xj)));
+}
+
+// Gibbs kernel value without jitter and its log-derivative factor w.r.t. tilde_l_i
+__device__ __forceinline__ void gibbs_pair(double xi, double xj, double li, double lj, double sij, double& k0,
+                                           double& cfac) {
+  const double d = ref_sqdist(xi, xj);
+  const double li2 = __dmul_rn(li, li);
+  const double A = __dadd_rn(li2, __dmul_rn(lj, lj));
+  const double Bm = __dmul_rn(li, lj);
+  const double root = sqrt(__ddiv_rn(__dmul_rn(2.0, Bm), A));
+  const double e = exp(__ddiv_rn(-d, A));
+  k0 = __dmul_rn(__dmul_rn(sij, root), e);            // (C*sqrt(2B/A))*exp(-d/A), kernels.py:72
+  const double q = li2 / A;
+  cfac = 0.5 - q + 2.0 * d * q / A;
+}
+
+// ------------------------------------------------------------------------------------------ unit kernels
+__global__ void rbf_cov_kernel(const double* __restrict__ x1, int N1, const double* __restrict__ x2, int N2,
+                               double alpha2, double beta, int self, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= N2 || i >= N1) return;
+  const double a = x1[i] / beta, b = x2[j] / beta;                 // kernels.py:38-39
+  const double d = ref_sqdist(a, b);
+  double v = __dmul_rn(exp(__dmul_rn(-0.5, d)), alpha2);            // exp(-0.5*dist)*alpha**2, kernels.py:42
+  if (self && i == j) v = __dadd_rn(kJitter, v);                    // jitter identity is the accumulator, :35
+  out[(long)i * N2 + j] = v;
+}
+
+__global__ void gibbs_cov_kernel(const double* __restrict__ x1, const double* __restrict__ s1,
+                                 const double* __restrict__ l1, int N1, const double* __restrict__ x2,
+                                 const double* __restrict__ s2, const double* __restrict__ l2, int N2, int self,
+                                 double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= N2 || i >= N1) return;
+  const double sij = (s1 ? s1[i] : 1.0) * (s2 ? s2[j] : 1.0);
+  double k0, cf;
+  gibbs_pair(x1[i], x2[j], l1[i], l2[j], sij, k0, cf);
+  if (self && i == j) k0 = __dadd_rn(kJitter, k0);
+  out[(long)i * N2 + j] = k0;
+}
+
+// prior covariance into the padded block layout (full symmetric, identity padding)
+__global__ void prior_cov_blocks_kernel(const double* __restrict__ x, int N, double alpha2, double beta, double* A,
+                                        long strideA, int ld) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  const int c = blockIdx.z;
+  if (q >= ld) return;
+  double v;
+  if (p < N && q < N) {
+    const double* xs = x + (long)c * N;
+    const double a = xs[p] / beta, b = xs[q] / beta;
+    v = __dmul_rn(exp(__dmul_rn(-0.5, ref_sqdist(a, b))), alpha2);
+    if (p == q) v = __dadd_rn(kJitter, v);
+  } else {
+    v = (p == q) ? 1.0 : 0.0;
+  }
+  A[(long)c * strideA + (long)p * ld + q] = v;
+}
+
+// compact lower Cholesky factor [c][N][N] (zero strict upper) and half log-determinant out of the padded layout
+__global__ void extract_factor_kernel(const double* __restrict__ A, long strideA, int ld, int N,
+                                      const double* __restrict__ logdet, double* __restrict__ Lp,
+                                      double* __restrict__ hld) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  const int c = blockIdx.z;
+  if (p == 0 && q == 0) hld[c] = 0.5 * logdet[c];
+  if (q >= N) return;
+  Lp[((long)c * N + p) * N + q] = (q <= p) ? A[(long)c * strideA + (long)p * ld + q] : 0.0;
+}
+
+// Triangular solves with the cached prior factor, nv right-hand sides per subject, by blocked substitution
+// (the arithmetic MultivariateNormal.log_prob and its autograd backward do: logpos.py:274,279,358,365):
+//   TRANS=0:  L   X = rhs   (forward)        TRANS=1:  L^T X = rhs   (backward)
+// One CTA per (subject, chunk of 32 right-hand sides); 32-row blocks: GEMM-like update from the already solved
+// part, then a 32x32 substitution with one thread per right-hand side.
+template <int TRANS>
+__global__ void __launch_bounds__(256) prior_solve_kernel(const double* __restrict__ Lp, const double* __restrict__ rhs,
+                                                          double* out, int N, int nv) {
+  constexpr int BS = 32;
+  __shared__ double Ld[BS][BS + 1];
+  __shared__ double Zb[BS][BS + 1];
+  const int c = blockIdx.x;
+  const int v0 = blockIdx.y * BS;
+  const int vc = min(BS, nv - v0);
+  const double* L = Lp + (long)c * N * N;
+  const double* R = rhs + (long)c * N * nv;
+  double* X = out + (long)c * N * nv;
+  const int nblk = (N + BS - 1) / BS;
+  for (int bk = 0; bk < nblk; ++bk) {
+    const int k0 = TRANS ? (nblk - 1 - bk) * BS : bk * BS;
+    const int rows = min(BS, N - k0);
+    for (int idx = threadIdx.x; idx < rows * vc; idx += 256) {
+      const int r = idx / vc, v = idx % vc;
+      double acc = R[(long)(k0 + r) * nv + v0 + v];
+      if (TRANS) {
+        for (int j = k0 + rows; j < N; ++j) acc -= L[(long)j * N + k0 + r] * X[(long)j * nv + v0 + v];
+      } else {
+        const double* lrow = L + (long)(k0 + r) * N;
+        for (int j = 0; j < k0; ++j) acc -= lrow[j] * X[(long)j * nv + v0 + v];
+      }
+      Zb[r][v] = acc;
+    }
+    for (int idx = threadIdx.x; idx < rows * rows; idx += 256) {
+      const int r = idx / rows, cc = idx % rows;
+      Ld[r][cc] = L[(long)(k0 + r) * N + k0 + cc];
+    }
+    __syncthreads();
+    if (threadIdx.x < vc) {
+      const int v = threadIdx.x;
+      if (TRANS) {
+        for (int r = rows - 1; r >= 0; --r) {
+          double sacc = Zb[r][v];
+          for (int cc = r + 1; cc < rows; ++cc) sacc -= Ld[cc][r] * Zb[cc][v];
+          Zb[r][v] = sacc / Ld[r][r];
+        }
+      } else {
+        for (int r = 0; r < rows; ++r) {
+          double sacc = Zb[r][v];
+          for (int cc = 0; cc < r; ++cc) sacc -= Ld[r][cc] * Zb[cc][v];
+          Zb[r][v] = sacc / Ld[r][r];
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows * vc; idx += 256) {
+      const int r = idx / vc, v = idx % vc;
+      X[(long)(k0 + r) * nv + v0 + v] = Zb[r][v];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ shared by models
+// Gibbs kernel matrix Kx (with jitter) and CK = c_ij * K0_ij for every subject of the chunk.
+__global__ void kx_kernel(const double* __restrict__ x, const double* __restrict__ ell, const double* __restrict__ sig,
+                          int N, double* __restrict__ Kx, double* __restrict__ CK) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  const int c = blockIdx.z;
+  if (j >= N) return;
+  const double* xs = x + (long)c * N;
+  const double* ls = ell + (long)c * N;
+  const double sij = sig ? sig[(long)c * N + i] * sig[(long)c * N + j] : 1.0;
+  double k0, cf;
+  gibbs_pair(xs[i], xs[j], ls[i], ls[j], sij, k0, cf);
+  const long o = ((long)c * N + i) * N + j;
+  CK[o] = cf * k0;
+  Kx[o] = (i == j) ? __dadd_rn(kJitter, k0) : k0;
+}
+
+// alpha[b][p] = sum_q A[b][p][q] y[b][q]   (full symmetric A in the padded layout; one warp per row)
+__global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ A, long strideA, int ld, int n,
+                                                   const double* __restrict__ y, double* __restrict__ alpha) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const double* row = A + (long)b * strideA + (long)p * ld;
+  const double* yb = y + (long)b * n;
+  double s = 0.0;
+  for (int q = lane; q < n; q += 32) s += row[q] * yb[q];
+  s = warp_sum(s);
+  if (lane == 0) alpha[(long)b * n + p] = s;
+}
+
+// ------------------------------------------------------------------------------------------ nonseparable
+// pars -> ell, Lst rows, sigma2, prior residuals    (Utility/utils.py:10-74, logpos.py:337-343)
+__global__ void svc_prep_kernel(const double* __restrict__ pars, int P, int N, int M, int MT, double mu0, double mu1,
+                                double* __restrict__ ell, double* __restrict__ Lst, double* __restrict__ s2,
+                                double* __restrict__ R0, double* __restrict__ R1) {
+  const int c = blockIdx.x;
+  const int T = tril_size(M);
+  const double* p = pars + (long)c * P;
+  if (threadIdx.x == 0) s2[c] = exp(p[P - 1]);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double tl = p[i];
+    ell[(long)c * N + i] = exp(tl);
+    R0[(long)c * N + i] = tl - mu0;
+  }
+  for (int idx = threadIdx.x; idx < N * M * MT; idx += blockDim.x) {
+    const int k = idx % MT, m = (idx / MT) % M, i = idx / (MT * M);
+    double v = 0.0;
+    if (k <= m) {
+      const double u = p[N + (long)i * T + m * (m + 1) / 2 + k];
+      v = (k == m) ? exp(u) : u;
+    }
+    Lst[((long)c * N * M + (long)i * M + m) * MT + k] = v;
+  }
+  for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) R1[(long)c * N * T + idx] = p[N + idx] - mu1;
+}
+
+// Sigma = Kx[i,j] * L_i L_j^T + sigma2 I, time-major, lower block triangle of the padded layout
+__global__ void __launch_bounds__(256) svc_build_kernel(const double* __restrict__ Kx, const double* __restrict__ Lst,
+                                                        const double* __restrict__ s2v, int N, int M, int MT,
+                                                        double* A, long strideA, int ld) {
+  __shared__ double Lr[NB * 16];
+  __shared__ double Lc[NB * 16];
+  int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((long)ti * (ti + 1) / 2 > (long)blockIdx.x) --ti;
+  while ((long)(ti + 1) * (ti + 2) / 2 <= (long)blockIdx.x) ++ti;
+  const int tj = blockIdx.x - ti * (ti + 1) / 2;
+  const int c = blockIdx.y;
+  const int n = N * M;
+  const int p0 = ti * NB, q0 = tj * NB;
+  const double* Ls = Lst + (long)c * n * MT;
+  for (int idx = threadIdx.x; idx < NB * MT; idx += 256) {
+    const int r = idx / MT, k = idx % MT;
+    Lr[idx] = (p0 + r < n) ? Ls[(long)(p0 + r) * MT + k] : 0.0;
+    Lc[idx] = (q0 + r < n) ? Ls[(long)(q0 + r) * MT + k] : 0.0;
+  }
+  __syncthreads();
+  const double s2 = s2v[c];
+  const double* Kc = Kx + (long)c * N * N;
+  double* Ac = A + (long)c * strideA;
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+    const int r = idx / NB, cc = idx % NB;
+    const int p = p0 + r, q = q0 + cc;
+    double v;
+    if (p < n && q < n) {
+      const int i = p / M, j = q / M;
+      double dot = 0.0;
+      for (int k = 0; k < M; ++k) dot += Lr[r * MT + k] * Lc[cc * MT + k];
+      v = Kc[(long)i * N + j] * dot;
+      if (p == q) v += s2;
+    } else {
+      v = (p == q) ? 1.0 : 0.0;
+    }
+    Ac[(long)p * ld + q] = v;
+  }
+}
+
+// Reference-ordered dense covariance for the parity entry point (output-major, full symmetric, no padding).
+__global__ void svc_cov_reference_order_kernel(const double* __restrict__ x, const double* __restrict__ pars, int N,
+                                               int M, double* __restrict__ out) {
+  const int n = N * M, T = tril_size(M), P = N + N * T + 1;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  const int c = blockIdx.z;
+  if (q >= n) return;
+  const double* pr = pars + (long)c * P;
+  const double* xs = x + (long)c * N;
+  const int m = p / N, i = p % N, m2 = q / N, j = q % N;
+  double k0, cf;
+  gibbs_pair(xs[i], xs[j], exp(pr[i]), exp(pr[j]), 1.0, k0, cf);
+  if (i == j) k0 = __dadd_rn(kJitter, k0);
+  double dot = 0.0;
+  const int kmax = min(m, m2);
+  for (int k = 0; k <= kmax; ++k) {
+    double a = pr[N + (long)i * T + m * (m + 1) / 2 + k];
+    double b = pr[N + (long)j * T + m2 * (m2 + 1) / 2 + k];
+    if (k == m) a = exp(a);
+    if (k == m2) b = exp(b);
+    dot += a * b;
+  }
+  double v = k0 * dot;
+  if (p == q) v += exp(pr[P - 1]);
+  out[((long)c * n + p) * n + q] = v;
+}
+
+// One pass over Sigma^-1: for every row p=(i,m)
+//   Wout[p][k] = sum_q Kx[i,j] G[p,q] Lst[q][k],   Vout[p][k] = sum_q CK[i,j] G[p,q] Lst[q][k],
+// with G = -0.5 Sigma^-1 + 0.5 alpha alpha^T (never materialised).  One warp per row, lanes stride the columns.
+template <int MT>
+__global__ void __launch_bounds__(256) svc_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N,
+                                                           int M, const double* __restrict__ alpha,
+                                                           const double* __restrict__ Kx, const double* __restrict__ CK,
+                                                           const double* __restrict__ Lst, double* __restrict__ Wout,
+                                                           double* __restrict__ Vout) {
+  const int c = blockIdx.y;
+  const int n = N * M;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const int i = p / M;
+  const double* row = A + (long)c * strideA + (long)p * ld;
+  const double* al = alpha + (long)c * n;
+  const double* kr = Kx + ((long)c * N + i) * N;
+  const double* cr = CK + ((long)c * N + i) * N;
+  const double* Ls = Lst + (long)c * n * MT;
+  const double ap = al[p];
+  const float invM = 1.0f / (float)M;
+  double w[MT], v[MT];
+#pragma unroll
+  for (int k = 0; k < MT; ++k) w[k] = v[k] = 0.0;
+  for (int q = lane; q < n; q += 32) {
+    int j = (int)(((float)q + 0.5f) * invM);
+    const double g = -0.5 * row[q] + 0.5 * ap * al[q];
+    const double gk = g * kr[j], gc = g * cr[j];
+    const double* lq = Ls + (long)q * MT;
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+      const double l = lq[k];
+      w[k] += gk * l;
+      v[k] += gc * l;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MT; ++k) {
+    w[k] = warp_sum(w[k]);
+    v[k] = warp_sum(v[k]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+      Wout[((long)c * n + p) * MT + k] = w[k];
+      Vout[((long)c * n + p) * MT + k] = v[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) svc_finish_kernel(
+    int N, int M, int MT, int P, const double* __restrict__ pars, const double* __restrict__ Y, HyperConst h,
+    const double* __restrict__ A, long strideA, int ld, const double* __restrict__ logdet,
+    const int* __restrict__ info_in, const double* __restrict__ alpha, const double* __restrict__ s2v,
+    const double* __restrict__ Lst, const double* __restrict__ Wout, const double* __restrict__ Vout,
+    const double* __restrict__ Z0, const double* __restrict__ Z1, const double* __restrict__ G0,
+    const double* __restrict__ G1, const double* __restrict__ hld0, const double* __restrict__ hld1,
+    double* __restrict__ vals, double* __restrict__ grad, int* __restrict__ info) {
+  __shared__ double scratch[40];
+  const int c = blockIdx.x;
+  const int n = N * M, T = tril_size(M);
+  const double* p = pars + (long)c * P;
+  const double* y = Y + (long)c * n;  // time-major y == Y flattened row-major (logpos.py:336, permuted)
+  const double* al = alpha + (long)c * n;
+  const double* Ac = A + (long)c * strideA;
+  double q = 0.0, tr = 0.0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const double a = al[r];
+    q += y[r] * a;
+    tr += -0.5 * Ac[(long)r * ld + r] + 0.5 * a * a;
+  }
+  const double quad = block_sum(q, scratch);
+  const double trG = block_sum(tr, scratch);
+  double z0 = 0.0, z1 = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { const double z = Z0[(long)c * N + i]; z0 += z * z; }
+  for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) { const double z = Z1[(long)c * N * T + idx]; z1 += z * z; }
+  const double q0 = block_sum(z0, scratch);
+  const double q1 = block_sum(z1, scratch);
+
+  const double s2 = s2v[c];
+  const double ts2 = p[P - 1];
+  const double log2pi = 1.8378770664093453;
+  const double loglik = -0.5 * logdet[c] - 0.5 * quad;                 // distributions.py:22
+  const double lp_l = -0.5 * (N * log2pi + q0) - hld0[c];              // MVN.log_prob, logpos.py:358
+  const double lp_L = -0.5 * ((double)T * N * log2pi + q1) - (double)T * hld1[c];   // logpos.py:365
+  const double lp_s = (-h.ig_a - 1.0) * log(s2) - h.ig_b / s2 + h.ig_alogb - h.ig_lgamma;          // distributions.py:134
+  double res = loglik;
+  if (h.prior) res += lp_l + lp_L + lp_s + ts2;                        // logpos.py:359-376
+  const double pf = h.prior ? 1.0 : 0.0;
+  if (threadIdx.x == 0) {
+    double* v = vals + (long)c * 6;
+    v[0] = -res; v[1] = loglik; v[2] = lp_l; v[3] = lp_L; v[4] = lp_s; v[5] = 0.0;
+    info[c] = info_in[c];
+  }
+  if (grad == nullptr) return;
+  double* g = grad + (long)c * P;
+  const double* Ls = Lst + (long)c * n * MT;
+  const double* Wc = Wout + (long)c * n * MT;
+  const double* Vc = Vout + (long)c * n * MT;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double s = 0.0;
+    for (int m = 0; m < M; ++m)
+      for (int k = 0; k <= m; ++k) s += Ls[((long)i * M + m) * MT + k] * Vc[((long)i * M + m) * MT + k];
+    g[i] = -(2.0 * s - pf * G0[(long)c * N + i]);
+  }
+  for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) {
+    const int i = idx / T, t = idx % T;
+    int m = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (m * (m + 1) / 2 > t) --m;
+    while ((m + 1) * (m + 2) / 2 <= t) ++m;
+    const int k = t - m * (m + 1) / 2;
+    double d = 2.0 * Wc[((long)i * M + m) * MT + k];
+    if (k == m) d *= Ls[((long)i * M + m) * MT + m];                   // d exp(u)/du on the diagonal slots
+    g[N + idx] = -(d - pf * G1[(long)c * N * T + idx]);
+  }
+  if (threadIdx.x == 0) g[P - 1] = -(s2 * trG + pf * ((-h.ig_a - 1.0) + h.ig_b / s2 + 1.0));
+}
+
+// ------------------------------------------------------------------------------------------ separable / stationary
+// Cyclic Jacobi eigen-decomposition of a symmetric M x M matrix held in shared memory, by one warp.
+// On exit Bm holds the eigenvalues on its diagonal and V the eigenvectors in its columns.
+__device__ void jacobi_eig_warp(double* Bm, double* V, int M, int lds) {
+  const int lane = threadIdx.x & 31;
+  for (int idx = lane; idx < M * M; idx += 32) V[(idx / M) * lds + idx % M] = (idx / M == idx % M) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int idx = lane; idx < M * M; idx += 32) {
+      const int r = idx / M, cc = idx % M;
+      const double v = Bm[r * lds + cc];
+      if (r != cc) off += v * v; else dg += v * v;
+    }
+    off = warp_sum(off);
+    dg = warp_sum(dg);
+    if (off <= 1e-40 * dg || off == 0.0) break;
+    for (int p = 0; p < M - 1; ++p)
+      for (int q = p + 1; q < M; ++q) {
+        const double apq = Bm[p * lds + q];
+        if (apq != 0.0) {  // uniform across the warp
+          const double app = Bm[p * lds + p], aqq = Bm[q * lds + q];
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+          __syncwarp();
+          // columns p,q of B and V
+          for (int r = lane; r < M; r += 32) {
+            const double bp = Bm[r * lds + p], bq = Bm[r * lds + q];
+            Bm[r * lds + p] = cs * bp - sn * bq;
+            Bm[r * lds + q] = sn * bp + cs * bq;
+            const double vp = V[r * lds + p], vq = V[r * lds + q];
+            V[r * lds + p] = cs * vp - sn * vq;
+            V[r * lds + q] = sn * vp + cs * vq;
+          }
+          __syncwarp();
+          // rows p,q of B
+          for (int r = lane; r < M; r += 32) {
+            const double bp = Bm[p * lds + r], bq = Bm[q * lds + r];
+            Bm[p * lds + r] = cs * bp - sn * bq;
+            Bm[q * lds + r] = sn * bp + cs * bq;
+          }
+          __syncwarp();
+        }
+      }
+  }
+  __syncwarp();
+}
+
+// pars -> ell, sigma, sigma2, L, eig(B), rotated observations, prior residuals   (logpos.py:249-257, 423-429)
+__global__ void __launch_bounds__(256) sep_prep_kernel(int model, const double* __restrict__ pars, int P, int N, int M,
+                                                       const double* __restrict__ Y, double mu0, double mu1,
+                                                       double* __restrict__ ell, double* __restrict__ sig,
+                                                       double* __restrict__ s2, double* __restrict__ Lmat,
+                                                       double* __restrict__ lam, double* __restrict__ Vec,
+                                                       double* __restrict__ yv, double* __restrict__ R0,
+                                                       double* __restrict__ R1) {
+  __shared__ double Ls[16 * 17], Bs[16 * 17], Vs[16 * 17];
+  const int c = blockIdx.x;
+  const int T = tril_size(M);
+  const double* p = pars + (long)c * P;
+  const bool stat = (model == 0);
+  const double* uL = stat ? p + 2 : p + 2 * N;
+  if (threadIdx.x == 0) s2[c] = exp(p[P - 1]);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double tl = stat ? p[0] : p[i];
+    const double tsg = stat ? p[1] : p[N + i];
+    ell[(long)c * N + i] = exp(tl);
+    sig[(long)c * N + i] = exp(tsg);
+    if (!stat) {
+      R0[(long)c * N + i] = tl - mu0;
+      R1[(long)c * N + i] = tsg - mu1;
+    }
+  }
+  for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
+    const int m = idx / M, k = idx % M;
+    double v = 0.0;
+    if (k <= m) {
+      const double u = uL[m * (m + 1) / 2 + k];
+      v = (k == m) ? exp(u) : u;
+    }
+    Ls[m * 17 + k] = v;
+    Lmat[(long)c * M * M + idx] = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
+    const int a = idx / M, b = idx % M;
+    double s = 0.0;
+    for (int k = 0; k < M; ++k) s += Ls[a * 17 + k] * Ls[b * 17 + k];
+    Bs[a * 17 + b] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) jacobi_eig_warp(Bs, Vs, M, 17);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) Vec[(long)c * M * M + idx] = Vs[(idx / M) * 17 + idx % M];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) lam[(long)c * M + m] = Bs[m * 17 + m];
+  // rotated observations  yv[m][i] = sum_m' Y[i][m'] V[m'][m]
+  for (int idx = threadIdx.x; idx < M * N; idx += blockDim.x) {
+    const int m = idx / N, i = idx % N;
+    double s = 0.0;
+    for (int k = 0; k < M; ++k) s += Y[((long)c * N + i) * M + k] * Vs[k * 17 + m];
+    yv[((long)c * M + m) * N + i] = s;
+  }
+}
+
+// S_m = lam_m Kx + sigma2 I in the padded layout (full symmetric lower+upper of the lower block triangle)
+__global__ void sep_build_kernel(const double* __restrict__ Kx, const double* __restrict__ lam,
+                                 const double* __restrict__ s2v, int N, int M, double* A, long strideA, int ld) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  const int b = blockIdx.z;  // c*M + m
+  if (q >= ld) return;
+  const int c = b / M;
+  double v;
+  if (p < N && q < N) {
+    v = lam[b] * Kx[((long)c * N + p) * N + q];
+    if (p == q) v += s2v[c];
+  } else {
+    v = (p == q) ? 1.0 : 0.0;
+  }
+  A[(long)b * strideA + (long)p * ld + q] = v;
+}
+
+// One pass over the M inverses S_m^-1 of a subject, one warp per row i:
+//   gl[i] = sum_j GK_ij CK_ij,  gs[i] = sum_j GK_ij K0_ij,  rowSK[i][m] = sum_j S_m^-1[i,j] Kx[i,j],
+//   KA[i][m] = sum_j Kx[i,j] alpha_m[j],     GK = sum_m lam_m (-0.5 S_m^-1 + 0.5 alpha_m alpha_m^T)
+__global__ void __launch_bounds__(256) sep_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N,
+                                                           int M, const double* __restrict__ alpha,
+                                                           const double* __restrict__ lam,
+                                                           const double* __restrict__ Kx, const double* __restrict__ CK,
+                                                           const double* __restrict__ sig,
+                                                           double* __restrict__ gl, double* __restrict__ gs,
+                                                           double* __restrict__ rowSK, double* __restrict__ KA) {
+  const int c = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const double* kr = Kx + ((long)c * N + i) * N;
+  const double* cr = CK + ((long)c * N + i) * N;
+  const double sii = sig[(long)c * N + i] * sig[(long)c * N + i];
+  double agl = 0.0, ags = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double* row = A + ((long)c * M + m) * strideA + (long)i * ld;
+    const double* al = alpha + ((long)c * M + m) * N;
+    const double lm = lam[(long)c * M + m];
+    const double ai = al[i];
+    double sk = 0.0, ka = 0.0;
+    for (int j = lane; j < N; j += 32) {
+      const double sinv = row[j];
+      const double kx = kr[j];
+      const double k0 = (j == i) ? sii : kx;            // K0_ii = sigma_i^2 exactly (2B/A == 1, exp(0) == 1)
+      const double gk = lm * (-0.5 * sinv + 0.5 * ai * al[j]);
+      agl += gk * cr[j];
+      ags += gk * k0;
+      sk += sinv * kx;
+      ka += kx * al[j];
+    }
+    sk = warp_sum(sk);
+    ka = warp_sum(ka);
+    if (lane == 0) {
+      rowSK[((long)c * N + i) * M + m] = sk;
+      KA[((long)c * N + i) * M + m] = ka;
+    }
+  }
+  agl = warp_sum(agl);
+  ags = warp_sum(ags);
+  if (lane == 0) {
+    gl[(long)c * N + i] = agl;
+    gs[(long)c * N + i] = ags;
+  }
+}
+
+__global__ void __launch_bounds__(256) sep_finish_kernel(
+    int model, int N, int M, int P, const double* __restrict__ pars, HyperConst h, const double* __restrict__ A,
+    long strideA, int ld, const double* __restrict__ logdet, const int* __restrict__ info_in,
+    const double* __restrict__ alpha, const double* __restrict__ yv, const double* __restrict__ s2v,
+    const double* __restrict__ sig, const double* __restrict__ Lmat, const double* __restrict__ lam,
+    const double* __restrict__ Vec, const double* __restrict__ gl, const double* __restrict__ gs,
+    const double* __restrict__ rowSK, const double* __restrict__ KA, const double* __restrict__ Z0,
+    const double* __restrict__ Z1, const double* __restrict__ G0, const double* __restrict__ G1,
+    const double* __restrict__ hld0, const double* __restrict__ hld1, double* __restrict__ vals,
+    double* __restrict__ grad, int* __restrict__ info) {
+  __shared__ double scratch[40];
+  __shared__ double D[16 * 16], dB[16 * 16], tmp[16 * 16];
+  const int c = blockIdx.x;
+  const int T = tril_size(M);
+  const bool stat = (model == 0);
+  const double* p = pars + (long)c * P;
+  const double* uL = stat ? p + 2 : p + 2 * N;
+  const double* Vc = Vec + (long)c * M * M;
+  const double* Lc = Lmat + (long)c * M * M;
+
+  // per-output reductions
+  double quad = 0.0, trG = 0.0, ldsum = 0.0;
+  int bad = 0;
+  for (int m = 0; m < M; ++m) {
+    const double* al = alpha + ((long)c * M + m) * N;
+    const double* ym = yv + ((long)c * M + m) * N;
+    const double* Am = A + ((long)c * M + m) * strideA;
+    double q = 0.0, t = 0.0, sk = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double a = al[i];
+      q += ym[i] * a;
+      t += -0.5 * Am[(long)i * ld + i] + 0.5 * a * a;
+      sk += rowSK[((long)c * N + i) * M + m];
+    }
+    quad += block_sum(q, scratch);
+    trG += block_sum(t, scratch);
+    const double trSK = block_sum(sk, scratch);
+    ldsum += logdet[(long)c * M + m];
+    if (info_in[(long)c * M + m] != 0 && bad == 0) bad = info_in[(long)c * M + m];
+    // D = 0.5 A^T Kx A - 0.5 diag(tr(S_m^-1 Kx))   (eigenbasis of B)
+    for (int m2 = 0; m2 < M; ++m2) {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < N; i += blockDim.x) s += al[i] * KA[((long)c * N + i) * M + m2];
+      const double aka = block_sum(s, scratch);
+      if (threadIdx.x == 0) D[m * 16 + m2] = 0.5 * aka - (m == m2 ? 0.5 * trSK : 0.0);
+    }
+  }
+  __syncthreads();
+  // dB = V D V^T ; dL = 2 tril(dB L)
+  for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
+    const int a = idx / M, b = idx % M;
+    double s = 0.0;
+    for (int k = 0; k < M; ++k) s += Vc[a * M + k] * D[k * 16 + b];
+    tmp[a * 16 + b] = s;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
+    const int a = idx / M, b = idx % M;
+    double s = 0.0;
+    for (int k = 0; k < M; ++k) s += tmp[a * 16 + k] * Vc[b * M + k];
+    dB[a * 16 + b] = s;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) {
+    const int a = idx / M, b = idx % M;
+    double s = 0.0;
+    for (int k = 0; k < M; ++k) s += 0.5 * (dB[a * 16 + k] + dB[k * 16 + a]) * Lc[k * M + b];
+    tmp[a * 16 + b] = 2.0 * s;
+  }
+  __syncthreads();
+
+  // priors
+  const double s2 = s2v[c];
+  const double ts2 = p[P - 1];
+  const double log2pi = 1.8378770664093453;
+  const double half_log2pi = h.half_log2pi;
+  double lp_l, lp_sig = 0.0;
+  if (stat) {
+    const double dl = p[0] - h.s_loc;
+    lp_l = -(dl * dl) / (2.0 * h.s_var) - h.s_logscale - half_log2pi;          // Normal.log_prob, logpos.py:446
+  } else {
+    double z0 = 0.0, z1 = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double a = Z0[(long)c * N + i], b = Z1[(long)c * N + i];
+      z0 += a * a;
+      z1 += b * b;
+    }
+    const double q0 = block_sum(z0, scratch), q1 = block_sum(z1, scratch);
+    lp_l = -0.5 * (N * log2pi + q0) - hld0[c];                                 // logpos.py:274
+    lp_sig = -0.5 * (N * log2pi + q1) - hld1[c];                               // logpos.py:279
+  }
+  double lpu = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const double d = uL[t] - h.n_loc;
+    lpu += -(d * d) / (2.0 * h.n_var) - h.n_logscale - half_log2pi;            // logpos.py:283,450
+  }
+  const double lp_uL = block_sum(lpu, scratch);
+  const double lp_s = (-h.ig_a - 1.0) * log(s2) - h.ig_b / s2 + h.ig_alogb - h.ig_lgamma;
+  const double loglik = -0.5 * ldsum - 0.5 * quad;
+  double res = loglik;
+  if (h.prior) res += lp_l + lp_sig + lp_uL + lp_s + ts2;
+  const double pf = h.prior ? 1.0 : 0.0;
+  if (threadIdx.x == 0) {
+    double* v = vals + (long)c * 6;
+    v[0] = -res; v[1] = loglik; v[2] = lp_l;
+    if (stat) { v[3] = lp_uL; v[4] = lp_s; v[5] = 0.0; }
+    else { v[3] = lp_sig; v[4] = lp_uL; v[5] = lp_s; }
+    info[c] = bad;
+  }
+  if (grad == nullptr) return;
+  double* g = grad + (long)c * P;
+  double* guL = stat ? g + 2 : g + 2 * N;
+  if (stat) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { a += gl[(long)c * N + i]; b += gs[(long)c * N + i]; }
+    const double sl = block_sum(a, scratch), ss = block_sum(b, scratch);
+    if (threadIdx.x == 0) {
+      g[0] = -(2.0 * sl + pf * (-(p[0] - h.s_loc) / h.s_var));
+      g[1] = -(2.0 * ss);
+    }
+  } else {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      g[i] = -(2.0 * gl[(long)c * N + i] - pf * G0[(long)c * N + i]);
+      g[N + i] = -(2.0 * gs[(long)c * N + i] - pf * G1[(long)c * N + i]);
+    }
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    int m = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (m * (m + 1) / 2 > t) --m;
+    while ((m + 1) * (m + 2) / 2 <= t) ++m;
+    const int k = t - m * (m + 1) / 2;
+    double d = tmp[m * 16 + k];
+    if (k == m) d *= Lc[m * M + m];
+    guL[t] = -(d + pf * (-(uL[t] - h.n_loc) / h.n_var));
+  }
+  if (threadIdx.x == 0) g[P - 1] = -(s2 * trG + pf * ((-h.ig_a - 1.0) + h.ig_b / s2 + 1.0));
+}
+
+}  // namespace
+
+// =================================================================================================== host side
+int padded_M(int M) {
+  const int buckets[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
+  for (int b : buckets)
+    if (M <= b) return b;
+  return -1;
+}
+
+#define NMGP_LAUNCH_CHECK()                 \
+  do {                                      \
+    NMGP_CUDA_TRY(cudaGetLastError());      \
+    if (launches) ++*launches;              \
+  } while (0)
+
+int launch_rbf_cov(const double* x1, int N1, const double* x2, int N2, double alpha, double beta, double* out,
+                   cudaStream_t st) {
+  const int self = (x2 == nullptr);
+  if (self) { x2 = x1; N2 = N1; }
+  if (N1 <= 0 || N2 <= 0) return 0;
+  dim3 grid((N2 + 127) / 128, N1);
+  rbf_cov_kernel<<<grid, 128, 0, st>>>(x1, N1, x2, N2, alpha * alpha, beta, self, out);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_gibbs_cov(const double* x1, const double* s1, const double* l1, int N1, const double* x2, const double* s2,
+                     const double* l2, int N2, double* out, cudaStream_t st) {
+  const int self = (x2 == nullptr);
+  if (self) { x2 = x1; s2 = s1; l2 = l1; N2 = N1; }
+  if (N1 <= 0 || N2 <= 0) return 0;
+  dim3 grid((N2 + 127) / 128, N1);
+  gibbs_cov_kernel<<<grid, 128, 0, st>>>(x1, s1, l1, N1, x2, s2, l2, N2, self, out);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_prior_cov_blocks(const double* x, int cs, int N, double alpha, double beta, const BlockBatch& b,
+                            cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  dim3 grid((b.nP + 127) / 128, b.nP, cs);
+  prior_cov_blocks_kernel<<<grid, 128, 0, st>>>(x, N, alpha * alpha, beta, b.A, b.strideA(), b.nP);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_extract_factor(const BlockBatch& b, int N, double* Lp, double* hld, cudaStream_t st, long* launches) {
+  if (b.batch <= 0) return 0;
+  dim3 grid((N + 127) / 128, N, b.batch);
+  extract_factor_kernel<<<grid, 128, 0, st>>>(b.A, b.strideA(), b.nP, N, b.logdet, Lp, hld);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_prior_solve(const double* Lp, const double* rhs, double* out, int cs, int N, int nv, int trans,
+                       cudaStream_t st, long* launches) {
+  if (cs <= 0 || nv <= 0) return 0;
+  dim3 grid(cs, (nv + 31) / 32);
+  if (trans) prior_solve_kernel<1><<<grid, 256, 0, st>>>(Lp, rhs, out, N, nv);
+  else prior_solve_kernel<0><<<grid, 256, 0, st>>>(Lp, rhs, out, N, nv);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_nonseparable_cov_reference_order(const double* x, const double* pars, int batch, int N, int M, double* out,
+                                            cudaStream_t st) {
+  if (batch <= 0) return 0;
+  const int n = N * M;
+  dim3 grid((n + 127) / 128, n, batch);
+  svc_cov_reference_order_kernel<<<grid, 128, 0, st>>>(x, pars, N, M, out);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int svc_forward(int cs, int N, int M, const double* x, const double* pars, int P, const HyperConst& h, const Scratch& w,
+                const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  const int MT = padded_M(M);
+  svc_prep_kernel<<<cs, 256, 0, st>>>(pars, P, N, M, MT, h.mu0, h.mu1, w.ell, w.Lst, w.s2, w.R0, w.R1);
+  NMGP_LAUNCH_CHECK();
+  dim3 gk((N + 127) / 128, N, cs);
+  kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, nullptr, N, w.Kx, w.CK);
+  NMGP_LAUNCH_CHECK();
+  dim3 gb(b.Kt * (b.Kt + 1) / 2, cs);
+  svc_build_kernel<<<gb, 256, 0, st>>>(w.Kx, w.Lst, w.s2, N, M, MT, b.A, b.strideA(), b.nP);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int MT>
+static void launch_svc_contract(dim3 grid, cudaStream_t st, const BlockBatch& b, int N, int M, const Scratch& w) {
+  svc_contract_kernel<MT><<<grid, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, w.alpha, w.Kx, w.CK, w.Lst, w.Wout, w.Vout);
+}
+
+int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int P, const HyperConst& h,
+                 const Scratch& w, const BlockBatch& b, const double* hld0, const double* hld1, double* vals,
+                 double* grad, int* info, cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  const int n = N * M, MT = padded_M(M);
+  dim3 gs((n + 7) / 8, cs);
+  symv_kernel<<<gs, 256, 0, st>>>(b.A, b.strideA(), b.nP, n, Y, w.alpha);
+  NMGP_LAUNCH_CHECK();
+  if (grad != nullptr) {
+    switch (MT) {
+      case 2: launch_svc_contract<2>(gs, st, b, N, M, w); break;
+      case 3: launch_svc_contract<3>(gs, st, b, N, M, w); break;
+      case 4: launch_svc_contract<4>(gs, st, b, N, M, w); break;
+      case 5: launch_svc_contract<5>(gs, st, b, N, M, w); break;
+      case 6: launch_svc_contract<6>(gs, st, b, N, M, w); break;
+      case 8: launch_svc_contract<8>(gs, st, b, N, M, w); break;
+      case 10: launch_svc_contract<10>(gs, st, b, N, M, w); break;
+      case 12: launch_svc_contract<12>(gs, st, b, N, M, w); break;
+      default: launch_svc_contract<16>(gs, st, b, N, M, w); break;
+    }
+    NMGP_LAUNCH_CHECK();
+  }
+  svc_finish_kernel<<<cs, 256, 0, st>>>(N, M, MT, P, pars, Y, h, b.A, b.strideA(), b.nP, b.logdet, b.info, w.alpha, w.s2,
+                                        w.Lst, w.Wout, w.Vout, w.Z0, w.Z1, w.G0, w.G1, hld0, hld1, vals, grad, info);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,
+                const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  sep_prep_kernel<<<cs, 256, 0, st>>>(model, pars, P, N, M, Y, h.mu0, h.mu1, w.ell, w.sig, w.s2, w.Lst, w.lam, w.Vec, w.yv,
+                                      w.R0, w.R1);
+  NMGP_LAUNCH_CHECK();
+  dim3 gk((N + 127) / 128, N, cs);
+  kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, w.sig, N, w.Kx, w.CK);
+  NMGP_LAUNCH_CHECK();
+  dim3 gb((b.nP + 127) / 128, b.nP, cs * M);
+  sep_build_kernel<<<gb, 128, 0, st>>>(w.Kx, w.lam, w.s2, N, M, b.A, b.strideA(), b.nP);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int sep_backward(int model, int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w,
+                 const BlockBatch& b, const double* hld0, const double* hld1, double* vals, double* grad, int* info,
+                 cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  dim3 gs((N + 7) / 8, cs * M);
+  symv_kernel<<<gs, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, w.yv, w.alpha);
+  NMGP_LAUNCH_CHECK();
+  dim3 gc((N + 7) / 8, cs);
+  sep_contract_kernel<<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, w.alpha, w.lam, w.Kx, w.CK, w.sig, w.gl, w.gs,
+                                          w.Wout, w.Vout);
+  NMGP_LAUNCH_CHECK();
+  sep_finish_kernel<<<cs, 256, 0, st>>>(model, N, M, P, pars, h, b.A, b.strideA(), b.nP, b.logdet, b.info, w.alpha, w.yv,
+                                        w.s2, w.sig, w.Lst, w.lam, w.Vec, w.gl, w.gs, w.Wout, w.Vout, w.Z0, w.Z1, w.G0,
+                                        w.G1, hld0, hld1, vals, grad, info);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace nmgp

@@ -1,0 +1,80 @@
+// Model-specific kernels around the factorisation engine: parameter transforms, covariance construction,
+// gradient contraction, priors.  See models.cu.
+#pragma once
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace nmgp {
+
+// Hyper-parameter constants precomputed on the host once per plan.
+struct HyperConst {
+  // GP priors (nonseparable: [tilde_l, uL]; separable: [tilde_l, tilde_sigma])
+  double mu0, mu1;
+  // torch.distributions.Normal(loc, scale) built from Python numbers rounds loc/scale to float32 and evaluates
+  // scale^2 and log(scale) in float32 (Utility/logpos.py:283,446,450); these are those values, widened.
+  double n_loc, n_var, n_logscale;   // Normal(0,c) on uL (stationary / separable)
+  double s_loc, s_var, s_logscale;   // Normal(mu_tilde_l, sigma_tilde_l) on tilde_l (stationary)
+  double ig_a, ig_b, ig_alogb, ig_lgamma;  // inverse gamma: a log b, lgamma(a)  (distributions.py:126-134)
+  double half_log2pi;                // math.log(math.sqrt(2*math.pi)) as torch's Normal.log_prob forms it
+  int prior;                         // `Prior=` keyword
+};
+
+// Per-chunk scratch (device pointers); sizes in comments are per chunk of `cs` subjects.
+struct Scratch {
+  double* ell;    // [cs][N]
+  double* sig;    // [cs][N]            (separable / stationary)
+  double* s2;     // [cs]
+  double* Lst;    // nonseparable: [cs][n][MT] rows (i,m) of L_i, zero padded; separable: [cs][M*M] L
+  double* Kx;     // [cs][N][N]  Gibbs kernel incl. jitter
+  double* CK;     // [cs][N][N]  c_ij * K0_ij  (d K0_ij / d tilde_l_i)
+  double* alpha;  // [cs][nmat][n]   Sigma^-1 y
+  double* yv;     // [cs][nmat][n]   right-hand sides (nonseparable: Y itself is used instead)
+  double* Wout;   // nonseparable [cs][n][MT];  separable: rowSK [cs][N][M]
+  double* Vout;   // nonseparable [cs][n][MT];  separable: KA    [cs][N][M]
+  double* gl;     // separable [cs][N]   sum_j GK_ij CK_ij
+  double* gs;     // separable [cs][N]   sum_j GK_ij K0_ij
+  double* lam;    // separable [cs][M]
+  double* Vec;    // separable [cs][M][M]  eigenvectors of B (columns)
+  double* R0;     // [cs][N]       residual for prior 0
+  double* R1;     // [cs][N][nv1]  residual for prior 1 (nonseparable nv1 = T; separable nv1 = 1)
+  double* Z0;     // [cs][N]
+  double* Z1;     // [cs][N][nv1]
+  double* G0;     // [cs][N]
+  double* G1;     // [cs][N][nv1]
+};
+
+int padded_M(int M);  // template bucket for the nonseparable contraction (>= M)
+
+// ---- elementwise covariance kernels (unit entry points + plan creation)
+int launch_rbf_cov(const double* x1, int N1, const double* x2, int N2, double alpha, double beta, double* out,
+                   cudaStream_t st);
+int launch_gibbs_cov(const double* x1, const double* s1, const double* l1, int N1, const double* x2, const double* s2,
+                     const double* l2, int N2, double* out, cudaStream_t st);
+// prior covariance alpha^2 exp(-0.5 d/beta^2) + jitter I for `cs` subjects, written into the engine's padded layout
+int launch_prior_cov_blocks(const double* x, int cs, int N, double alpha, double beta, const BlockBatch& b,
+                            cudaStream_t st, long* launches);
+// after potrf: compact lower factor [cs][N][N] and half log-determinants
+int launch_extract_factor(const BlockBatch& b, int N, double* Lp, double* hld, cudaStream_t st, long* launches);
+
+// blocked substitution with the cached prior factor: trans=0 solves L X = rhs, trans=1 solves L^T X = rhs;
+// rhs / out are [cs][N][nv]
+int launch_prior_solve(const double* Lp, const double* rhs, double* out, int cs, int N, int nv, int trans,
+                       cudaStream_t st, long* launches);
+
+// ---- nonseparable model (Utility/logpos.py:326-380)
+int svc_forward(int cs, int N, int M, const double* x, const double* pars, int P, const HyperConst& h, const Scratch& w,
+                const BlockBatch& b, cudaStream_t st, long* launches);  // prep + Kx + build
+int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int P, const HyperConst& h,
+                 const Scratch& w, const BlockBatch& b, const double* hld0, const double* hld1, double* vals,
+                 double* grad, int* info, cudaStream_t st, long* launches);  // symv + contraction + finish
+int launch_nonseparable_cov_reference_order(const double* x, const double* pars, int batch, int N, int M, double* out,
+                                            cudaStream_t st);
+
+// ---- separable / stationary models (Utility/logpos.py:237-296, 405-462)
+int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,
+                const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches);
+int sep_backward(int model, int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w,
+                 const BlockBatch& b, const double* hld0, const double* hld1, double* vals, double* grad, int* info,
+                 cudaStream_t st, long* launches);
+
+}  // namespace nmgp
