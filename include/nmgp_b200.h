@@ -84,6 +84,18 @@ int nmgp_logpost_grad(nmgp_plan* plan, const double* pars_dev, double* vals_dev,
 int nmgp_logpost_grad_host(nmgp_plan* plan, const double* pars_host, double* vals_host, double* grad_host,
                            int* info_host, void* stream);
 
+/* Same evaluation with CUDA events between its phases (synchronises once per chunk): phase_ms[NMGP_NPHASES] (host)
+ * receives the milliseconds spent in {0: parameter transform + covariance build, 1: Cholesky factorisation (potrf),
+ * 2: inverse (trtri + lauum + symmetrise), 3: GP-prior triangular solves, 4: alpha = Sigma^-1 y, gradient contraction
+ * and assembly}.  bench.py uses it for the live roofline figures ("FP64 Cholesky TFLOP/s"). */
+#define NMGP_NPHASES 5
+int nmgp_logpost_grad_profile(nmgp_plan* plan, const double* pars_dev, double* vals_dev, double* grad_dev,
+                              int* info_dev, float* phase_ms, void* stream);
+
+/* Factorisation engine selection: 0 = automatic (left-looking accumulate-in-registers path for large batches,
+ * right-looking tile tasks otherwise), 1 = force right-looking, 2 = force left-looking.  For tests and A/B timing. */
+int nmgp_plan_set_engine(nmgp_plan* plan, int mode);
+
 /* Number of kernels the plan's last evaluation launched (bench.py's `gpu_launches`). */
 long nmgp_plan_last_launches(const nmgp_plan* plan);
 /* Bytes of device memory owned by the plan. */

@@ -14,13 +14,15 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
-SOURCES = ["engine.cu", "models.cu", "api.cu"]
+SOURCES = ["engine.cu", "engine_ll.cu", "models.cu", "api.cu"]
 HEADERS = ["common.cuh", "engine.cuh", "models.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 NVALS = 6
 NHYPER = 9
+NPHASES = 5
+PHASE_NAMES = ("build", "potrf", "potri", "prior_solves", "contract")
 STATIONARY, SEPARABLE, NONSEPARABLE = 0, 1, 2
 
 _lock = threading.Lock()
@@ -69,6 +71,10 @@ def _declare(lib):
     lib.nmgp_logpost_grad.argtypes = [c.c_void_p, dp, dp, dp, ip, vp]
     lib.nmgp_logpost_grad_host.restype = c.c_int
     lib.nmgp_logpost_grad_host.argtypes = [c.c_void_p, dp, dp, dp, ip, vp]
+    lib.nmgp_logpost_grad_profile.restype = c.c_int
+    lib.nmgp_logpost_grad_profile.argtypes = [c.c_void_p, dp, dp, dp, ip, c.POINTER(c.c_float), vp]
+    lib.nmgp_plan_set_engine.restype = c.c_int
+    lib.nmgp_plan_set_engine.argtypes = [c.c_void_p, c.c_int]
     lib.nmgp_plan_last_launches.restype = c.c_long
     lib.nmgp_plan_last_launches.argtypes = [c.c_void_p]
     lib.nmgp_plan_device_bytes.restype = c.c_size_t
@@ -91,7 +97,7 @@ def _declare(lib):
 
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
-           "nmgp_logpost_grad_host", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
+           "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
            "nmgp_plan_block", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 

@@ -96,6 +96,11 @@ class LogPosteriorPlan:
     def last_launches(self) -> int:
         return self.lib.nmgp_plan_last_launches(self._handle)
 
+    def set_engine(self, mode: str):
+        """'auto' | 'right' (right-looking tile tasks) | 'left' (left-looking / Takahashi): tests and A/B timing."""
+        _lib.check(self.lib.nmgp_plan_set_engine(self._handle, {"auto": 0, "right": 1, "left": 2}[mode]),
+                   "nmgp_plan_set_engine")
+
     # ------------------------------------------------------------------ evaluation
     def value_and_grad(self, pars, need_grad: bool = True):
         """Device path: pars [S,P] CUDA float64 -> (vals [S,6], grad [S,P] or None, info [S] int32), all CUDA.
@@ -116,6 +121,21 @@ class LogPosteriorPlan:
                                             ctypes.c_void_p(stream))
         _lib.check(rc, "nmgp_logpost_grad")
         return vals, grad, info
+
+    def profile(self, pars):
+        """One evaluation with CUDA events between phases: returns ({phase: ms}, vals, grad, info) (device tensors)."""
+        torch = _lib.require_cuda()
+        p = pars.detach().to(torch.float64).reshape(self.S, self.P).contiguous()
+        vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
+        grad = torch.empty((self.S, self.P), dtype=torch.float64, device=self.device)
+        info = torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        ms = (ctypes.c_float * _lib.NPHASES)()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_logpost_grad_profile(self._handle, p.data_ptr(), vals.data_ptr(), grad.data_ptr(),
+                                                    info.data_ptr(), ms, ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_logpost_grad_profile")
+        return dict(zip(_lib.PHASE_NAMES, [float(v) for v in ms])), vals, grad, info
 
     def _pinned_buffers(self):
         torch = _lib.require_cuda()

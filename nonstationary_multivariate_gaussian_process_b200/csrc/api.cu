@@ -25,6 +25,7 @@ struct nmgp_plan {
   int chunk = 0;  // subjects per pass
   int nprior = 0; // GP-prior covariance matrices per subject (0 stationary, 2 otherwise)
   int nv1 = 1;    // right-hand sides for prior 1
+  int engine_mode = 0;  // 0 auto, 1 force right-looking tile tasks, 2 force left-looking (tests / A-B timing)
   double hyper[NMGP_NHYPER] = {0};
   HyperConst hc{};
   std::vector<void*> allocs;
@@ -95,7 +96,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   const size_t MT = pl->model == NMGP_NONSEPARABLE ? padded_M(pl->M) : 0;
   size_t d = 0;
   d += nm * nP * nP;            // A
-  d += nm * Kt * kNB * kNB;     // Dinv
+  d += 2 * nm * Kt * kNB * kNB; // Dinv, Pbuf
   d += nm;                      // logdet
   d += 2 * N + 1;               // ell, sig, s2
   d += pl->model == NMGP_NONSEPARABLE ? n * MT : M * M;  // Lst
@@ -115,6 +116,11 @@ int alloc_workspace(nmgp_plan* pl) {
   b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
   NMGP_TRY(dev_alloc(pl, &b.A, cs * nm * (size_t)pl->nP * pl->nP));
   NMGP_TRY(dev_alloc(pl, &b.Dinv, cs * nm * (size_t)pl->Kt * kNB * kNB));
+  NMGP_TRY(dev_alloc(pl, &b.Pbuf, cs * nm * (size_t)pl->Kt * kNB * kNB));
+  // the left-looking engine multiplies padding / not-yet-written upper tiles by exact zeros: they must be finite
+  NMGP_CUDA_TRY(cudaMemsetAsync(b.A, 0, cs * nm * (size_t)pl->nP * pl->nP * sizeof(double), 0));
+  NMGP_CUDA_TRY(cudaMemsetAsync(b.Pbuf, 0, cs * nm * (size_t)pl->Kt * kNB * kNB * sizeof(double), 0));
+  NMGP_CUDA_TRY(cudaStreamSynchronize(0));
   NMGP_TRY(dev_alloc(pl, &b.logdet, cs * nm));
   NMGP_TRY(dev_alloc(pl, &b.info, cs * nm));
   Scratch& w = pl->w;
@@ -325,11 +331,16 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
   return 0;
 }
 
-int nmgp_logpost_grad(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, void* stream) {
-  if (!pl || (pl->S > 0 && (!pars || !vals || !info))) { set_last_error("nmgp_logpost_grad: null argument"); return NMGP_EINVAL; }
-  cudaStream_t st = (cudaStream_t)stream;
+static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st,
+                    float* phase_ms) {
   long launches = 0;
   const int N = pl->N, M = pl->M, P = pl->P;
+  cudaEvent_t ev[NMGP_NPHASES + 1];
+  if (phase_ms) {
+    for (int i = 0; i <= NMGP_NPHASES; ++i) NMGP_CUDA_TRY(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < NMGP_NPHASES; ++i) phase_ms[i] = 0.f;
+  }
+#define NMGP_MARK(i) do { if (phase_ms) NMGP_CUDA_TRY(cudaEventRecord(ev[i], st)); } while (0)
   for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
     const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
     BlockBatch b = pl->bb;
@@ -340,23 +351,29 @@ int nmgp_logpost_grad(nmgp_plan* pl, const double* pars, double* vals, double* g
     double* vs = vals + (size_t)s0 * NMGP_NVALS;
     double* gs = grad ? grad + (size_t)s0 * P : nullptr;
     int* is = info + s0;
+    NMGP_MARK(0);
     if (pl->model == NMGP_NONSEPARABLE) {
       NMGP_TRY(svc_forward(cs, N, M, xs, ps, P, pl->hc, pl->w, b, st, &launches));
     } else {
       NMGP_TRY(sep_forward(pl->model, cs, N, M, xs, Ys, ps, P, pl->hc, pl->w, b, st, &launches));
     }
-    NMGP_TRY(engine_potrf(b, st, &launches));
-    NMGP_TRY(engine_potri(b, st, &launches));
+    NMGP_MARK(1);
+    const bool ll = b.Pbuf != nullptr && (pl->engine_mode == 2 || (pl->engine_mode == 0 && prefer_left_looking(b)));
+    if (ll) NMGP_TRY(engine_potrf_ll(b, st, &launches)); else NMGP_TRY(engine_potrf(b, st, &launches));
+    NMGP_MARK(2);
+    if (ll) NMGP_TRY(engine_potri_ll(b, st, &launches)); else NMGP_TRY(engine_potri(b, st, &launches));
+    NMGP_MARK(3);
     if (pl->nprior) {
-      const double* W0 = pl->Wp0 + (size_t)s0 * N * N;
-      const double* W1 = pl->Wp1 + (size_t)s0 * N * N;
-      NMGP_TRY(launch_prior_solve(W0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
-      NMGP_TRY(launch_prior_solve(W1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, st, &launches));
+      const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
+      const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
+      NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
+      NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, st, &launches));
       if (grad) {
-        NMGP_TRY(launch_prior_solve(W0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, st, &launches));
-        NMGP_TRY(launch_prior_solve(W1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, st, &launches));
+        NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, st, &launches));
+        NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, st, &launches));
       }
     }
+    NMGP_MARK(4);
     const double* h0 = pl->hld0 ? pl->hld0 + s0 : nullptr;
     const double* h1 = pl->hld1 ? pl->hld1 + s0 : nullptr;
     if (pl->model == NMGP_NONSEPARABLE) {
@@ -364,9 +381,32 @@ int nmgp_logpost_grad(nmgp_plan* pl, const double* pars, double* vals, double* g
     } else {
       NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
     }
+    NMGP_MARK(5);
+    if (phase_ms) {
+      NMGP_CUDA_TRY(cudaEventSynchronize(ev[NMGP_NPHASES]));
+      for (int i = 0; i < NMGP_NPHASES; ++i) {
+        float ms = 0.f;
+        NMGP_CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        phase_ms[i] += ms;
+      }
+    }
   }
+#undef NMGP_MARK
+  if (phase_ms)
+    for (int i = 0; i <= NMGP_NPHASES; ++i) cudaEventDestroy(ev[i]);
   pl->last_launches = launches;
   return 0;
+}
+
+int nmgp_logpost_grad(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, void* stream) {
+  if (!pl || (pl->S > 0 && (!pars || !vals || !info))) { set_last_error("nmgp_logpost_grad: null argument"); return NMGP_EINVAL; }
+  return evaluate(pl, pars, vals, grad, info, (cudaStream_t)stream, nullptr);
+}
+
+int nmgp_logpost_grad_profile(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, float* phase_ms,
+                              void* stream) {
+  if (!pl || !phase_ms || (pl->S > 0 && (!pars || !vals || !info))) { set_last_error("nmgp_logpost_grad_profile: null argument"); return NMGP_EINVAL; }
+  return evaluate(pl, pars, vals, grad, info, (cudaStream_t)stream, phase_ms);
 }
 
 int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, double* grad_h, int* info_h,
@@ -381,6 +421,12 @@ int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, 
   if (grad_h) NMGP_CUDA_TRY(cudaMemcpyAsync(grad_h, pl->grad_d, SP * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (info_h) NMGP_CUDA_TRY(cudaMemcpyAsync(info_h, pl->info_d, (size_t)pl->S * sizeof(int), cudaMemcpyDeviceToHost, st));
   NMGP_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nmgp_plan_set_engine(nmgp_plan* pl, int mode) {
+  if (!pl || mode < 0 || mode > 2) return NMGP_EINVAL;
+  pl->engine_mode = mode;
   return 0;
 }
 

@@ -314,21 +314,30 @@ EngineArgs make_args(const BlockBatch& b) {
 
 }  // namespace
 
-int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
+int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
-  if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine_potrf: bad block layout"); return -1; }
+  if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine: bad block layout"); return -1; }
   static bool configured = false;
   if (!configured) {
     NMGP_CUDA_TRY(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     configured = true;
   }
   EngineArgs g = make_args(b);
+  g.step = k;
   const int dgrid = b.batch < 148 * 8 ? b.batch : 148 * 8;
+  diag_kernel<<<dgrid, DIAG_THREADS, DIAG_SMEM, st>>>(g, b.logdet, b.info);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
+  if (b.batch <= 0) return 0;
+  if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine_potrf: bad block layout"); return -1; }
+  EngineArgs g = make_args(b);
   for (int k = 0; k < b.Kt; ++k) {
     g.step = k;
-    diag_kernel<<<dgrid, DIAG_THREADS, DIAG_SMEM, st>>>(g, b.logdet, b.info);
-    NMGP_CUDA_TRY(cudaGetLastError());
-    if (launches) ++*launches;
+    NMGP_TRY(engine_diag_step(b, k, st, launches));
     const int r = b.Kt - k - 1;
     if (stable_panel) {
       if (r > 0) {

@@ -12,6 +12,7 @@ namespace nmgp {
 struct BlockBatch {
   double* A = nullptr;
   double* Dinv = nullptr;
+  double* Pbuf = nullptr;    // [batch][Kt][NB*NB]  panel side buffer of the left-looking inverse (zero-initialised once)
   double* logdet = nullptr;  // [batch]
   int* info = nullptr;       // [batch]
   int n = 0;                 // logical dimension
@@ -35,5 +36,17 @@ int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stab
 int engine_trtri(const BlockBatch& b, cudaStream_t st, long* launches);
 // After potrf: A <- inverse (both triangles filled).  trtri + lauum + symmetrize.
 int engine_potri(const BlockBatch& b, cudaStream_t st, long* launches);
+
+// One diagonal-block step (factor A(k,k), W_kk = L_kk^-1 into Dinv, log det, info) -- shared by both engines.
+int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches);
+
+// Left-looking potrf / Takahashi inverse for large batches of mid-size matrices (engine_ll.cu).  Same results layout as
+// engine_potrf / engine_potri.  Requires b.Pbuf, and A's padding and upper block triangle to hold finite values
+// (the plan zero-fills the workspace once).
+int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches);
+int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches);
+
+// Heuristic: the left-looking path needs >= ~2 waves of 64x64 tiles per block column from the batch alone.
+inline bool prefer_left_looking(const BlockBatch& b) { return b.Pbuf != nullptr && b.batch >= 96; }
 
 }  // namespace nmgp

@@ -1,0 +1,207 @@
+"""Objective functions with the reference's names, signatures and return conventions (Utility/logpos.py),
+evaluated by the B200 CUDA library through the C ABI.
+
+    nlogpos_obj_S   (pars, Y, x, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, verbose=False, Prior=True)     logpos.py:383
+    nlogpos_obj     (pars, Y, x, mu_tilde_l=0., ..., a=1, b=1, c=10, verbose=False, Prior=True)            logpos.py:216
+    nlogpos_obj_SVC (pars, Y, x, mu_tilde_l=0., alpha_tilde_l=5., ..., a=1, b=1, verbose=False, Prior=True) logpos.py:299
+
+`pars` is the flat float64 parameter vector the drivers build with `torch.cat([...leaf tensors...])`; the returned
+value is a 0-dim tensor on the same device that participates in autograd, so `NegLog.backward()` fills the
+leaves' `.grad` exactly as in the drivers' MAP loops (e.g. Nonseparable_model_mpisim.py:183-190) -- the gradient
+is the analytic one computed on the GPU in the same call.  With verbose=True the extra tuple entries (loglik and
+the prior components) are returned detached, as the drivers only print them.
+
+A plan (cached loop-invariant device state: x, Y, hyper-parameters, factored GP-prior covariances, workspace) is
+kept per (model, data, hyper-parameters) so that repeated calls from a MAP / HMC loop only move `pars` in and
+`value, components, grad` out.  Batched entry points for many subjects at once: `nlogpos_obj*_batched`.
+
+There is no CPU fallback: without a CUDA device or without the built library these functions raise.
+"""
+from __future__ import annotations
+
+import collections
+
+import numpy as np
+
+from . import _lib, batched
+from .batched import LogPosteriorPlan
+
+_PLAN_CACHE: "collections.OrderedDict[tuple, LogPosteriorPlan]" = collections.OrderedDict()
+_PLAN_CACHE_SIZE = 8
+
+
+# ------------------------------------------------------------------------------------- parameter slicing
+def vec2pars(pars, N, M):
+    """(logpos.py:17-29)"""
+    T = M * (M + 1) // 2
+    return pars[:N], pars[N:2 * N], pars[2 * N:2 * N + T], pars[-1]
+
+
+def vec2pars_SVC(pars, N, M):
+    """(logpos.py:32-43)"""
+    T = M * (M + 1) // 2
+    return pars[:N], pars[N:N + N * T], pars[-1]
+
+
+def vec2pars_S(pars, M):
+    """(logpos.py:46-57)"""
+    T = M * (M + 1) // 2
+    return pars[0], pars[1], pars[2:2 + T], pars[-1]
+
+
+def generate_K_index_SVC(L_f_list):
+    """Stack the per-time-point factors and form L L^T, time-major (logpos.py:111-118); evaluated on the GPU."""
+    torch = _lib.require_cuda()
+    dev = L_f_list[0].device
+    L = torch.cat([l.cuda() for l in L_f_list], dim=0)
+    return (L @ L.t()).to(dev)
+
+
+# ------------------------------------------------------------------------------------- plan cache
+def _fingerprint(t):
+    a = t.detach().cpu().contiguous().numpy()
+    return (a.shape, hash(a.tobytes()))
+
+
+def _get_plan(model, Y, x, hyper, prior):
+    torch = _lib.require_cuda()
+    Y = torch.as_tensor(Y, dtype=torch.float64)
+    x = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
+    key = (model, _fingerprint(Y), _fingerprint(x), tuple(sorted((k, float(v)) for k, v in hyper.items())), bool(prior),
+           torch.cuda.current_device())
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = LogPosteriorPlan(model, x, Y, hyper, prior=prior)
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _, old = _PLAN_CACHE.popitem(last=False)
+            old.close()
+    else:
+        _PLAN_CACHE.move_to_end(key)
+    return plan
+
+
+def clear_plan_cache():
+    while _PLAN_CACHE:
+        _, p = _PLAN_CACHE.popitem()
+        p.close()
+
+
+# ------------------------------------------------------------------------------------- autograd bridge
+def _make_function():
+    torch = _lib.require_cuda()
+
+    class _NegLogPosterior(torch.autograd.Function):
+        """vals[S,6] = plan(pars[S,P]); only vals[:,0] (= -log posterior) is differentiable."""
+
+        @staticmethod
+        def forward(ctx, pars, plan):
+            need_grad = pars.requires_grad
+            if pars.is_cuda:
+                vals, grad, info = plan.value_and_grad(pars, need_grad=need_grad)
+            else:
+                vals, grad, info = plan.value_and_grad_host(pars, need_grad=need_grad)
+            ctx.save_for_backward(grad if need_grad else None)
+            ctx.shape = pars.shape
+            ctx.mark_non_differentiable(info)
+            return vals, info
+
+        @staticmethod
+        def backward(ctx, gvals, _ginfo):
+            (grad,) = ctx.saved_tensors
+            if grad is None:
+                return None, None
+            return (gvals[:, :1] * grad).reshape(ctx.shape), None
+
+    return _NegLogPosterior
+
+
+_FN = None
+
+
+def _evaluate(plan, pars):
+    """pars [S,P] or [P] tensor -> (vals [S,6] with autograd on column 0, info [S])."""
+    global _FN
+    torch = _lib.require_cuda()
+    if _FN is None:
+        _FN = _make_function()
+    p = torch.as_tensor(pars)
+    if p.dtype != torch.float64:
+        p = p.to(torch.float64)
+    return _FN.apply(p.reshape(plan.S, plan.P), plan)
+
+
+def _single(model, pars, Y, x, hyper, verbose, Prior):
+    plan = _get_plan(model, Y, x, hyper, Prior)
+    vals, _ = _evaluate(plan, pars)
+    if not verbose:
+        return vals[0, 0]
+    n = batched.N_VERBOSE[model]
+    return (vals[0, 0],) + tuple(vals[0, k].detach() for k in range(1, n))
+
+
+# ------------------------------------------------------------------------------------- reference signatures
+def nlogpos_obj_S(pars, Y, x, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, verbose=False, Prior=True):
+    """Stationary model: -log posterior [, loglik, lp_tilde_l, lp_uL, lp_sigma2]  (logpos.py:383-402)."""
+    hyper = dict(mu_tilde_l=mu_tilde_l, sigma_tilde_l=sigma_tilde_l, a=a, b=b, c=c)
+    return _single("stationary", pars, Y, x, hyper, verbose, Prior)
+
+
+def nlogpos_obj(pars, Y, x, mu_tilde_l=0., alpha_tilde_l=1., beta_tilde_l=1., mu_tilde_sigma=0., alpha_tilde_sigma=1.,
+                beta_tilde_sigma=1., a=1, b=1, c=10, verbose=False, Prior=True):
+    """Separable model: -log posterior [, loglik, lp_tilde_l, lp_tilde_sigma, lp_uL, lp_sigma2]  (logpos.py:216-234)."""
+    hyper = dict(mu_tilde_l=mu_tilde_l, alpha_tilde_l=alpha_tilde_l, beta_tilde_l=beta_tilde_l,
+                 mu_tilde_sigma=mu_tilde_sigma, alpha_tilde_sigma=alpha_tilde_sigma,
+                 beta_tilde_sigma=beta_tilde_sigma, a=a, b=b, c=c)
+    return _single("separable", pars, Y, x, hyper, verbose, Prior)
+
+
+def nlogpos_obj_SVC(pars, Y, x, mu_tilde_l=0., alpha_tilde_l=5., beta_tilde_l=1., mu_L=0., alpha_L=5., beta_L=1., a=1,
+                    b=1, verbose=False, Prior=True):
+    """Nonseparable model: -log posterior [, loglik, lp_tilde_l, lp_uL, lp_sigma2]  (logpos.py:299-323)."""
+    hyper = dict(mu_tilde_l=mu_tilde_l, alpha_tilde_l=alpha_tilde_l, beta_tilde_l=beta_tilde_l, mu_L=mu_L,
+                 alpha_L=alpha_L, beta_L=beta_L, a=a, b=b)
+    return _single("nonseparable", pars, Y, x, hyper, verbose, Prior)
+
+
+def _positive(out, verbose):
+    if not verbose:
+        return -out
+    return (-out[0],) + tuple(out[1:])
+
+
+def logpos_S(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, mu_tilde_l, sigma_tilde_l, a, b, c, verbose=False,
+             Prior=True):
+    """log posterior of the stationary model from its separate parameters (logpos.py:405-462)."""
+    torch = _lib.require_cuda()
+    pars = torch.cat([tilde_l.reshape(1), tilde_sigma.reshape(1), uL_vec.reshape(-1), tilde_sigma2_err.reshape(1)])
+    return _positive(nlogpos_obj_S(pars, Y, x, mu_tilde_l, sigma_tilde_l, a, b, c, verbose, Prior), verbose)
+
+
+def logpos(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+           mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose=False, Prior=True):
+    """log posterior of the separable model (logpos.py:237-296)."""
+    torch = _lib.require_cuda()
+    pars = torch.cat([tilde_l.reshape(-1), tilde_sigma.reshape(-1), uL_vec.reshape(-1), tilde_sigma2_err.reshape(1)])
+    return _positive(nlogpos_obj(pars, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma,
+                                 alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose, Prior), verbose)
+
+
+def logpos_SVC(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L,
+               a, b, verbose=False, Prior=True):
+    """log posterior of the nonseparable model (logpos.py:326-380)."""
+    torch = _lib.require_cuda()
+    pars = torch.cat([tilde_l.reshape(-1), uL_vecs.reshape(-1), tilde_sigma2_err.reshape(1)])
+    return _positive(nlogpos_obj_SVC(pars, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b,
+                                     verbose, Prior), verbose)
+
+
+# ------------------------------------------------------------------------------------- batched entry points
+def nlogpos_obj_batched(model, pars, plan):
+    """Batched objective over all S subjects of `plan` (model in {'stationary','separable','nonseparable'}):
+    pars [S,P] -> (neg_logpost [S] (differentiable), components [S,5] detached, info [S]).
+    This is what the subject-sharded drivers (sharding.py, bench.py) call."""
+    if plan.model != model:
+        raise ValueError(f"plan was built for the {plan.model} model, not {model}")
+    vals, info = _evaluate(plan, pars)
+    return vals[:, 0], vals[:, 1:].detach(), info

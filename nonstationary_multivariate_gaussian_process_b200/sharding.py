@@ -1,0 +1,43 @@
+"""Subject sharding across the GPUs of one box: one process per GPU, block partition, one tiny all-reduce.
+
+The reference runs one OS process per subject (`srun -n 1000 python Nonseparable_model_mpisim.py`,
+Nonseparable_Model/sim_job:9) and uses MPI only as a rank -> subject index (Nonseparable_model_mpisim.py:39-43);
+nothing is exchanged between subjects.  Here rank r owns subjects [lo, hi) of the S_total; `x`, `Y`, `pars` and
+`grad` of a subject never leave its GPU.  The only collective is an all-reduce(sum) of a short float64 vector of
+sweep totals (sum of -log posterior, of each component, failure count, subject count) -- NCCL over NVLink on the
+GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+SUMMARY_FIELDS = ("neg_logpost", "c1", "c2", "c3", "c4", "c5", "n_failed", "n_subjects")
+
+
+def shard_range(S_total: int, rank: int, world: int):
+    """Block partition of S_total subjects: the first S_total % world ranks hold one extra subject."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    base, extra = divmod(S_total, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def local_summary(vals, info):
+    """vals [S_local,6], info [S_local] -> float64 vector [8] of this rank's partial sums.
+    Subjects whose factorisation failed (info != 0, NaN values) are counted, not summed."""
+    import torch
+    ok = (info == 0)
+    v = torch.where(ok.unsqueeze(1), vals, torch.zeros_like(vals))
+    out = torch.zeros(len(SUMMARY_FIELDS), dtype=torch.float64, device=vals.device)
+    out[:6] = v.sum(0)
+    out[6] = (~ok).sum().to(torch.float64)
+    out[7] = float(vals.shape[0])
+    return out
+
+
+def all_reduce_summary(summary, group=None):
+    """Sum the per-rank summaries over all ranks (in place) and return a dict.  No-op without a process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(summary, op=dist.ReduceOp.SUM, group=group)
+    return dict(zip(SUMMARY_FIELDS, summary.tolist()))

@@ -1,0 +1,85 @@
+"""GPU tests of the factorisation engines through the C ABI: unit potrf/potri against LAPACK (numpy), the two engines
+(right-looking tile tasks, left-looking/Takahashi) against each other, ragged sizes, failure reporting."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _spd(n, batch, seed, cond=1e3):
+    rng = np.random.RandomState(seed)
+    A = rng.standard_normal((batch, n, n))
+    S = A @ A.transpose(0, 2, 1) / n + np.eye(n) * (1.0 / cond) * 10
+    return S
+
+
+@pytest.mark.parametrize("n,batch", [(1, 3), (5, 2), (63, 2), (64, 3), (65, 2), (100, 4), (200, 5), (600, 2), (333, 3)])
+def test_unit_potrf_potri_match_lapack(n, batch, cuda_device):
+    from nonstationary_multivariate_gaussian_process_b200 import _lib
+    lib = _lib.load_library()
+    S = _spd(n, batch, n)
+    for invert in (False, True):
+        A = torch.from_numpy(S.copy()).cuda()
+        logdet = torch.empty(batch, dtype=torch.float64, device="cuda")
+        info = torch.empty(batch, dtype=torch.int32, device="cuda")
+        fn = lib.nmgp_potrf_potri_batched if invert else lib.nmgp_potrf_batched
+        _lib.check(fn(A.data_ptr(), n, batch, logdet.data_ptr(), info.data_ptr(), None), "potrf")
+        torch.cuda.synchronize()
+        assert int(info.abs().sum()) == 0
+        ref_ld = np.linalg.slogdet(S)[1]
+        assert np.allclose(logdet.cpu().numpy(), ref_ld, rtol=1e-12, atol=1e-10)
+        out = A.cpu().numpy()
+        if invert:
+            ref = np.linalg.inv(S)
+            assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-11
+            assert np.abs(out - out.transpose(0, 2, 1)).max() / np.abs(ref).max() < 1e-12
+        else:
+            ref = np.linalg.cholesky(S)
+            assert np.abs(np.tril(out) - ref).max() / np.abs(ref).max() < 1e-12
+            # strict upper triangle untouched
+            iu = np.triu_indices(n, 1)
+            assert np.array_equal(out[:, iu[0], iu[1]], S[:, iu[0], iu[1]])
+
+
+def test_unit_potrf_reports_failing_pivot(cuda_device):
+    from nonstationary_multivariate_gaussian_process_b200 import _lib
+    lib = _lib.load_library()
+    n = 100
+    S = _spd(n, 3, 1)
+    S[1, 70, 70] = -5.0   # not positive definite from pivot 71 at the latest
+    A = torch.from_numpy(S).cuda()
+    logdet = torch.empty(3, dtype=torch.float64, device="cuda")
+    info = torch.empty(3, dtype=torch.int32, device="cuda")
+    _lib.check(lib.nmgp_potrf_batched(A.data_ptr(), n, 3, logdet.data_ptr(), info.data_ptr(), None), "potrf")
+    torch.cuda.synchronize()
+    i = info.cpu().numpy()
+    assert i[0] == 0 and i[2] == 0 and 1 <= i[1] <= 71
+    assert np.isnan(logdet[1].item()) and np.isfinite(logdet[0].item())
+
+
+@pytest.mark.parametrize("N,M,S", [(100, 6, 5), (33, 5, 4), (21, 3, 3), (64, 2, 3), (75, 8, 2)])
+def test_left_and_right_looking_engines_agree(N, M, S, cuda_device):
+    from nonstationary_multivariate_gaussian_process_b200 import synth
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    hyper = {"mu_tilde_l": 0.0, "alpha_tilde_l": 10.0, "beta_tilde_l": 1.0, "mu_L": 0.0, "alpha_L": 1.0, "beta_L": 1.0,
+             "a": 1e-2, "b": 1e-2}
+    xs, Ys, ps = [], [], []
+    for s in range(S):
+        x, Y, _ = synth.sample_subject(N, M, 100 + s)
+        xs.append(x); Ys.append(Y); ps.append(synth.start_point("nonseparable", N, M, 100 + s, 0.05))
+    plan = LogPosteriorPlan("nonseparable", np.stack(xs), np.stack(Ys), hyper)
+    p = torch.from_numpy(np.stack(ps)).cuda()
+    res = {}
+    for mode in ("right", "left"):
+        plan.set_engine(mode)
+        v, g, i = plan.value_and_grad(p)
+        torch.cuda.synchronize()
+        assert int(i.abs().sum()) == 0
+        res[mode] = (v.cpu().numpy(), g.cpu().numpy())
+    dv = np.abs(res["left"][0][:, 1] - res["right"][0][:, 1]) / np.abs(res["right"][0][:, 1])
+    dg = np.linalg.norm(res["left"][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
+    assert dv.max() < 1e-12, dv
+    assert dg.max() < 1e-11, dg

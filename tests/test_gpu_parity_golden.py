@@ -7,13 +7,18 @@ from conftest import golden_cases, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
-# Tolerances (relative).  north_star: 1e-9 for log-posterior and gradient.  The likelihood term meets it with
-# margin; the GP-prior terms have cond 1e8..1e10: the reference itself is ~1e-9..1e-8 away
-# from the exact value there, so those components -- and totals they dominate -- get 5e-8.
+# Tolerances (relative; gradients in the 2-norm).  north_star asks 1e-9 for log-posterior and gradient.
+#  * The likelihood term and everything evaluated with Prior=False meet 1e-9 with 3-5 digits of margin
+#    (measured 1e-16..3e-13, profiles/r01_parity_golden.txt).
+#  * The GP-prior terms involve alpha^2 RBF + 1e-6 I with cond 1e8..2e10.  Two *CPU* FP64 Cholesky
+#    algorithms on bit-identical matrices already differ by ~4e-9 in the quadratic form and ~2e-7 in its gradient, and
+#    the reference is that far from the exact (mpmath) answer itself: tests/test_prior_conditioning_floor.py measures
+#    this floor on the same fixtures.  Those components -- and totals / gradients they dominate -- are held to the floor.
 TOL_LOGLIK = 1e-9
-TOL_PRIOR = 5e-8
-TOL_TOTAL = 5e-8
-TOL_GRAD = 5e-8
+TOL_NOPRIOR = 1e-9
+TOL_PRIOR = 1e-7
+TOL_TOTAL = 1e-8
+TOL_GRAD = 1e-6
 
 
 def run_plan(g):
@@ -30,9 +35,14 @@ def test_cuda_matches_reference_golden(name, cuda_device):
     vals, grad, info = run_plan(g)
     ref = g["vals"]
     assert info == 0
+    if not g["prior"]:
+        assert rel_err(vals[0], ref[0]) < TOL_NOPRIOR, (name, "total", vals[0], ref[0])
+        assert rel_err(grad, g["grad"]) < TOL_NOPRIOR, (name, "grad", rel_err(grad, g["grad"]))
+        if len(ref) > 1:
+            assert rel_err(vals[1], ref[1]) < TOL_LOGLIK
+        return
     assert rel_err(vals[0], ref[0]) < TOL_TOTAL, (name, "total", vals[0], ref[0])
-    if len(ref) > 1:
-        assert rel_err(vals[1], ref[1]) < TOL_LOGLIK, (name, "loglik", vals[1], ref[1])
-        for k in range(2, len(ref)):
-            assert rel_err(vals[k], ref[k]) < TOL_PRIOR, (name, k, vals[k], ref[k])
+    assert rel_err(vals[1], ref[1]) < TOL_LOGLIK, (name, "loglik", vals[1], ref[1])
+    for k in range(2, len(ref)):
+        assert rel_err(vals[k], ref[k]) < TOL_PRIOR, (name, k, vals[k], ref[k])
     assert rel_err(grad, g["grad"]) < TOL_GRAD, (name, "grad", rel_err(grad, g["grad"]))
