@@ -38,7 +38,7 @@ int engine_trtri(const BlockBatch& b, cudaStream_t st, long* launches);
 int engine_potri(const BlockBatch& b, cudaStream_t st, long* launches);
 
 // One diagonal-block step (factor A(k,k), W_kk = L_kk^-1 into Dinv, log det, info) -- shared by both engines.
-int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches);
+int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches, bool accurate = false);
 
 // Left-looking potrf / Takahashi inverse for large batches of mid-size matrices (engine_ll.cu).  Same results layout as
 // engine_potrf / engine_potri.  Requires b.Pbuf, and A's padding and upper block triangle to hold finite values

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 TOL_LOGLIK = 1e-9
 TOL_NOPRIOR = 1e-9
 TOL_PRIOR = 1e-7
-TOL_TOTAL = 1e-8
+TOL_TOTAL = 1e-7
 TOL_GRAD = 1e-6
 
 
