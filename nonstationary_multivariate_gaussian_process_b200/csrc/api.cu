@@ -103,7 +103,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   d += 2 * N * N;               // Kx, CK
   d += 2 * nm * n;              // alpha, yv
   d += pl->model == NMGP_NONSEPARABLE ? 2 * n * MT : 2 * N * M;  // Wout, Vout
-  d += 2 * N + M + M * M;       // gl, gs, lam, Vec
+  d += 2 * N + M + M * M + 2 * N * MT;  // gl, gs, lam, Vec, Sa, Ca
   d += 3 * (N + N * (size_t)pl->nv1);  // R, Z, G
   return d * sizeof(double) + nm * sizeof(int);
 }
@@ -134,6 +134,8 @@ int alloc_workspace(nmgp_plan* pl) {
   NMGP_TRY(dev_alloc(pl, &w.yv, svc ? 1 : cs * nm * n));
   NMGP_TRY(dev_alloc(pl, &w.Wout, svc ? cs * n * MT : cs * N * M));
   NMGP_TRY(dev_alloc(pl, &w.Vout, svc ? cs * n * MT : cs * N * M));
+  NMGP_TRY(dev_alloc(pl, &w.Sa, svc ? cs * N * MT : 1));
+  NMGP_TRY(dev_alloc(pl, &w.Ca, svc ? cs * N * MT : 1));
   NMGP_TRY(dev_alloc(pl, &w.gl, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.gs, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.lam, cs * M));

@@ -213,12 +213,15 @@ __global__ void svc_prep_kernel(const double* __restrict__ pars, int P, int N, i
   for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) R1[(long)c * N * T + idx] = p[N + idx] - mu1;
 }
 
-// Sigma = Kx[i,j] * L_i L_j^T + sigma2 I, time-major, lower block triangle of the padded layout
+// Sigma = Kx[i,j] * L_i L_j^T + sigma2 I, time-major, lower block triangle of the padded layout.
+// One CTA per 64x64 tile; a warp writes one tile row as 32 double2 (512 B, coalesced); the factor rows of the tile's
+// columns sit k-major in shared memory so the M-term dot products read it conflict-free.  Memory-bound on the stores.
+template <int M>
 __global__ void __launch_bounds__(256) svc_build_kernel(const double* __restrict__ Kx, const double* __restrict__ Lst,
-                                                        const double* __restrict__ s2v, int N, int M, int MT,
-                                                        double* A, long strideA, int ld) {
-  __shared__ double Lr[NB * 16];
-  __shared__ double Lc[NB * 16];
+                                                        const double* __restrict__ s2v, int N, int MT, double* A,
+                                                        long strideA, int ld) {
+  __shared__ double Lr[NB][M];
+  __shared__ __align__(16) double LcT[M][NB];
   int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
   while ((long)ti * (ti + 1) / 2 > (long)blockIdx.x) --ti;
   while ((long)(ti + 1) * (ti + 2) / 2 <= (long)blockIdx.x) ++ti;
@@ -227,29 +230,39 @@ __global__ void __launch_bounds__(256) svc_build_kernel(const double* __restrict
   const int n = N * M;
   const int p0 = ti * NB, q0 = tj * NB;
   const double* Ls = Lst + (long)c * n * MT;
-  for (int idx = threadIdx.x; idx < NB * MT; idx += 256) {
-    const int r = idx / MT, k = idx % MT;
-    Lr[idx] = (p0 + r < n) ? Ls[(long)(p0 + r) * MT + k] : 0.0;
-    Lc[idx] = (q0 + r < n) ? Ls[(long)(q0 + r) * MT + k] : 0.0;
+  for (int idx = threadIdx.x; idx < NB * M; idx += 256) {
+    const int r = idx / M, k = idx % M;
+    Lr[r][k] = (p0 + r < n) ? Ls[(long)(p0 + r) * MT + k] : 0.0;
+    LcT[k][r] = (q0 + r < n) ? Ls[(long)(q0 + r) * MT + k] : 0.0;
   }
   __syncthreads();
   const double s2 = s2v[c];
   const double* Kc = Kx + (long)c * N * N;
   double* Ac = A + (long)c * strideA;
-  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
-    const int r = idx / NB, cc = idx % NB;
-    const int p = p0 + r, q = q0 + cc;
-    double v;
-    if (p < n && q < n) {
-      const int i = p / M, j = q / M;
-      double dot = 0.0;
-      for (int k = 0; k < M; ++k) dot += Lr[r * MT + k] * Lc[cc * MT + k];
-      v = Kc[(long)i * N + j] * dot;
-      if (p == q) v += s2;
-    } else {
-      v = (p == q) ? 1.0 : 0.0;
+#pragma unroll
+  for (int it = 0; it < (NB * NB / 2) / 256; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    const int r = idx >> 5, c2 = idx & 31;
+    const int p = p0 + r, q = q0 + 2 * c2;
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double lr = Lr[r][k];
+      const double2 lc = *reinterpret_cast<const double2*>(&LcT[k][2 * c2]);
+      d0 += lr * lc.x;
+      d1 += lr * lc.y;
     }
-    Ac[(long)p * ld + q] = v;
+    double2 v;
+    if (p < n) {
+      const int i = p / M;
+      const double* krow = Kc + (long)i * N;
+      v.x = (q < n) ? krow[q / M] * d0 + (p == q ? s2 : 0.0) : 0.0;
+      v.y = (q + 1 < n) ? krow[(q + 1) / M] * d1 + (p == q + 1 ? s2 : 0.0) : 0.0;
+    } else {
+      v.x = (p == q) ? 1.0 : 0.0;
+      v.y = (p == q + 1) ? 1.0 : 0.0;
+    }
+    *reinterpret_cast<double2*>(Ac + (long)p * ld + q) = v;
   }
 }
 
@@ -281,53 +294,135 @@ __global__ void svc_cov_reference_order_kernel(const double* __restrict__ x, con
   out[((long)c * n + p) * n + q] = v;
 }
 
-// One pass over Sigma^-1: for every row p=(i,m)
-//   Wout[p][k] = sum_q Kx[i,j] G[p,q] Lst[q][k],   Vout[p][k] = sum_q CK[i,j] G[p,q] Lst[q][k],
-// with G = -0.5 Sigma^-1 + 0.5 alpha alpha^T (never materialised).  One warp per row, lanes stride the columns.
-template <int MT>
+// The gradient needs  W[p][k] = sum_q Kx[i,j] G[p,q] L_j[m'][k]  and  V[p][k] = sum_q CK[i,j] G[p,q] L_j[m'][k]
+// (p=(i,m), q=(j,m')) with G = -0.5 Sigma^-1 + 0.5 alpha alpha^T.  G is never formed: the Sigma^-1 part is ONE pass over
+// the inverse that also produces alpha = Sigma^-1 y (so the inverse is read exactly once); the rank-one part is an
+// O(N^2 M) correction (svc_alpha_terms_kernel).  One warp per row, lanes over the time blocks j: a lane reads the M
+// contiguous entries of block (p, j), the factor L_j from shared memory (odd stride: conflict-free), Kx/CK once per block.
+template <int M>
 __global__ void __launch_bounds__(256) svc_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N,
-                                                           int M, const double* __restrict__ alpha,
-                                                           const double* __restrict__ Kx, const double* __restrict__ CK,
-                                                           const double* __restrict__ Lst, double* __restrict__ Wout,
+                                                           int MT, int JC, int rows_per_warp,
+                                                           const double* __restrict__ Y, const double* __restrict__ Kx,
+                                                           const double* __restrict__ CK, const double* __restrict__ Lst,
+                                                           double* __restrict__ alpha, double* __restrict__ Wout,
                                                            double* __restrict__ Vout) {
+  extern __shared__ __align__(16) double Lsm[];   // [JC][LS]
+  constexpr int LS = (M * M) | 1;
   const int c = blockIdx.y;
   const int n = N * M;
-  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* Ls = Lst + (long)c * n * MT;
+  const double* y = Y + (long)c * n;
+  const int nch = (N + JC - 1) / JC;
+  auto stage = [&](int ch) {
+    const int j0 = ch * JC, jn = min(JC, N - j0);
+    for (int idx = threadIdx.x; idx < jn * M * M; idx += 256) {
+      const int k = idx % M, m2 = (idx / M) % M, jj = idx / (M * M);
+      Lsm[jj * LS + m2 * M + k] = Ls[((long)(j0 + jj) * M + m2) * MT + k];
+    }
+  };
+  if (nch == 1) { stage(0); __syncthreads(); }
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int p = (blockIdx.x * 8 + warp) * rows_per_warp + rr;
+    const bool valid = p < n;
+    const int i = valid ? p / M : 0;
+    const double* row = A + (long)c * strideA + (long)(valid ? p : 0) * ld;
+    const double* kr = Kx + ((long)c * N + i) * N;
+    const double* cr = CK + ((long)c * N + i) * N;
+    double aacc = 0.0, w[M], v[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) w[k] = v[k] = 0.0;
+    for (int ch = 0; ch < nch; ++ch) {
+      if (nch > 1) { __syncthreads(); stage(ch); __syncthreads(); }
+      if (!valid) continue;
+      const int j0 = ch * JC, jn = min(JC, N - j0);
+      for (int jj = lane; jj < jn; jj += 32) {
+        const int j = j0 + jj;
+        double sv[M], qv[M];
+#pragma unroll
+        for (int m2 = 0; m2 < M; ++m2) {
+          sv[m2] = row[j * M + m2];
+          aacc += sv[m2] * y[j * M + m2];
+        }
+        const double* lj = Lsm + jj * LS;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          double t = 0.0;
+#pragma unroll
+          for (int m2 = k; m2 < M; ++m2) t += sv[m2] * lj[m2 * M + k];   // L_j is lower triangular
+          qv[k] = t;
+        }
+        const double kx = kr[j], ck = cr[j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          w[k] += kx * qv[k];
+          v[k] += ck * qv[k];
+        }
+      }
+    }
+    aacc = warp_sum(aacc);
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      w[k] = warp_sum(w[k]);
+      v[k] = warp_sum(v[k]);
+    }
+    if (valid && lane == 0) {
+      alpha[(long)c * n + p] = aacc;
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        Wout[((long)c * n + p) * MT + k] = w[k];
+        Vout[((long)c * n + p) * MT + k] = v[k];
+      }
+    }
+  }
+}
+
+// rank-one part:  Sa[i][k] = sum_j Kx[i,j] u_j[k],  Ca[i][k] = sum_j CK[i,j] u_j[k],  u_j = L_j^T alpha_j   (one warp per i)
+template <int M>
+__global__ void __launch_bounds__(256) svc_alpha_terms_kernel(int N, int MT, const double* __restrict__ alpha,
+                                                              const double* __restrict__ Kx,
+                                                              const double* __restrict__ CK,
+                                                              const double* __restrict__ Lst, double* __restrict__ Sa,
+                                                              double* __restrict__ Ca) {
+  const int c = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (p >= n) return;
-  const int i = p / M;
-  const double* row = A + (long)c * strideA + (long)p * ld;
+  if (i >= N) return;
+  const int n = N * M;
   const double* al = alpha + (long)c * n;
+  const double* Ls = Lst + (long)c * n * MT;
   const double* kr = Kx + ((long)c * N + i) * N;
   const double* cr = CK + ((long)c * N + i) * N;
-  const double* Ls = Lst + (long)c * n * MT;
-  const double ap = al[p];
-  const float invM = 1.0f / (float)M;
-  double w[MT], v[MT];
+  double sa[M], ca[M];
 #pragma unroll
-  for (int k = 0; k < MT; ++k) w[k] = v[k] = 0.0;
-  for (int q = lane; q < n; q += 32) {
-    int j = (int)(((float)q + 0.5f) * invM);
-    const double g = -0.5 * row[q] + 0.5 * ap * al[q];
-    const double gk = g * kr[j], gc = g * cr[j];
-    const double* lq = Ls + (long)q * MT;
+  for (int k = 0; k < M; ++k) sa[k] = ca[k] = 0.0;
+  for (int j = lane; j < N; j += 32) {
+    double u[M];
 #pragma unroll
-    for (int k = 0; k < MT; ++k) {
-      const double l = lq[k];
-      w[k] += gk * l;
-      v[k] += gc * l;
+    for (int k = 0; k < M; ++k) u[k] = 0.0;
+#pragma unroll
+    for (int m2 = 0; m2 < M; ++m2) {
+      const double a = al[j * M + m2];
+#pragma unroll
+      for (int k = 0; k <= m2; ++k) u[k] += a * Ls[((long)j * M + m2) * MT + k];
+    }
+    const double kx = kr[j], ck = cr[j];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      sa[k] += kx * u[k];
+      ca[k] += ck * u[k];
     }
   }
 #pragma unroll
-  for (int k = 0; k < MT; ++k) {
-    w[k] = warp_sum(w[k]);
-    v[k] = warp_sum(v[k]);
+  for (int k = 0; k < M; ++k) {
+    sa[k] = warp_sum(sa[k]);
+    ca[k] = warp_sum(ca[k]);
   }
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < MT; ++k) {
-      Wout[((long)c * n + p) * MT + k] = w[k];
-      Vout[((long)c * n + p) * MT + k] = v[k];
+    for (int k = 0; k < M; ++k) {
+      Sa[((long)c * N + i) * MT + k] = sa[k];
+      Ca[((long)c * N + i) * MT + k] = ca[k];
     }
   }
 }
@@ -337,6 +432,7 @@ __global__ void __launch_bounds__(256) svc_finish_kernel(
     const double* __restrict__ A, long strideA, int ld, const double* __restrict__ logdet,
     const int* __restrict__ info_in, const double* __restrict__ alpha, const double* __restrict__ s2v,
     const double* __restrict__ Lst, const double* __restrict__ Wout, const double* __restrict__ Vout,
+    const double* __restrict__ Sa, const double* __restrict__ Ca,
     const double* __restrict__ Z0, const double* __restrict__ Z1, const double* __restrict__ G0,
     const double* __restrict__ G1, const double* __restrict__ hld0, const double* __restrict__ hld1,
     double* __restrict__ vals, double* __restrict__ grad, int* __restrict__ info) {
@@ -383,8 +479,12 @@ __global__ void __launch_bounds__(256) svc_finish_kernel(
   const double* Vc = Vout + (long)c * n * MT;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     double s = 0.0;
-    for (int m = 0; m < M; ++m)
-      for (int k = 0; k <= m; ++k) s += Ls[((long)i * M + m) * MT + k] * Vc[((long)i * M + m) * MT + k];
+    for (int m = 0; m < M; ++m) {
+      const double ap = al[i * M + m];
+      for (int k = 0; k <= m; ++k)
+        s += Ls[((long)i * M + m) * MT + k] *
+             (-0.5 * Vc[((long)i * M + m) * MT + k] + 0.5 * ap * Ca[((long)c * N + i) * MT + k]);
+    }
     g[i] = -(2.0 * s - pf * G0[(long)c * N + i]);
   }
   for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) {
@@ -393,7 +493,7 @@ __global__ void __launch_bounds__(256) svc_finish_kernel(
     while (m * (m + 1) / 2 > t) --m;
     while ((m + 1) * (m + 2) / 2 <= t) ++m;
     const int k = t - m * (m + 1) / 2;
-    double d = 2.0 * Wc[((long)i * M + m) * MT + k];
+    double d = -Wc[((long)i * M + m) * MT + k] + al[i * M + m] * Sa[((long)c * N + i) * MT + k];
     if (k == m) d *= Ls[((long)i * M + m) * MT + m];                   // d exp(u)/du on the diagonal slots
     g[N + idx] = -(d - pf * G1[(long)c * N * T + idx]);
   }
@@ -720,6 +820,8 @@ int padded_M(int M) {
   return -1;
 }
 
+#define NMGP_FOR_EACH_M(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
 #define NMGP_LAUNCH_CHECK()                 \
   do {                                      \
     NMGP_CUDA_TRY(cudaGetLastError());      \
@@ -795,14 +897,11 @@ int svc_forward(int cs, int N, int M, const double* x, const double* pars, int P
   kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, nullptr, N, w.Kx, w.CK);
   NMGP_LAUNCH_CHECK();
   dim3 gb(b.Kt * (b.Kt + 1) / 2, cs);
-  svc_build_kernel<<<gb, 256, 0, st>>>(w.Kx, w.Lst, w.s2, N, M, MT, b.A, b.strideA(), b.nP);
+#define NMGP_BUILD_CASE(MM) case MM: svc_build_kernel<MM><<<gb, 256, 0, st>>>(w.Kx, w.Lst, w.s2, N, MT, b.A, b.strideA(), b.nP); break;
+  switch (M) { NMGP_FOR_EACH_M(NMGP_BUILD_CASE) default: set_last_error("M out of range"); return -1; }
+#undef NMGP_BUILD_CASE
   NMGP_LAUNCH_CHECK();
   return 0;
-}
-
-template <int MT>
-static void launch_svc_contract(dim3 grid, cudaStream_t st, const BlockBatch& b, int N, int M, const Scratch& w) {
-  svc_contract_kernel<MT><<<grid, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, w.alpha, w.Kx, w.CK, w.Lst, w.Wout, w.Vout);
 }
 
 int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int P, const HyperConst& h,
@@ -810,25 +909,26 @@ int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int 
                  double* grad, int* info, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   const int n = N * M, MT = padded_M(M);
-  dim3 gs((n + 7) / 8, cs);
-  symv_kernel<<<gs, 256, 0, st>>>(b.A, b.strideA(), b.nP, n, Y, w.alpha);
+  // one pass over Sigma^-1: alpha and the Sigma^-1 part of the gradient sums
+  const int LS = (M * M) | 1;
+  int JC = 6144 / LS;
+  if (JC > N) JC = N;
+  const int rpw = (JC >= N) ? 4 : 1;
+  dim3 gc((n + 8 * rpw - 1) / (8 * rpw), cs);
+  const size_t smem = (size_t)JC * LS * sizeof(double);
+#define NMGP_CONTRACT_CASE(MM) case MM: svc_contract_kernel<MM><<<gc, 256, smem, st>>>(b.A, b.strideA(), b.nP, N, MT, JC, rpw, Y, w.Kx, w.CK, w.Lst, w.alpha, w.Wout, w.Vout); break;
+  switch (M) { NMGP_FOR_EACH_M(NMGP_CONTRACT_CASE) default: set_last_error("M out of range"); return -1; }
+#undef NMGP_CONTRACT_CASE
   NMGP_LAUNCH_CHECK();
   if (grad != nullptr) {
-    switch (MT) {
-      case 2: launch_svc_contract<2>(gs, st, b, N, M, w); break;
-      case 3: launch_svc_contract<3>(gs, st, b, N, M, w); break;
-      case 4: launch_svc_contract<4>(gs, st, b, N, M, w); break;
-      case 5: launch_svc_contract<5>(gs, st, b, N, M, w); break;
-      case 6: launch_svc_contract<6>(gs, st, b, N, M, w); break;
-      case 8: launch_svc_contract<8>(gs, st, b, N, M, w); break;
-      case 10: launch_svc_contract<10>(gs, st, b, N, M, w); break;
-      case 12: launch_svc_contract<12>(gs, st, b, N, M, w); break;
-      default: launch_svc_contract<16>(gs, st, b, N, M, w); break;
-    }
+    dim3 ga((N + 7) / 8, cs);
+#define NMGP_ALPHA_CASE(MM) case MM: svc_alpha_terms_kernel<MM><<<ga, 256, 0, st>>>(N, MT, w.alpha, w.Kx, w.CK, w.Lst, w.Sa, w.Ca); break;
+    switch (M) { NMGP_FOR_EACH_M(NMGP_ALPHA_CASE) default: break; }
+#undef NMGP_ALPHA_CASE
     NMGP_LAUNCH_CHECK();
   }
   svc_finish_kernel<<<cs, 256, 0, st>>>(N, M, MT, P, pars, Y, h, b.A, b.strideA(), b.nP, b.logdet, b.info, w.alpha, w.s2,
-                                        w.Lst, w.Wout, w.Vout, w.Z0, w.Z1, w.G0, w.G1, hld0, hld1, vals, grad, info);
+                                        w.Lst, w.Wout, w.Vout, w.Sa, w.Ca, w.Z0, w.Z1, w.G0, w.G1, hld0, hld1, vals, grad, info);
   NMGP_LAUNCH_CHECK();
   return 0;
 }

@@ -31,6 +31,8 @@ struct Scratch {
   double* yv;     // [cs][nmat][n]   right-hand sides (nonseparable: Y itself is used instead)
   double* Wout;   // nonseparable [cs][n][MT];  separable: rowSK [cs][N][M]
   double* Vout;   // nonseparable [cs][n][MT];  separable: KA    [cs][N][M]
+  double* Sa;     // nonseparable [cs][N][MT]  rank-one (alpha alpha^T) part of the gradient sums, Kx-weighted
+  double* Ca;     // nonseparable [cs][N][MT]  same, CK-weighted
   double* gl;     // separable [cs][N]   sum_j GK_ij CK_ij
   double* gs;     // separable [cs][N]   sum_j GK_ij K0_ij
   double* lam;    // separable [cs][M]
