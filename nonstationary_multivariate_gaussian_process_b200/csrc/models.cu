@@ -92,65 +92,94 @@ __global__ void extract_factor_kernel(const double* __restrict__ A, long strideA
   Lp[((long)c * N + p) * N + q] = (q <= p) ? A[(long)c * strideA + (long)p * ld + q] : 0.0;
 }
 
-// Triangular solves with the cached prior factor, nv right-hand sides per subject, by blocked substitution
-// (the arithmetic MultivariateNormal.log_prob and its autograd backward do: logpos.py:274,279,358,365):
-//   TRANS=0:  L   X = rhs   (forward)        TRANS=1:  L^T X = rhs   (backward)
-// One CTA per (subject, chunk of 32 right-hand sides); 32-row blocks: GEMM-like update from the already solved
-// part, then a 32x32 substitution with one thread per right-hand side.
+// Triangular solves with the cached prior factor, nv right-hand sides per subject, by blocked (64-row) right-looking
+// substitution -- the arithmetic MultivariateNormal.log_prob and its autograd backward do (logpos.py:274,279,358,365):
+//   TRANS=0:  L   X = rhs   (forward, blocks ascending)        TRANS=1:  L^T X = rhs   (backward, blocks descending)
+// Two kernels per block step, both batched over subjects, so a single large subject still spreads over the GPU:
+//   prior_diag_solve : X_k <- L_kk^-1 X_k  (or L_kk^-T)   one thread per right-hand side, L_kk in shared memory
+//   prior_update     : X_i <- X_i - L(i,k) X_k  for all i > k   (or  X_i - L(k,i)^T X_k, i < k)   one CTA per row block
+constexpr int PBS = 64;   // block rows
+constexpr int PVC = 24;   // right-hand sides per CTA (static shared memory stays under 48 KB)
+
 template <int TRANS>
-__global__ void __launch_bounds__(256) prior_solve_kernel(const double* __restrict__ Lp, const double* __restrict__ rhs,
-                                                          double* out, int N, int nv) {
-  constexpr int BS = 32;
-  __shared__ double Ld[BS][BS + 1];
-  __shared__ double Zb[BS][BS + 1];
+__global__ void __launch_bounds__(128) prior_diag_solve_kernel(const double* __restrict__ Lp, double* X, int N, int nv,
+                                                               int k0) {
+  __shared__ double Ld[PBS][PBS + 1];
+  __shared__ double Zb[PBS][PVC + 1];
   const int c = blockIdx.x;
-  const int v0 = blockIdx.y * BS;
-  const int vc = min(BS, nv - v0);
+  const int v0 = blockIdx.y * PVC;
+  const int vc = min(PVC, nv - v0);
+  const int rows = min(PBS, N - k0);
   const double* L = Lp + (long)c * N * N;
-  const double* R = rhs + (long)c * N * nv;
-  double* X = out + (long)c * N * nv;
-  const int nblk = (N + BS - 1) / BS;
-  for (int bk = 0; bk < nblk; ++bk) {
-    const int k0 = TRANS ? (nblk - 1 - bk) * BS : bk * BS;
-    const int rows = min(BS, N - k0);
-    for (int idx = threadIdx.x; idx < rows * vc; idx += 256) {
-      const int r = idx / vc, v = idx % vc;
-      double acc = R[(long)(k0 + r) * nv + v0 + v];
-      if (TRANS) {
-        for (int j = k0 + rows; j < N; ++j) acc -= L[(long)j * N + k0 + r] * X[(long)j * nv + v0 + v];
-      } else {
-        const double* lrow = L + (long)(k0 + r) * N;
-        for (int j = 0; j < k0; ++j) acc -= lrow[j] * X[(long)j * nv + v0 + v];
+  double* Xc = X + (long)c * N * nv;
+  for (int idx = threadIdx.x; idx < rows * rows; idx += 128) {
+    const int r = idx / rows, cc = idx % rows;
+    Ld[r][cc] = L[(long)(k0 + r) * N + k0 + cc];
+  }
+  for (int idx = threadIdx.x; idx < rows * vc; idx += 128) {
+    const int r = idx / vc, v = idx % vc;
+    Zb[r][v] = Xc[(long)(k0 + r) * nv + v0 + v];
+  }
+  __syncthreads();
+  if (threadIdx.x < vc) {
+    const int v = threadIdx.x;
+    if (TRANS) {
+      for (int r = rows - 1; r >= 0; --r) {
+        double sacc = Zb[r][v];
+        for (int cc = r + 1; cc < rows; ++cc) sacc -= Ld[cc][r] * Zb[cc][v];
+        Zb[r][v] = sacc / Ld[r][r];
       }
-      Zb[r][v] = acc;
-    }
-    for (int idx = threadIdx.x; idx < rows * rows; idx += 256) {
-      const int r = idx / rows, cc = idx % rows;
-      Ld[r][cc] = L[(long)(k0 + r) * N + k0 + cc];
-    }
-    __syncthreads();
-    if (threadIdx.x < vc) {
-      const int v = threadIdx.x;
-      if (TRANS) {
-        for (int r = rows - 1; r >= 0; --r) {
-          double sacc = Zb[r][v];
-          for (int cc = r + 1; cc < rows; ++cc) sacc -= Ld[cc][r] * Zb[cc][v];
-          Zb[r][v] = sacc / Ld[r][r];
-        }
-      } else {
-        for (int r = 0; r < rows; ++r) {
-          double sacc = Zb[r][v];
-          for (int cc = 0; cc < r; ++cc) sacc -= Ld[r][cc] * Zb[cc][v];
-          Zb[r][v] = sacc / Ld[r][r];
-        }
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        double sacc = Zb[r][v];
+        for (int cc = 0; cc < r; ++cc) sacc -= Ld[r][cc] * Zb[cc][v];
+        Zb[r][v] = sacc / Ld[r][r];
       }
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < rows * vc; idx += 256) {
-      const int r = idx / vc, v = idx % vc;
-      X[(long)(k0 + r) * nv + v0 + v] = Zb[r][v];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < rows * vc; idx += 128) {
+    const int r = idx / vc, v = idx % vc;
+    Xc[(long)(k0 + r) * nv + v0 + v] = Zb[r][v];
+  }
+}
+
+template <int TRANS>
+__global__ void __launch_bounds__(256) prior_update_kernel(const double* __restrict__ Lp, double* X, int N, int nv,
+                                                           int k0) {
+  __shared__ double Lt[PBS][PBS + 1];   // Lt[r][k]: coefficient of X_k[k] in row r of the target block
+  __shared__ double Zk[PBS][PVC + 1];
+  const int c = blockIdx.x;
+  const int v0 = blockIdx.z * PVC;
+  const int vc = min(PVC, nv - v0);
+  const int krows = min(PBS, N - k0);
+  // target block i: forward -> blocks after k; backward -> blocks before k
+  const int i0 = TRANS ? blockIdx.y * PBS : k0 + PBS + blockIdx.y * PBS;
+  const int irows = min(PBS, (TRANS ? k0 : N) - i0);
+  const double* L = Lp + (long)c * N * N;
+  double* Xc = X + (long)c * N * nv;
+  for (int idx = threadIdx.x; idx < PBS * PBS; idx += 256) {
+    double v = 0.0;
+    if (TRANS) {   // L(k,i)^T : Lt[r][k] = L[k0+k][i0+r]; read with r fastest (coalesced)
+      const int kk = idx / PBS, r = idx % PBS;
+      if (kk < krows && r < irows) v = L[(long)(k0 + kk) * N + i0 + r];
+      Lt[r][kk] = v;
+    } else {       // L(i,k)   : Lt[r][k] = L[i0+r][k0+k]
+      const int r = idx / PBS, kk = idx % PBS;
+      if (kk < krows && r < irows) v = L[(long)(i0 + r) * N + k0 + kk];
+      Lt[r][kk] = v;
     }
-    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < krows * vc; idx += 256) {
+    const int r = idx / vc, v = idx % vc;
+    Zk[r][v] = Xc[(long)(k0 + r) * nv + v0 + v];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < irows * vc; idx += 256) {
+    const int r = idx / vc, v = idx % vc;
+    double acc = 0.0;
+    for (int kk = 0; kk < krows; ++kk) acc += Lt[r][kk] * Zk[kk][v];
+    Xc[(long)(i0 + r) * nv + v0 + v] -= acc;
   }
 }
 
@@ -870,10 +899,24 @@ int launch_extract_factor(const BlockBatch& b, int N, double* Lp, double* hld, c
 int launch_prior_solve(const double* Lp, const double* rhs, double* out, int cs, int N, int nv, int trans,
                        cudaStream_t st, long* launches) {
   if (cs <= 0 || nv <= 0) return 0;
-  dim3 grid(cs, (nv + 31) / 32);
-  if (trans) prior_solve_kernel<1><<<grid, 256, 0, st>>>(Lp, rhs, out, N, nv);
-  else prior_solve_kernel<0><<<grid, 256, 0, st>>>(Lp, rhs, out, N, nv);
-  NMGP_LAUNCH_CHECK();
+  NMGP_CUDA_TRY(cudaMemcpyAsync(out, rhs, (size_t)cs * N * nv * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  const int nblk = (N + PBS - 1) / PBS;
+  const int nvc = (nv + PVC - 1) / PVC;
+  for (int bk = 0; bk < nblk; ++bk) {
+    const int kb = trans ? nblk - 1 - bk : bk;
+    const int k0 = kb * PBS;
+    dim3 gd(cs, nvc);
+    if (trans) prior_diag_solve_kernel<1><<<gd, 128, 0, st>>>(Lp, out, N, nv, k0);
+    else prior_diag_solve_kernel<0><<<gd, 128, 0, st>>>(Lp, out, N, nv, k0);
+    NMGP_LAUNCH_CHECK();
+    const int others = trans ? kb : nblk - 1 - kb;
+    if (others > 0) {
+      dim3 gu(cs, others, nvc);
+      if (trans) prior_update_kernel<1><<<gu, 256, 0, st>>>(Lp, out, N, nv, k0);
+      else prior_update_kernel<0><<<gu, 256, 0, st>>>(Lp, out, N, nv, k0);
+      NMGP_LAUNCH_CHECK();
+    }
+  }
   return 0;
 }
 

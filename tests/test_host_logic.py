@@ -1,0 +1,93 @@
+"""CPU-only tests of the host-side mirror of the reference interface: parameter slicing and transforms
+(Utility/logpos.py:17-57, Utility/utils.py:10-88), hyper-parameter marshalling, subject partitioning, the synthetic
+generator against the oracle's covariance."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nmgp_oracle as O
+from nonstationary_multivariate_gaussian_process_b200 import batched, logpos, sharding, synth, utils
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 6, 10])
+def test_uL_transforms_round_trip_and_match_oracle(M):
+    T = M * (M + 1) // 2
+    rng = np.random.RandomState(M)
+    u = rng.standard_normal(T)
+    L = utils.uLvec2Lvec(u, M)
+    assert np.allclose(utils.Lvec2uLvec(L, M), u, rtol=0, atol=1e-14)
+    Lt = utils.uLvec2Lvec(torch.from_numpy(u), M)
+    assert torch.equal(Lt, O.unconstrained_to_tril_vec(torch.from_numpy(u), M))
+    mat = utils.vec2lowtriangle(Lt, M)
+    assert torch.equal(mat, O.tril_vec_to_matrix(Lt, M))
+    assert torch.equal(utils.lowtriangle2vec(mat, M), Lt)
+    # diagonal slots are cumsum(1..M)-1 (utils.py:12)
+    d = np.cumsum(np.arange(1, M + 1)) - 1
+    assert np.all(np.asarray(L)[d] > 0)
+    N = 4
+    us = rng.standard_normal(N * T)
+    assert np.allclose(utils.Lvecs2uLvecs(utils.uLvecs2Lvecs(us, N, M), N, M), us, atol=1e-14)
+
+
+def test_vec2lowtriangle_checks_size():
+    with pytest.raises(ValueError):
+        utils.vec2lowtriangle(np.zeros(5), 3)
+
+
+def test_parameter_slicing_matches_reference_layout():
+    N, M = 7, 3
+    T = 6
+    p = torch.arange(2 * N + T + 1, dtype=torch.float64)
+    tl, ts, uL, e = logpos.vec2pars(p, N, M)
+    assert tl.tolist() == list(range(N)) and ts.tolist() == list(range(N, 2 * N))
+    assert uL.tolist() == list(range(2 * N, 2 * N + T)) and float(e) == 2 * N + T
+    p = torch.arange(N + N * T + 1, dtype=torch.float64)
+    tl, uLs, e = logpos.vec2pars_SVC(p, N, M)
+    assert uLs.numel() == N * T and float(uLs[0]) == N and float(e) == N + N * T
+    p = torch.arange(T + 3, dtype=torch.float64)
+    tl, ts, uL, e = logpos.vec2pars_S(p, M)
+    assert float(tl) == 0 and float(ts) == 1 and uL.numel() == T and float(e) == T + 2
+    for model in ("stationary", "separable", "nonseparable"):
+        assert batched.n_params(model, N, M) == O.n_params(model, N, M)
+
+
+def test_hyper_vector_order_defaults_and_errors():
+    v = batched.hyper_vector("nonseparable", {"alpha_L": 1.0, "a": 1e-2})
+    assert v.tolist() == [0.0, 5.0, 1.0, 0.0, 1.0, 1.0, 1e-2, 1.0, 0.0]     # logpos.py:299 defaults
+    v = batched.hyper_vector("separable", {})
+    assert v.tolist() == [0.0, 1.0, 1.0, 0.0, 1.0, 1.0, 1.0, 1.0, 10.0]      # logpos.py:216 defaults
+    with pytest.raises(TypeError):
+        batched.hyper_vector("stationary", {"a": 1})                         # mu_tilde_l / sigma_tilde_l are required
+    with pytest.raises(TypeError):
+        batched.hyper_vector("nonseparable", {"c": 3})                       # not a keyword of nlogpos_obj_SVC
+
+
+@pytest.mark.parametrize("S,world", [(10000, 8), (10, 3), (5, 8), (0, 2), (256, 8)])
+def test_shard_range_partitions_subjects(S, world):
+    spans = [sharding.shard_range(S, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == S
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(S, world, world)
+
+
+def test_local_summary_counts_failures_instead_of_summing_them():
+    vals = torch.tensor([[1.0, 2, 3, 4, 5, 6], [float("nan")] * 6, [10.0, 20, 30, 40, 50, 60]], dtype=torch.float64)
+    info = torch.tensor([0, 17, 0], dtype=torch.int32)
+    s = sharding.local_summary(vals, info)
+    assert s.tolist() == [11.0, 22.0, 33.0, 44.0, 55.0, 66.0, 1.0, 3.0]
+    assert sharding.all_reduce_summary(s)["n_failed"] == 1.0                 # no process group: identity
+
+
+def test_synthetic_covariance_matches_oracle_up_to_the_ordering_permutation():
+    N, M = 9, 3
+    x, tl, uL, ts2 = synth.truth(N, M, 3)
+    K_tm = synth.dense_cov_time_major(x, tl, uL, M)
+    K_om = O.nonseparable_cov(torch.from_numpy(x), torch.from_numpy(tl), torch.from_numpy(uL.reshape(-1)), M).numpy()
+    perm = np.arange(N * M).reshape(N, M).T.reshape(-1)      # output-major position -> time-major index
+    assert np.allclose(K_tm[np.ix_(perm, perm)], K_om, rtol=1e-13, atol=1e-15)
+    assert np.all(np.diff(x) > 0) and x.min() > 0 and x.max() < 1
+    xs, Y, pars = synth.sample_subject(N, M, 3)
+    assert Y.shape == (N, M) and pars.shape == (O.n_params("nonseparable", N, M),)
