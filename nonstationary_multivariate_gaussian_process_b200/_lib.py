@@ -14,10 +14,10 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
-SOURCES = ["engine.cu", "engine_ll.cu", "models.cu", "api.cu"]
+SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "api.cu"]
 HEADERS = ["common.cuh", "engine.cuh", "models.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 NVALS = 6
 NHYPER = 9
@@ -46,12 +46,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise NmgpError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:      # one nvcc per translation unit, in parallel
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise NmgpError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise NmgpError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -41,6 +41,9 @@ struct nmgp_plan {
   // staging for the host-buffer call
   double *pars_d = nullptr, *vals_d = nullptr, *grad_d = nullptr;
   int* info_d = nullptr;
+  // side stream: the GP-prior triangular solves are independent of the factorisation and run beside it
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -103,7 +106,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   d += 2 * N * N;               // Kx, CK
   d += 2 * nm * n;              // alpha, yv
   d += pl->model == NMGP_NONSEPARABLE ? 2 * n * MT : 2 * N * M;  // Wout, Vout
-  d += 2 * N + M + M * M + 2 * N * MT;  // gl, gs, lam, Vec, Sa, Ca
+  d += 2 * N + M + M * M + 3 * N * MT;  // gl, gs, lam, Vec, Sa, Ca, Ua
   d += 3 * (N + N * (size_t)pl->nv1);  // R, Z, G
   return d * sizeof(double) + nm * sizeof(int);
 }
@@ -136,6 +139,7 @@ int alloc_workspace(nmgp_plan* pl) {
   NMGP_TRY(dev_alloc(pl, &w.Vout, svc ? cs * n * MT : cs * N * M));
   NMGP_TRY(dev_alloc(pl, &w.Sa, svc ? cs * N * MT : 1));
   NMGP_TRY(dev_alloc(pl, &w.Ca, svc ? cs * N * MT : 1));
+  NMGP_TRY(dev_alloc(pl, &w.Ua, svc ? cs * N * MT : 1));
   NMGP_TRY(dev_alloc(pl, &w.gl, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.gs, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.lam, cs * M));
@@ -252,6 +256,9 @@ int nmgp_n_params(int model, int N, int M) {
 int nmgp_plan_destroy(nmgp_plan* pl) {
   if (!pl) return 0;
   for (void* p : pl->allocs) cudaFree(p);
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->side) cudaStreamDestroy(pl->side);
   delete pl;
   return 0;
 }
@@ -324,6 +331,13 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
       if ((rc = factor_prior(pl, a0, b0, pl->Wp0, pl->hld0, st))) break;
       if ((rc = factor_prior(pl, a1, b1, pl->Wp1, pl->hld1, st))) break;
     }
+    if (pl->nprior) {
+      if (cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        set_last_error("nmgp_plan_create: creating the side stream failed"); rc = NMGP_ECUDA; break;
+      }
+    }
     if (cudaStreamSynchronize(st) != cudaSuccess) {
       set_last_error(std::string("nmgp_plan_create: ") + cudaGetErrorString(cudaGetLastError())); rc = NMGP_ECUDA; break;
     }
@@ -360,21 +374,36 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
       NMGP_TRY(sep_forward(pl->model, cs, N, M, xs, Ys, ps, P, pl->hc, pl->w, b, st, &launches));
     }
     NMGP_MARK(1);
+    // The prior solves only need the residuals written by the forward pass.  In the normal call they run on the plan's
+    // side stream beside the factorisation (fork/join with events, so the call stays stream-ordered on `st`); the
+    // profiling call keeps them on `st` so that every phase is timed alone.
+    const bool overlap = pl->nprior && !phase_ms && pl->side;
+    cudaStream_t ps_st = overlap ? pl->side : st;
+    auto prior_solves = [&]() -> int {
+      if (!pl->nprior) return 0;
+      const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
+      const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
+      NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, ps_st, &launches));
+      NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, ps_st, &launches));
+      if (grad) {
+        NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, ps_st, &launches));
+        NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, ps_st, &launches));
+      }
+      return 0;
+    };
+    if (overlap) {
+      NMGP_CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
+      NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+      NMGP_TRY(prior_solves());
+      NMGP_CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
+    }
     const bool ll = b.Pbuf != nullptr && (pl->engine_mode == 2 || (pl->engine_mode == 0 && prefer_left_looking(b)));
     if (ll) NMGP_TRY(engine_potrf_ll(b, st, &launches)); else NMGP_TRY(engine_potrf(b, st, &launches));
     NMGP_MARK(2);
     if (ll) NMGP_TRY(engine_potri_ll(b, st, &launches)); else NMGP_TRY(engine_potri(b, st, &launches));
     NMGP_MARK(3);
-    if (pl->nprior) {
-      const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
-      const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
-      NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
-      NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, st, &launches));
-      if (grad) {
-        NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, st, &launches));
-        NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, st, &launches));
-      }
-    }
+    if (overlap) NMGP_CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+    else NMGP_TRY(prior_solves());
     NMGP_MARK(4);
     const double* h0 = pl->hld0 ? pl->hld0 + s0 : nullptr;
     const double* h1 = pl->hld1 ? pl->hld1 + s0 : nullptr;

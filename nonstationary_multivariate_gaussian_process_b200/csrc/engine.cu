@@ -163,171 +163,6 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Diagonal block: factor A(k,k) = L L^T in shared memory, W = L^-1, accumulate log det, report failures.
-// Blocked with inner block 8 so that the CTA synchronises 3 times per 8 columns instead of 3 times per column:
-//   Cholesky: warp 0 factors the 8x8 sub-block in registers (row per lane, shuffles), 56-8p threads solve the panel
-//             rows, all 256 threads apply the rank-8 trailing update;
-//   inverse : block row i of W = L^-1 from the rows above:  W(i,:) = -inv(L_ii) * [L(i,0:i) W(0:i,:)],  W(i,i) = inv(L_ii).
-constexpr int DIAG_THREADS = 256;
-constexpr int LDD = NB + 1;
-constexpr int IB = 8;
-// L block + T scratch + rinv + reduction: 38 KB -> 5-6 CTAs per SM (the kernel is latency-bound: sqrt/div chains)
-constexpr size_t DIAG_SMEM = (1ull * NB * LDD + IB * NB + NB + 16) * sizeof(double);
-
-// ACCURATE: sqrt + true divisions (one rounding per element, like LAPACK's potf2) -- used for the ill-conditioned
-// GP-prior covariances at plan creation.  Fast path: rsqrt pivot and multiplication by the reciprocal.
-template <bool ACCURATE>
-__global__ void __launch_bounds__(DIAG_THREADS) diag_kernel(EngineArgs g, double* __restrict__ logdet,
-                                                            int* __restrict__ info) {
-  extern __shared__ __align__(16) double smem[];
-  double* L = smem;                 // [NB][LDD]
-  double* Tb = L + NB * LDD;        // [IB][NB]
-  double* rinv = Tb + IB * NB;      // [NB]
-  double* red = rinv + NB;          // [16]
-  __shared__ int fail;
-  const int k = g.step;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  for (int mat = blockIdx.x; mat < g.batch; mat += gridDim.x) {
-    double* Akk = g.A + (long)mat * g.strideA + ((long)k * NB) * g.ld + (long)k * NB;
-    double* W = g.Dinv + (long)mat * g.strideD + (long)k * NB * NB;   // [NB][NB] in global memory (L2-resident)
-    if (tid == 0) fail = 0;
-    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-      const int r = idx / NB, c = idx % NB;
-      L[r * LDD + c] = (c <= r) ? Akk[(long)r * g.ld + c] : 0.0;
-      if (c > r) W[idx] = 0.0;
-    }
-    // ---- Cholesky
-    for (int p = 0; p < NB / IB; ++p) {
-      const int c0 = p * IB;
-      __syncthreads();
-      if (warp == 0) {
-        const int t = lane & 7;
-        double row[IB];
-#pragma unroll
-        for (int c = 0; c < IB; ++c) row[c] = L[(c0 + t) * LDD + c0 + c];
-#pragma unroll
-        for (int j = 0; j < IB; ++j) {
-          const double d = __shfl_sync(0xffffffffu, row[j], j);
-          if (!(d > 0.0) && lane == 0 && fail == 0) fail = k * NB + c0 + j + 1;
-          double rj, ri, lj;
-          if (ACCURATE) {
-            rj = sqrt(d);           // NaN on failure: propagates in-band
-            ri = 1.0 / rj;
-            lj = (t == j) ? rj : row[j] / rj;
-          } else {
-            ri = rsqrt(d);
-            rj = d * ri;
-            lj = (t == j) ? rj : row[j] * ri;
-          }
-          row[j] = lj;
-#pragma unroll
-          for (int c = j + 1; c < IB; ++c) {
-            const double lc = __shfl_sync(0xffffffffu, lj, c);
-            if (t >= c) row[c] -= lj * lc;
-          }
-          if (lane == j) rinv[c0 + j] = ri;
-        }
-        if (lane < IB) {
-#pragma unroll
-          for (int c = 0; c < IB; ++c)
-            if (c <= t) L[(c0 + t) * LDD + c0 + c] = row[c];
-        }
-      }
-      __syncthreads();
-      const int m = NB - IB - c0;  // rows below the sub-block
-      if (tid < m) {
-        double* xr = L + (c0 + IB + tid) * LDD + c0;
-        double x[IB];
-#pragma unroll
-        for (int c = 0; c < IB; ++c) x[c] = xr[c];
-#pragma unroll
-        for (int c = 0; c < IB; ++c) {
-          double sacc = x[c];
-#pragma unroll
-          for (int c2 = 0; c2 < c; ++c2) sacc -= x[c2] * L[(c0 + c) * LDD + c0 + c2];
-          x[c] = ACCURATE ? sacc / L[(c0 + c) * LDD + c0 + c] : sacc * rinv[c0 + c];
-        }
-#pragma unroll
-        for (int c = 0; c < IB; ++c) xr[c] = x[c];
-      }
-      __syncthreads();
-      {
-        const int rr = tid >> 2, cp = tid & 3;
-        if (rr < m) {
-          const int r = c0 + IB + rr;
-          double xr[IB];
-#pragma unroll
-          for (int q = 0; q < IB; ++q) xr[q] = L[r * LDD + c0 + q];
-          for (int c = c0 + IB + cp; c <= r; c += 4) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int q = 0; q < IB; ++q) sacc += xr[q] * L[c * LDD + c0 + q];
-            L[r * LDD + c] -= sacc;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- lower factor back to the matrix, log det
-    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-      const int r = idx / NB, c = idx % NB;
-      if (c <= r) Akk[(long)r * g.ld + c] = L[r * LDD + c];
-    }
-    double lg = (tid < NB) ? log(L[tid * LDD + tid]) : 0.0;
-    lg = warp_sum(lg);
-    if (lane == 0 && warp < 2) red[warp] = lg;
-    // ---- W = L^-1, block row by block row (rows above are read back from global memory)
-    for (int ib = 0; ib < NB / IB; ++ib) {
-      const int r0 = ib * IB;
-      for (int idx = tid; idx < IB * r0; idx += DIAG_THREADS) {
-        const int c = idx % r0, rr = idx / r0;
-        const double* lrow = L + (r0 + rr) * LDD;
-        double sacc = 0.0;
-        for (int q = (c & ~(IB - 1)); q < r0; ++q) sacc += lrow[q] * W[q * NB + c];
-        Tb[rr * NB + c] = sacc;
-      }
-      __syncthreads();
-      const int wcols = r0 + IB;
-      for (int idx = tid; idx < IB * wcols; idx += DIAG_THREADS) {
-        const int c = idx % wcols, rr = idx / wcols;
-        // row rr of inv(L_ii) by back substitution
-        double w[IB];
-#pragma unroll
-        for (int q = IB - 1; q >= 0; --q) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int s2 = q + 1; s2 < IB; ++s2)
-            if (s2 <= rr) sacc += w[s2] * L[(r0 + s2) * LDD + r0 + q];
-          w[q] = (q == rr) ? rinv[r0 + q] : (q < rr ? -sacc * rinv[r0 + q] : 0.0);
-        }
-        double out;
-        if (c < r0) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int q = 0; q < IB; ++q) sacc += w[q] * Tb[q * NB + c];   // w[q] == 0 for q > rr
-          out = -sacc;
-        } else {
-          out = 0.0;
-#pragma unroll
-          for (int q = 0; q < IB; ++q)
-            if (q == c - r0) out = w[q];
-        }
-        W[(r0 + rr) * NB + c] = out;
-      }
-      __syncthreads();   // also orders this CTA's global writes of W before the next block row reads them
-    }
-    if (tid == 0) {
-      const double sld = 2.0 * (red[0] + red[1]);
-      logdet[mat] = (k == 0 ? 0.0 : logdet[mat]) + sld;
-      if (k == 0) info[mat] = fail;
-      else if (fail != 0 && info[mat] == 0) info[mat] = fail;
-    }
-    __syncthreads();
-  }
-}
-
 // Mirror the lower block triangle into the upper one: A(j,i) = A(i,j)^T for i > j.
 __global__ void __launch_bounds__(256) symmetrize_kernel(EngineArgs g) {
   __shared__ double T[NB][NB + 1];
@@ -408,25 +243,6 @@ EngineArgs make_args(const BlockBatch& b) {
 }
 
 }  // namespace
-
-int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches, bool accurate) {
-  if (b.batch <= 0) return 0;
-  if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine: bad block layout"); return -1; }
-  static bool configured = false;
-  if (!configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-    configured = true;
-  }
-  EngineArgs g = make_args(b);
-  g.step = k;
-  const int dgrid = b.batch < 148 * 16 ? b.batch : 148 * 16;
-  if (accurate) diag_kernel<true><<<dgrid, DIAG_THREADS, DIAG_SMEM, st>>>(g, b.logdet, b.info);
-  else diag_kernel<false><<<dgrid, DIAG_THREADS, DIAG_SMEM, st>>>(g, b.logdet, b.info);
-  NMGP_CUDA_TRY(cudaGetLastError());
-  if (launches) ++*launches;
-  return 0;
-}
 
 int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
   if (b.batch <= 0) return 0;

@@ -46,7 +46,11 @@ int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches
 int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches);
 int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches);
 
-// Heuristic: the left-looking path needs >= ~2 waves of 64x64 tiles per block column from the batch alone.
-inline bool prefer_left_looking(const BlockBatch& b) { return b.Pbuf != nullptr && b.batch >= 96; }
+// Heuristic: the left-looking path launches (Kt - k) * batch CTAs per block column, each a long K loop; it needs about
+// two waves of them (148 SMs x 3 resident CTAs) on average to keep the tensor pipes busy.  Measured on B200: n = 16 384
+// with batch 8 is 1.6x faster left-looking, batch 1 is 1.5x faster right-looking (profiles/r01_configs_h.txt).
+inline bool prefer_left_looking(const BlockBatch& b) {
+  return b.Pbuf != nullptr && (b.batch >= 96 || (long)b.batch * b.Kt >= 1024);
+}
 
 }  // namespace nmgp

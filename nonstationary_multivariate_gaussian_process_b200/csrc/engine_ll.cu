@@ -20,7 +20,7 @@ namespace nmgp {
 namespace {
 
 constexpr int NB = kNB;      // 64
-constexpr int KC = 16;       // k-chunk per pipeline stage
+constexpr int KC = 16;       // k-chunk per pipeline stage (tools/dmma_pipe.cu: 16 x 3 stages beats 32 x 2 and 8 x 4)
 constexpr int STAGES = 3;
 constexpr int LDK = KC + 4;  // k-major chunk [64][20]   (== 4 mod 16: conflict-free fragment loads)
 constexpr int LDM = NB + 4;  // m-major chunk [16][68]
@@ -35,7 +35,7 @@ struct LLArgs {
   double* Dinv;
   double* Pbuf;
   long strideA, strideD, strideP;
-  int ld, Kt, batch, step, n8;
+  int ld, Kt, batch, step, n8, ntiles;
 };
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
@@ -49,16 +49,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // issue the copies of one k-chunk of one operand tile
 template <bool KM>
 __device__ __forceinline__ void issue_chunk(double* S, const double* tile, int ld, int kc) {
-  if (KM) {  // rows 0..63, columns kc*16 .. +16  ->  S[row][LDK]
+  constexpr int V = KC / 2;               // 16-byte vectors per row of a k-major chunk
+  constexpr int ITERS = NB * V / THREADS; // copies per thread (both layouts move NB*KC doubles)
+  if (KM) {  // rows 0..63, columns kc*KC .. +KC  ->  S[row][LDK]
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int idx = threadIdx.x + it * THREADS;  // 0..511
-      const int r = idx >> 3, c2 = idx & 7;
+    for (int it = 0; it < ITERS; ++it) {
+      const int idx = threadIdx.x + it * THREADS;
+      const int r = idx / V, c2 = idx % V;
       cp_async16(S + r * LDK + 2 * c2, tile + (long)r * ld + kc * KC + 2 * c2);
     }
-  } else {   // rows kc*16 .. +16, columns 0..63  ->  S[k][LDM]
+  } else {   // rows kc*KC .. +KC, columns 0..63  ->  S[k][LDM]
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const int idx = threadIdx.x + it * THREADS;
       const int r = idx >> 5, c2 = idx & 31;
       cp_async16(S + r * LDM + 2 * c2, tile + (long)(kc * KC + r) * ld + 2 * c2);
@@ -94,66 +96,92 @@ __device__ __forceinline__ void mma_chunk(const double* __restrict__ SA, const d
   }
 }
 
+// One CTA walks a LIST of output tiles of one matrix (tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of this launch) and
+// streams all their k-chunks through ONE cp.async ring: the loads of the next tile are already in flight while the
+// current tile's epilogue runs, so the pipeline never drains between tiles (with one tile per CTA the fill/drain cost
+// 20-30 % of the short panel modes).  The epilogue works from registers only (the mirror of the symmetric inverse is a
+// direct transposed store: 8 lanes write 64 contiguous bytes), so shared memory belongs to the ring at all times.
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
   extern __shared__ __align__(16) double smem[];
   constexpr bool A_KM = (MODE == LL_UPDATE || MODE == LL_SOLVE || MODE == TK_PANEL || MODE == TK_COL);
   constexpr bool B_KM = (MODE == LL_UPDATE || MODE == LL_SOLVE);
+  constexpr int CPB = NB / KC;   // chunks per k-block
   const int s = g.step;
-  const int t = blockIdx.x;
   const int last = g.Kt - 1;
   const int vlast = g.n8 - last * NB;  // valid rows/cols of the last block (multiple of 8)
+  const int j = s;                     // every mode writes block column s
 
-  // output tile (i,j) and the k-block sequence
-  int i, j, nkb;
-  if (MODE == LL_UPDATE) { i = s + t; j = s; nkb = s; }
-  else if (MODE == LL_SOLVE) { i = s + 1 + t; j = s; nkb = 1; }
-  else if (MODE == TK_PANEL) { i = s + 1 + t; j = s; nkb = 1; }
-  else if (MODE == TK_COL) { i = s + 1 + t; j = s; nkb = last - s; }
-  else { i = s; j = s; nkb = last - s + 1; }
+  // k-block sequence (the same for every tile of a launch)
+  int nkb;
+  if (MODE == LL_UPDATE) nkb = s;
+  else if (MODE == LL_SOLVE || MODE == TK_PANEL) nkb = 1;
+  else if (MODE == TK_COL) nkb = last - s;
+  else nkb = last - s + 1;
   // is the last k-block of the sequence the ragged block Kt-1 ?
   const bool ragged_k = (MODE == TK_COL) || (MODE == TK_DIAG && nkb > 1);
-  const int nchunks = (nkb - 1) * (NB / KC) + ((ragged_k ? vlast : NB) + KC - 1) / KC;
-  const int rows_valid = (i == last) ? vlast : NB;
+  const int nchunks = (nkb - 1) * CPB + ((ragged_k ? vlast : NB) + KC - 1) / KC;
   const int cols_valid = (j == last) ? vlast : NB;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Quarter of the tile owned by this warp.  The quarters do unequal work in the triangular modes below and every
+  // warp is pinned to one SM sub-partition (one DMMA pipe each), so the assignment is rotated per CTA: over the CTAs
+  // resident on an SM the light and heavy quarters then spread over all four pipes.
+  const int warp = ((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & 3, lane = threadIdx.x & 31;
   const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
-  const bool active = (m0 < rows_valid) && (n0 < cols_valid);
+  const int r = lane >> 2, c = 2 * (lane & 3);
+  const bool upper_quarter = (m0 == 0 && n0 == NB / 2);
+  // k-chunks that only multiply structural zeros of the triangular W = L_kk^-1 (W[a][b] = 0 for b > a):
+  //   LL_SOLVE  C[m][n] = sum_k A[m][k] W[n][k]   -> columns n < 32 need k < 32 only
+  //   TK_PANEL  C[m][n] = sum_k L[m][k] W[k][n]   -> columns n >= 32 need k >= 32 only
+  //   TK_DIAG   (first k-block) sum_k W[k][m] W[k][n] -> any quarter touching rows/cols >= 32 needs k >= 32 only
+  auto zero_chunk = [&](int qq) -> bool {
+    constexpr int HALF = (NB / 2) / KC;   // chunks per half block
+    if (MODE == LL_SOLVE) return n0 == 0 && qq >= HALF;
+    if (MODE == TK_PANEL) return n0 == NB / 2 && qq < HALF;
+    if (MODE == TK_DIAG) return (m0 == NB / 2 || n0 == NB / 2) && qq < HALF;
+    return false;
+  };
+  // block row of the tt-th tile of this CTA
+  auto tile_row = [&](int tt) -> int {
+    const int t = blockIdx.x + tt * gridDim.x;
+    if (MODE == LL_UPDATE) return s + t;
+    if (MODE == TK_DIAG) return s;
+    return s + 1 + t;
+  };
+  const int nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = nmy * nchunks;
 
   for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
     double* Am = g.A + (long)mat * g.strideA;
     const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * NB * NB;
     double* Pm = g.Pbuf + (long)mat * g.strideP;
 
-    auto operands = [&](int kb, const double*& ta, int& lda, const double*& tb, int& ldb) {
+    int itt = 0, iqq = 0;   // tile / chunk-in-tile of the next chunk to be issued
+    auto issue = [&](int q) {
+      const int tt = itt, qq = iqq;
+      if (++iqq == nchunks) { iqq = 0; ++itt; }
+      const int i = tile_row(tt);
+      const int kb = qq / CPB, kc = qq % CPB;
+      const double *ta, *tb;
+      int lda, ldb;
       if (MODE == LL_UPDATE) {
         ta = Am + ((long)i * NB) * g.ld + (long)kb * NB; lda = g.ld;
         tb = Am + ((long)s * NB) * g.ld + (long)kb * NB; ldb = g.ld;
-      } else if (MODE == LL_SOLVE) {
-        ta = Am + ((long)i * NB) * g.ld + (long)s * NB; lda = g.ld;
-        tb = Dm; ldb = NB;
-      } else if (MODE == TK_PANEL) {
+      } else if (MODE == LL_SOLVE || MODE == TK_PANEL) {
         ta = Am + ((long)i * NB) * g.ld + (long)s * NB; lda = g.ld;
         tb = Dm; ldb = NB;
       } else if (MODE == TK_COL) {
-        const int c = s + 1 + kb;
-        ta = Am + ((long)i * NB) * g.ld + (long)c * NB; lda = g.ld;
-        tb = Pm + (long)c * NB * NB; ldb = NB;
+        const int cb = s + 1 + kb;
+        ta = Am + ((long)i * NB) * g.ld + (long)cb * NB; lda = g.ld;
+        tb = Pm + (long)cb * NB * NB; ldb = NB;
       } else {
         if (kb == 0) { ta = Dm; lda = NB; tb = Dm; ldb = NB; }
         else {
-          const int c = s + kb;
-          ta = Pm + (long)c * NB * NB; lda = NB;
-          tb = Am + ((long)c * NB) * g.ld + (long)s * NB; ldb = g.ld;
+          const int cb = s + kb;
+          ta = Pm + (long)cb * NB * NB; lda = NB;
+          tb = Am + ((long)cb * NB) * g.ld + (long)s * NB; ldb = g.ld;
         }
       }
-    };
-    auto issue = [&](int q) {
-      const int kb = q / (NB / KC), kc = q % (NB / KC);
-      const double *ta, *tb;
-      int lda, ldb;
-      operands(kb, ta, lda, tb, ldb);
       double* S = smem + (q % STAGES) * 2 * OPSZ;
       issue_chunk<A_KM>(S, ta, lda, kc);
       issue_chunk<B_KM>(S + OPSZ, tb, ldb, kc);
@@ -167,90 +195,93 @@ __global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
 
 #pragma unroll
     for (int q = 0; q < STAGES - 1; ++q) {
-      if (q < nchunks) issue(q);
+      if (q < total) issue(q);
       cp_async_commit();
     }
-    for (int q = 0; q < nchunks; ++q) {
+    int tt = 0, qq = 0;
+    for (int q = 0; q < total; ++q) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
-      if (q + STAGES - 1 < nchunks) issue(q + STAGES - 1);
+      if (q + STAGES - 1 < total) issue(q + STAGES - 1);
       cp_async_commit();
-      if (active) {
+      const int i = tile_row(tt);
+      const int rows_valid = (i == last) ? vlast : NB;
+      // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
+      // of A(k,k); Z(j,j) is symmetric and mirrored below)
+      const bool tri_skip = upper_quarter && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
+      const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
+      if (active && !zero_chunk(qq)) {
         const double* S = smem + (q % STAGES) * 2 * OPSZ;
         mma_chunk<A_KM, B_KM>(S, S + OPSZ, m0, n0, acc);
       }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // ---- epilogue
-    const int r = lane >> 2, c = 2 * (lane & 3);
-    if (MODE == TK_PANEL) {
-      double* C = Pm + (long)i * NB * NB;
+      if (++qq < nchunks) continue;
+      // ---- epilogue of tile (i, j)
       if (active) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            double2 v; v.x = -acc[a][b][0]; v.y = -acc[a][b][1];
-            *reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * NB + n0 + 8 * b + c) = v;
-          }
-      }
-    } else {
-      double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
-      if (active) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            double2* p = reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * g.ld + n0 + 8 * b + c);
-            double2 v;
-            if (MODE == LL_UPDATE) {
-              v = *p;
-              v.x -= acc[a][b][0];
-              v.y -= acc[a][b][1];
-            } else {
-              v.x = acc[a][b][0];
-              v.y = acc[a][b][1];
-            }
-            *p = v;
-            acc[a][b][0] = v.x;
-            acc[a][b][1] = v.y;
-          }
-      }
-      if (MODE == TK_COL) {  // mirror: Z(j,i) = Z(i,j)^T through shared memory (pipeline buffers are free now)
-        double* T = smem;    // [64][65]
-        if (active) {
+        if (MODE == TK_PANEL) {
+          double* C = Pm + (long)i * NB * NB;
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              T[(m0 + 8 * a + r) * (NB + 1) + n0 + 8 * b + c] = acc[a][b][0];
-              T[(m0 + 8 * a + r) * (NB + 1) + n0 + 8 * b + c + 1] = acc[a][b][1];
+              double2 v; v.x = -acc[a][b][0]; v.y = -acc[a][b][1];
+              *reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * NB + n0 + 8 * b + c) = v;
+            }
+        } else {
+          double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
+          // the mirror tile: Z(j,i) = Z(i,j)^T, or the upper-right quarter of the symmetric diagonal tile
+          const bool mirror = (MODE == TK_COL) || (MODE == TK_DIAG && m0 == NB / 2 && n0 == 0);
+          double* U = Am + ((long)j * NB) * g.ld + (long)i * NB;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
+              double2* p = reinterpret_cast<double2*>(C + (long)row * g.ld + col);
+              double2 v;
+              if (MODE == LL_UPDATE) {
+                v = *p;
+                v.x -= acc[a][b][0];
+                v.y -= acc[a][b][1];
+              } else {
+                v.x = acc[a][b][0];
+                v.y = acc[a][b][1];
+              }
+              *p = v;
+              if (mirror) {
+                U[(long)col * g.ld + row] = v.x;
+                U[(long)(col + 1) * g.ld + row] = v.y;
+              }
             }
         }
-        __syncthreads();
-        double* U = Am + ((long)j * NB) * g.ld + (long)i * NB;  // rows = cols of the tile, cols = its rows
-        const int rv = (rows_valid + 31) & ~31, cv = (cols_valid + 31) & ~31;  // what the active warps produced
-        for (int idx = threadIdx.x; idx < cv * rv; idx += THREADS) {
-          const int ur = idx / rv, uc = idx % rv;
-          U[(long)ur * g.ld + uc] = T[uc * (NB + 1) + ur];
-        }
       }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      qq = 0;
+      ++tt;
     }
-    __syncthreads();
+    cp_async_wait<0>();
+    __syncthreads();   // the ring is reused by the next matrix
   }
 }
 
+// tiles of one matrix are split over gx CTAs; enough CTAs for ~8 waves of the 148 x 3 resident slots
 template <int MODE>
-int launch_ll(const LLArgs& g, int ntiles, cudaStream_t st, long* launches) {
-  if (ntiles <= 0 || g.batch <= 0) return 0;
+int launch_ll(const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
+  if (ntiles <= 0 || g0.batch <= 0) return 0;
   static bool configured = false;
   if (!configured) {
     NMGP_CUDA_TRY(cudaFuncSetAttribute(panel_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
     configured = true;
   }
-  dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
+  LLArgs g = g0;
+  g.ntiles = ntiles;
+  const int gy = g.batch < 65535 ? g.batch : 65535;
+  int gx = (148 * 3 * 8 + gy - 1) / gy;
+  if (gx > ntiles) gx = ntiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, gy);
   panel_gemm_kernel<MODE><<<grid, THREADS, LL_SMEM, st>>>(g);
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
@@ -263,6 +294,7 @@ LLArgs make_ll(const BlockBatch& b) {
   g.strideA = b.strideA(); g.strideD = b.strideD(); g.strideP = b.strideD();
   g.ld = b.nP; g.Kt = b.Kt; g.batch = b.batch; g.step = 0;
   g.n8 = (int)round_up(b.n, 8);
+  g.ntiles = 0;
   return g;
 }
 

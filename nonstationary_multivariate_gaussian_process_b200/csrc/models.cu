@@ -183,6 +183,100 @@ __global__ void __launch_bounds__(256) prior_update_kernel(const double* __restr
   }
 }
 
+// Many small systems (the batched regime: N ~ 100, thousands of subjects): ONE WARP solves all right-hand sides of one
+// subject, one right-hand side per lane, 32 rows of the solution in registers at a time.  The factor is staged through a
+// 32 x 32 shared-memory block per warp and read back as uniform-address (broadcast) LDS.128 -- no bank conflicts, no
+// shuffles, no CTA barriers; the already-solved part of the solution is re-read from the output array (written by the
+// same lane, coalesced across lanes).
+//   TRANS=0:  L x = b, block rows ascending:   acc[r] -= L[r][k] x[k]  (k < block),   staged TRANSPOSED ([k][r])
+//   TRANS=1:  L^T x = b, block rows descending: acc[k] -= L[r][k] x[r]  (r > block),   staged as stored ([r][k])
+constexpr int PWB = 4;   // warps (independent problems) per CTA
+
+template <int TRANS>
+__global__ void __launch_bounds__(32 * PWB) prior_solve_warp_kernel(const double* __restrict__ Lp,
+                                                                    const double* __restrict__ rhs, double* X, int cs,
+                                                                    int N, int nv, int nvc) {
+  __shared__ __align__(16) double Ls_all[PWB][32 * 34];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * PWB + warp;
+  if (prob >= cs * nvc) return;          // whole warps leave together; only __syncwarp below
+  const int c = prob / nvc, v = (prob % nvc) * 32 + lane;
+  const bool vok = v < nv;
+  double* Ls = Ls_all[warp];             // [32][34]
+  const double* L = Lp + (long)c * N * N;
+  const double* R = rhs + (long)c * N * nv;
+  double* Xc = X + (long)c * N * nv;
+  const int nblk = (N + 31) / 32;
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int b = TRANS ? nblk - 1 - bi : bi;
+    const int r0 = b * 32;
+    double acc[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc[r] = (vok && r0 + r < N) ? R[(long)(r0 + r) * nv + v] : 0.0;
+    // ---- off-diagonal blocks already solved
+    for (int oi = 0; oi < bi; ++oi) {
+      const int o = TRANS ? nblk - 1 - oi : oi;
+      const int k0 = o * 32;
+      __syncwarp();
+      if (TRANS) {   // rows k0.. (the solved x[r]), columns r0..r0+31 of L:  Ls[rr][kk] = L[k0+rr][r0+kk]
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr)
+          Ls[rr * 34 + lane] = (k0 + rr < N) ? L[(long)(k0 + rr) * N + r0 + lane] : 0.0;   // r0 + lane < k0 <= N
+      } else {       // rows r0..r0+31, columns k0..k0+31 (solved x[k]) of L, transposed:  Ls[kk][rr] = L[r0+rr][k0+kk]
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr)
+          Ls[lane * 34 + rr] = (r0 + rr < N) ? L[(long)(r0 + rr) * N + k0 + lane] : 0.0;
+      }
+      __syncwarp();
+#pragma unroll 4
+      for (int kk = 0; kk < 32; ++kk) {
+        const double xk = (vok && k0 + kk < N) ? Xc[(long)(k0 + kk) * nv + v] : 0.0;
+        const double* row = Ls + kk * 34;
+#pragma unroll
+        for (int r = 0; r < 32; r += 2) {
+          const double2 l2 = *reinterpret_cast<const double2*>(row + r);
+          acc[r] -= l2.x * xk;
+          acc[r + 1] -= l2.y * xk;
+        }
+      }
+    }
+    // ---- diagonal block
+    __syncwarp();
+    if (TRANS) {
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr)
+        Ls[rr * 34 + lane] = (r0 + rr < N && r0 + lane < N) ? L[(long)(r0 + rr) * N + r0 + lane] : (rr == lane ? 1.0 : 0.0);
+    } else {
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr)
+        Ls[lane * 34 + rr] = (r0 + rr < N && r0 + lane < N) ? L[(long)(r0 + rr) * N + r0 + lane] : (rr == lane ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    if (TRANS) {   // Ls[r][k] = L_bb[r][k]:  x[r] final (descending) -> acc[k] -= L[r][k] x[r], k < r
+#pragma unroll
+      for (int r = 31; r >= 0; --r) {
+        acc[r] = acc[r] / Ls[r * 34 + r];
+        const double xr = acc[r];
+#pragma unroll
+        for (int k = 0; k < r; ++k) acc[k] -= Ls[r * 34 + k] * xr;
+      }
+    } else {       // Ls[k][r] = L_bb[r][k]:  x[k] final (ascending) -> acc[r] -= L[r][k] x[k], r > k
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        acc[k] = acc[k] / Ls[k * 34 + k];
+        const double xk = acc[k];
+#pragma unroll
+        for (int r = k + 1; r < 32; ++r) acc[r] -= Ls[k * 34 + r] * xk;
+      }
+    }
+    if (vok) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (r0 + r < N) Xc[(long)(r0 + r) * nv + v] = acc[r];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ shared by models
 // Gibbs kernel matrix Kx (with jitter) and CK = c_ij * K0_ij for every subject of the chunk.
 __global__ void kx_kernel(const double* __restrict__ x, const double* __restrict__ ell, const double* __restrict__ sig,
@@ -326,120 +420,125 @@ __global__ void svc_cov_reference_order_kernel(const double* __restrict__ x, con
 // The gradient needs  W[p][k] = sum_q Kx[i,j] G[p,q] L_j[m'][k]  and  V[p][k] = sum_q CK[i,j] G[p,q] L_j[m'][k]
 // (p=(i,m), q=(j,m')) with G = -0.5 Sigma^-1 + 0.5 alpha alpha^T.  G is never formed: the Sigma^-1 part is ONE pass over
 // the inverse that also produces alpha = Sigma^-1 y (so the inverse is read exactly once); the rank-one part is an
-// O(N^2 M) correction (svc_alpha_terms_kernel).  One warp per row, lanes over the time blocks j: a lane reads the M
-// contiguous entries of block (p, j), the factor L_j from shared memory (odd stride: conflict-free), Kx/CK once per block.
+// O(N^2 M) correction (svc_u_kernel + svc_alpha_terms_kernel).
+// Mapping: a lane owns ROW p and keeps its 2M+1 partial sums in registers; the warp walks q = 0..n-1 and reads
+// Z[q][p0..p0+31] -- the inverse is symmetric, so the column strip a lane needs is a contiguous 256-byte row segment:
+// every load is perfectly coalesced and each byte of Sigma^-1 is fetched exactly once per subject.  The factors L_j and
+// the observations y_j are uniform across the warp: staged in shared memory, read as broadcasts.  Kx[i_p][j] / CK[i_p][j]
+// take ~32/M distinct rows per warp and walk along j, i.e. L1-resident lines.
 template <int M>
-__global__ void __launch_bounds__(256) svc_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N,
-                                                           int MT, int JC, int rows_per_warp,
-                                                           const double* __restrict__ Y, const double* __restrict__ Kx,
-                                                           const double* __restrict__ CK, const double* __restrict__ Lst,
-                                                           double* __restrict__ alpha, double* __restrict__ Wout,
-                                                           double* __restrict__ Vout) {
-  extern __shared__ __align__(16) double Lsm[];   // [JC][LS]
-  constexpr int LS = (M * M) | 1;
+__global__ void __launch_bounds__(128) svc_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N,
+                                                           int MT, int JC, const double* __restrict__ Y,
+                                                           const double* __restrict__ Kx, const double* __restrict__ CK,
+                                                           const double* __restrict__ Lst, double* __restrict__ alpha,
+                                                           double* __restrict__ Wout, double* __restrict__ Vout) {
+  extern __shared__ __align__(16) double csm[];   // [JC][LS] factors, then [JC][M] observations
+  constexpr int LS = M * M;
+  double* Lsm = csm;
+  double* ysm = csm + (size_t)JC * LS;
   const int c = blockIdx.y;
   const int n = N * M;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = p < n;
+  const int pc = valid ? p : n - 1;          // clamped: out-of-range lanes read a real column and discard the sums
+  const int ip = pc / M;
+  const double* Zc = A + (long)c * strideA + pc;
   const double* Ls = Lst + (long)c * n * MT;
   const double* y = Y + (long)c * n;
-  const int nch = (N + JC - 1) / JC;
-  auto stage = [&](int ch) {
-    const int j0 = ch * JC, jn = min(JC, N - j0);
-    for (int idx = threadIdx.x; idx < jn * M * M; idx += 256) {
-      const int k = idx % M, m2 = (idx / M) % M, jj = idx / (M * M);
-      Lsm[jj * LS + m2 * M + k] = Ls[((long)(j0 + jj) * M + m2) * MT + k];
+  const double* kr = Kx + ((long)c * N + ip) * N;
+  const double* cr = CK + ((long)c * N + ip) * N;
+  double aacc = 0.0, w[M], v[M];
+#pragma unroll
+  for (int k = 0; k < M; ++k) w[k] = v[k] = 0.0;
+  for (int j0 = 0; j0 < N; j0 += JC) {
+    const int jn = min(JC, N - j0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < jn * LS; idx += 128) {
+      const int k = idx % M, m2 = (idx / M) % M, jj = idx / LS;
+      Lsm[idx] = Ls[((long)(j0 + jj) * M + m2) * MT + k];
     }
-  };
-  if (nch == 1) { stage(0); __syncthreads(); }
-  for (int rr = 0; rr < rows_per_warp; ++rr) {
-    const int p = (blockIdx.x * 8 + warp) * rows_per_warp + rr;
-    const bool valid = p < n;
-    const int i = valid ? p / M : 0;
-    const double* row = A + (long)c * strideA + (long)(valid ? p : 0) * ld;
-    const double* kr = Kx + ((long)c * N + i) * N;
-    const double* cr = CK + ((long)c * N + i) * N;
-    double aacc = 0.0, w[M], v[M];
+    for (int idx = threadIdx.x; idx < jn * M; idx += 128) ysm[idx] = y[(long)j0 * M + idx];
+    __syncthreads();
+#pragma unroll 2
+    for (int jj = 0; jj < jn; ++jj) {
+      const int j = j0 + jj;
+      double z[M];
 #pragma unroll
-    for (int k = 0; k < M; ++k) w[k] = v[k] = 0.0;
-    for (int ch = 0; ch < nch; ++ch) {
-      if (nch > 1) { __syncthreads(); stage(ch); __syncthreads(); }
-      if (!valid) continue;
-      const int j0 = ch * JC, jn = min(JC, N - j0);
-      for (int jj = lane; jj < jn; jj += 32) {
-        const int j = j0 + jj;
-        double sv[M], qv[M];
+      for (int m2 = 0; m2 < M; ++m2) z[m2] = Zc[(long)(j * M + m2) * ld];
+      const double kx = kr[j], ck = cr[j];
+      const double* lj = Lsm + jj * LS;
+      const double* yj = ysm + jj * M;
+      double t[M];
 #pragma unroll
-        for (int m2 = 0; m2 < M; ++m2) {
-          sv[m2] = row[j * M + m2];
-          aacc += sv[m2] * y[j * M + m2];
-        }
-        const double* lj = Lsm + jj * LS;
+      for (int k = 0; k < M; ++k) t[k] = 0.0;
 #pragma unroll
-        for (int k = 0; k < M; ++k) {
-          double t = 0.0;
+      for (int m2 = 0; m2 < M; ++m2) {
+        aacc += z[m2] * yj[m2];
 #pragma unroll
-          for (int m2 = k; m2 < M; ++m2) t += sv[m2] * lj[m2 * M + k];   // L_j is lower triangular
-          qv[k] = t;
-        }
-        const double kx = kr[j], ck = cr[j];
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          w[k] += kx * qv[k];
-          v[k] += ck * qv[k];
-        }
+        for (int k = 0; k <= m2; ++k) t[k] += z[m2] * lj[m2 * M + k];   // L_j is lower triangular
       }
-    }
-    aacc = warp_sum(aacc);
-#pragma unroll
-    for (int k = 0; k < M; ++k) {
-      w[k] = warp_sum(w[k]);
-      v[k] = warp_sum(v[k]);
-    }
-    if (valid && lane == 0) {
-      alpha[(long)c * n + p] = aacc;
 #pragma unroll
       for (int k = 0; k < M; ++k) {
-        Wout[((long)c * n + p) * MT + k] = w[k];
-        Vout[((long)c * n + p) * MT + k] = v[k];
+        w[k] += kx * t[k];
+        v[k] += ck * t[k];
       }
+    }
+  }
+  if (valid) {
+    alpha[(long)c * n + p] = aacc;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      Wout[((long)c * n + p) * MT + k] = w[k];
+      Vout[((long)c * n + p) * MT + k] = v[k];
     }
   }
 }
 
-// rank-one part:  Sa[i][k] = sum_j Kx[i,j] u_j[k],  Ca[i][k] = sum_j CK[i,j] u_j[k],  u_j = L_j^T alpha_j   (one warp per i)
+// rank-one part of the gradient sums:  u_j = L_j^T alpha_j  (one thread per time point), then
+//   Sa[i][k] = sum_j Kx[i,j] u_j[k],  Ca[i][k] = sum_j CK[i,j] u_j[k]   (one warp per i, coalesced rows of Kx / CK / u)
 template <int M>
-__global__ void __launch_bounds__(256) svc_alpha_terms_kernel(int N, int MT, const double* __restrict__ alpha,
+__global__ void __launch_bounds__(128) svc_u_kernel(int N, int MT, const double* __restrict__ alpha,
+                                                    const double* __restrict__ Lst, double* __restrict__ U) {
+  const int c = blockIdx.y;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= N) return;
+  const double* al = alpha + ((long)c * N + j) * M;
+  const double* Lj = Lst + ((long)c * N + j) * M * MT;
+  double u[M];
+#pragma unroll
+  for (int k = 0; k < M; ++k) u[k] = 0.0;
+#pragma unroll
+  for (int m2 = 0; m2 < M; ++m2) {
+    const double a = al[m2];
+#pragma unroll
+    for (int k = 0; k <= m2; ++k) u[k] += a * Lj[m2 * MT + k];
+  }
+#pragma unroll
+  for (int k = 0; k < M; ++k) U[((long)c * N + j) * MT + k] = u[k];
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) svc_alpha_terms_kernel(int N, int MT, const double* __restrict__ U,
                                                               const double* __restrict__ Kx,
-                                                              const double* __restrict__ CK,
-                                                              const double* __restrict__ Lst, double* __restrict__ Sa,
+                                                              const double* __restrict__ CK, double* __restrict__ Sa,
                                                               double* __restrict__ Ca) {
   const int c = blockIdx.y;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= N) return;
-  const int n = N * M;
-  const double* al = alpha + (long)c * n;
-  const double* Ls = Lst + (long)c * n * MT;
+  const double* Uc = U + (long)c * N * MT;
   const double* kr = Kx + ((long)c * N + i) * N;
   const double* cr = CK + ((long)c * N + i) * N;
   double sa[M], ca[M];
 #pragma unroll
   for (int k = 0; k < M; ++k) sa[k] = ca[k] = 0.0;
   for (int j = lane; j < N; j += 32) {
-    double u[M];
-#pragma unroll
-    for (int k = 0; k < M; ++k) u[k] = 0.0;
-#pragma unroll
-    for (int m2 = 0; m2 < M; ++m2) {
-      const double a = al[j * M + m2];
-#pragma unroll
-      for (int k = 0; k <= m2; ++k) u[k] += a * Ls[((long)j * M + m2) * MT + k];
-    }
     const double kx = kr[j], ck = cr[j];
 #pragma unroll
     for (int k = 0; k < M; ++k) {
-      sa[k] += kx * u[k];
-      ca[k] += ck * u[k];
+      const double u = Uc[(long)j * MT + k];
+      sa[k] += kx * u;
+      ca[k] += ck * u;
     }
   }
 #pragma unroll
@@ -899,6 +998,14 @@ int launch_extract_factor(const BlockBatch& b, int N, double* Lp, double* hld, c
 int launch_prior_solve(const double* Lp, const double* rhs, double* out, int cs, int N, int nv, int trans,
                        cudaStream_t st, long* launches) {
   if (cs <= 0 || nv <= 0) return 0;
+  const int nvc32 = (nv + 31) / 32;
+  if ((long)cs * nvc32 >= 592) {   // >= one warp per SM sub-partition: the warp-per-problem kernel wins
+    const int grid = (int)(((long)cs * nvc32 + PWB - 1) / PWB);
+    if (trans) prior_solve_warp_kernel<1><<<grid, 32 * PWB, 0, st>>>(Lp, rhs, out, cs, N, nv, nvc32);
+    else prior_solve_warp_kernel<0><<<grid, 32 * PWB, 0, st>>>(Lp, rhs, out, cs, N, nv, nvc32);
+    NMGP_LAUNCH_CHECK();
+    return 0;
+  }
   NMGP_CUDA_TRY(cudaMemcpyAsync(out, rhs, (size_t)cs * N * nv * sizeof(double), cudaMemcpyDeviceToDevice, st));
   const int nblk = (N + PBS - 1) / PBS;
   const int nvc = (nv + PVC - 1) / PVC;
@@ -953,19 +1060,23 @@ int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int 
   if (cs <= 0) return 0;
   const int n = N * M, MT = padded_M(M);
   // one pass over Sigma^-1: alpha and the Sigma^-1 part of the gradient sums
-  const int LS = (M * M) | 1;
-  int JC = 6144 / LS;
+  const int LS = M * M;
+  int JC = (40 * 1024) / ((LS + M) * (int)sizeof(double));
   if (JC > N) JC = N;
-  const int rpw = (JC >= N) ? 4 : 1;
-  dim3 gc((n + 8 * rpw - 1) / (8 * rpw), cs);
-  const size_t smem = (size_t)JC * LS * sizeof(double);
-#define NMGP_CONTRACT_CASE(MM) case MM: svc_contract_kernel<MM><<<gc, 256, smem, st>>>(b.A, b.strideA(), b.nP, N, MT, JC, rpw, Y, w.Kx, w.CK, w.Lst, w.alpha, w.Wout, w.Vout); break;
+  dim3 gc((n + 127) / 128, cs);
+  const size_t smem = (size_t)JC * (LS + M) * sizeof(double);
+#define NMGP_CONTRACT_CASE(MM) case MM: svc_contract_kernel<MM><<<gc, 128, smem, st>>>(b.A, b.strideA(), b.nP, N, MT, JC, Y, w.Kx, w.CK, w.Lst, w.alpha, w.Wout, w.Vout); break;
   switch (M) { NMGP_FOR_EACH_M(NMGP_CONTRACT_CASE) default: set_last_error("M out of range"); return -1; }
 #undef NMGP_CONTRACT_CASE
   NMGP_LAUNCH_CHECK();
   if (grad != nullptr) {
+    dim3 gu((N + 127) / 128, cs);
+#define NMGP_U_CASE(MM) case MM: svc_u_kernel<MM><<<gu, 128, 0, st>>>(N, MT, w.alpha, w.Lst, w.Ua); break;
+    switch (M) { NMGP_FOR_EACH_M(NMGP_U_CASE) default: break; }
+#undef NMGP_U_CASE
+    NMGP_LAUNCH_CHECK();
     dim3 ga((N + 7) / 8, cs);
-#define NMGP_ALPHA_CASE(MM) case MM: svc_alpha_terms_kernel<MM><<<ga, 256, 0, st>>>(N, MT, w.alpha, w.Kx, w.CK, w.Lst, w.Sa, w.Ca); break;
+#define NMGP_ALPHA_CASE(MM) case MM: svc_alpha_terms_kernel<MM><<<ga, 256, 0, st>>>(N, MT, w.Ua, w.Kx, w.CK, w.Sa, w.Ca); break;
     switch (M) { NMGP_FOR_EACH_M(NMGP_ALPHA_CASE) default: break; }
 #undef NMGP_ALPHA_CASE
     NMGP_LAUNCH_CHECK();

@@ -33,6 +33,7 @@ struct Scratch {
   double* Vout;   // nonseparable [cs][n][MT];  separable: KA    [cs][N][M]
   double* Sa;     // nonseparable [cs][N][MT]  rank-one (alpha alpha^T) part of the gradient sums, Kx-weighted
   double* Ca;     // nonseparable [cs][N][MT]  same, CK-weighted
+  double* Ua;     // nonseparable [cs][N][MT]  u_j = L_j^T alpha_j
   double* gl;     // separable [cs][N]   sum_j GK_ij CK_ij
   double* gs;     // separable [cs][N]   sum_j GK_ij K0_ij
   double* lam;    // separable [cs][M]

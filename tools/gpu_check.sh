@@ -7,6 +7,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_$TAG.txt
 cat gpurun_out/pytest_$TAG.txt
 { python tools/run_config.py nonseparable 500 10 1 5
   python tools/run_config.py nonseparable 2048 8 1 2
+  python tools/run_config.py nonseparable 2048 8 8 1
   python tools/run_config.py separable 200 5 1 20
   python tools/run_config.py stationary 50 2 1 20
   python tools/run_config.py nonseparable 100 6 10000 3 ; } 2>&1 | tee gpurun_out/configs_$TAG.txt
