@@ -340,11 +340,13 @@ __global__ void svc_prep_kernel(const double* __restrict__ pars, int P, int N, i
 // One CTA per 64x64 tile; a warp writes one tile row as 32 double2 (512 B, coalesced); the factor rows of the tile's
 // columns sit k-major in shared memory so the M-term dot products read it conflict-free.  Memory-bound on the stores.
 template <int M>
-__global__ void __launch_bounds__(256) svc_build_kernel(const double* __restrict__ Kx, const double* __restrict__ Lst,
-                                                        const double* __restrict__ s2v, int N, int MT, double* A,
-                                                        long strideA, int ld) {
+__global__ void __launch_bounds__(256, 5) svc_build_kernel(const double* __restrict__ Kx, const double* __restrict__ Lst,
+                                                           const double* __restrict__ s2v, int N, int MT, double* A,
+                                                           long strideA, int ld) {
+  constexpr int KS = (NB + M - 1) / M + 1;          // time points a 64-row / 64-column range can touch
   __shared__ double Lr[NB][M];
   __shared__ __align__(16) double LcT[M][NB];
+  __shared__ double Ks[KS][KS + 1];                  // the Kx entries of this tile (no global load in the store loop)
   int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
   while ((long)ti * (ti + 1) / 2 > (long)blockIdx.x) --ti;
   while ((long)(ti + 1) * (ti + 2) / 2 <= (long)blockIdx.x) ++ti;
@@ -352,15 +354,20 @@ __global__ void __launch_bounds__(256) svc_build_kernel(const double* __restrict
   const int c = blockIdx.y;
   const int n = N * M;
   const int p0 = ti * NB, q0 = tj * NB;
+  const int i0 = p0 / M, j0 = q0 / M;
   const double* Ls = Lst + (long)c * n * MT;
+  const double* Kc = Kx + (long)c * N * N;
   for (int idx = threadIdx.x; idx < NB * M; idx += 256) {
     const int r = idx / M, k = idx % M;
     Lr[r][k] = (p0 + r < n) ? Ls[(long)(p0 + r) * MT + k] : 0.0;
     LcT[k][r] = (q0 + r < n) ? Ls[(long)(q0 + r) * MT + k] : 0.0;
   }
+  for (int idx = threadIdx.x; idx < KS * KS; idx += 256) {
+    const int ii = idx / KS, jj = idx % KS;
+    Ks[ii][jj] = (i0 + ii < N && j0 + jj < N) ? Kc[(long)(i0 + ii) * N + j0 + jj] : 0.0;
+  }
   __syncthreads();
   const double s2 = s2v[c];
-  const double* Kc = Kx + (long)c * N * N;
   double* Ac = A + (long)c * strideA;
 #pragma unroll
   for (int it = 0; it < (NB * NB / 2) / 256; ++it) {
@@ -377,10 +384,9 @@ __global__ void __launch_bounds__(256) svc_build_kernel(const double* __restrict
     }
     double2 v;
     if (p < n) {
-      const int i = p / M;
-      const double* krow = Kc + (long)i * N;
-      v.x = (q < n) ? krow[q / M] * d0 + (p == q ? s2 : 0.0) : 0.0;
-      v.y = (q + 1 < n) ? krow[(q + 1) / M] * d1 + (p == q + 1 ? s2 : 0.0) : 0.0;
+      const double* krow = Ks[p / M - i0];
+      v.x = (q < n) ? krow[q / M - j0] * d0 + (p == q ? s2 : 0.0) : 0.0;
+      v.y = (q + 1 < n) ? krow[(q + 1) / M - j0] * d1 + (p == q + 1 ? s2 : 0.0) : 0.0;
     } else {
       v.x = (p == q) ? 1.0 : 0.0;
       v.y = (p == q + 1) ? 1.0 : 0.0;
@@ -459,13 +465,22 @@ __global__ void __launch_bounds__(128) svc_contract_kernel(const double* __restr
     }
     for (int idx = threadIdx.x; idx < jn * M; idx += 128) ysm[idx] = y[(long)j0 * M + idx];
     __syncthreads();
+    // software pipeline: the M loads of time block j+1 are issued before the arithmetic of block j
+    double zn[M];
+#pragma unroll
+    for (int m2 = 0; m2 < M; ++m2) zn[m2] = Zc[(long)(j0 * M + m2) * ld];
+    double kxn = kr[j0], ckn = cr[j0];
 #pragma unroll 2
     for (int jj = 0; jj < jn; ++jj) {
-      const int j = j0 + jj;
       double z[M];
 #pragma unroll
-      for (int m2 = 0; m2 < M; ++m2) z[m2] = Zc[(long)(j * M + m2) * ld];
-      const double kx = kr[j], ck = cr[j];
+      for (int m2 = 0; m2 < M; ++m2) z[m2] = zn[m2];
+      const double kx = kxn, ck = ckn;
+      const int jnx = min(j0 + jj + 1, N - 1);       // clamped prefetch (the last one is discarded)
+#pragma unroll
+      for (int m2 = 0; m2 < M; ++m2) zn[m2] = Zc[(long)(jnx * M + m2) * ld];
+      kxn = kr[jnx];
+      ckn = cr[jnx];
       const double* lj = Lsm + jj * LS;
       const double* yj = ysm + jj * M;
       double t[M];
@@ -1061,7 +1076,7 @@ int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int 
   const int n = N * M, MT = padded_M(M);
   // one pass over Sigma^-1: alpha and the Sigma^-1 part of the gradient sums
   const int LS = M * M;
-  int JC = (40 * 1024) / ((LS + M) * (int)sizeof(double));
+  int JC = 32;    // time blocks staged per pass: small, so that registers (not shared memory) bound the occupancy
   if (JC > N) JC = N;
   dim3 gc((n + 127) / 128, cs);
   const size_t smem = (size_t)JC * (LS + M) * sizeof(double);

@@ -21,18 +21,22 @@ TOL_TOTAL = 1e-7
 TOL_GRAD = 1e-6
 
 
-def run_plan(g):
+def run_plan(g, engine="auto"):
     from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
     plan = LogPosteriorPlan(g["model"], g["x"], g["Y"], g["hyper"], prior=g["prior"])
+    plan.set_engine(engine)          # a FRESH plan per engine: no state left behind by the other factorisation path
     vals, grad, info = plan.value_and_grad_host(torch.from_numpy(g["pars"]))
     plan.close()
     return vals.numpy()[0], grad.numpy()[0], int(info[0])
 
 
+# "auto" picks the right-looking tile engine for a single subject; "left" forces the batched left-looking / Takahashi
+# engine (with the covariance generated inside the factorisation) that the 10 000-subject sweep uses.
+@pytest.mark.parametrize("engine", ["auto", "left"])
 @pytest.mark.parametrize("name", golden_cases())
-def test_cuda_matches_reference_golden(name, cuda_device):
+def test_cuda_matches_reference_golden(name, engine, cuda_device):
     g = load_golden(name)
-    vals, grad, info = run_plan(g)
+    vals, grad, info = run_plan(g, engine)
     ref = g["vals"]
     assert info == 0
     if not g["prior"]:
