@@ -289,7 +289,9 @@ def ours(a):
     achieved = S * (f_potrf + f_potri) / t_fact / 1e12 if t_fact > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
-                "kernel": "tile_kernel<mode> (DMMA.8x8x4 rank-64 tile updates of potrf/trtri/lauum) + diag_kernel",
+                "kernel": "panel_gemm_kernel<mode> (left-looking potrf + Takahashi inverse, 64x64 DMMA.8x8x4 tiles "
+                          "through a cp.async ring) + diag64_kernel; achieved = S*n^3 flop / (t_potrf + t_potri), "
+                          "phase times from CUDA events inside nmgp_logpost_grad_profile",
                 "peak_source": "FP64 DMMA peak measured on this pool's B200 (tools/fp64_peak.cu, "
                                "profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
                 "algorithmic_flops_per_eval": f_potrf + f_potri,
