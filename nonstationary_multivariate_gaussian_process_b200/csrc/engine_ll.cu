@@ -99,6 +99,10 @@ __device__ __forceinline__ void mma_chunk(const double* __restrict__ SA, const d
 // Measured dead ends (profiles/README.md): prefetch.global.L2 of the operand tiles 3 k-blocks ahead (-2 % : slower),
 // KC = 32 x 2 stages (-1 %), generating the covariance tile inside the LL_UPDATE epilogue instead of reading it
 // (+8 ms in potrf for 6 ms saved in the build kernel: the epilogue's loads sit on the critical path of the tensor pipe).
+// Also measured: fusing the diagonal-block factorisation and the panel solve of a block column into one kernel
+// (one CTA per matrix: pivots, then the W_kk^T multiplies) is 7 ms SLOWER per sweep -- a CTA slot (1/3 of an SM at this
+// register / shared-memory footprint) sits in the latency-bound pivot chain for ~45 us; as its own kernel the chain runs
+// at 4-5 CTAs per SM.
 // One CTA walks a LIST of output tiles of one matrix (tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of this launch) and
 // streams all their k-chunks through ONE cp.async ring: the loads of the next tile are already in flight while the
 // current tile's epilogue runs, so the pipeline never drains between tiles (with one tile per CTA the fill/drain cost
