@@ -44,6 +44,17 @@ struct nmgp_plan {
   // side stream: the GP-prior triangular solves are independent of the factorisation and run beside it
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // host-buffer call: copy streams and per-chunk events, so that the H2D of chunk c+1 and the D2H of chunk c-1 run
+  // under the evaluation of chunk c
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_start = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
+};
+
+// optional per-chunk synchronisation of evaluate(): wait for before[c] on the compute stream, record after[c] on it
+struct ChunkSync {
+  cudaEvent_t* before = nullptr;
+  cudaEvent_t* after = nullptr;
 };
 
 namespace {
@@ -259,6 +270,11 @@ int nmgp_plan_destroy(nmgp_plan* pl) {
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_join) cudaEventDestroy(pl->ev_join);
   if (pl->side) cudaStreamDestroy(pl->side);
+  if (pl->ev_start) cudaEventDestroy(pl->ev_start);
+  for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->ev_done) cudaEventDestroy(e);
+  if (pl->copy_in) cudaStreamDestroy(pl->copy_in);
+  if (pl->copy_out) cudaStreamDestroy(pl->copy_out);
   delete pl;
   return 0;
 }
@@ -324,12 +340,34 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
     if (chunk > S) chunk = S;
     const long maxc = 65535 / pl->nmat;
     if (chunk > maxc) chunk = maxc;
+    // Nothing is gained beyond ~4000 matrices per launch (9+ waves of CTAs); equal chunks of at most that size keep
+    // the workspace small and let the host-buffer call pipeline its copies against the evaluation.
+    const long kMaxMat = 4096;
+    if (chunk * pl->nmat > kMaxMat) {
+      const long per_chunk = kMaxMat / pl->nmat > 0 ? kMaxMat / pl->nmat : 1;
+      const long nch = (S + per_chunk - 1) / per_chunk;
+      chunk = (S + nch - 1) / nch;
+    }
     pl->chunk = (int)chunk;
     if ((rc = alloc_workspace(pl))) break;
     if (pl->nprior) {
       const double a0 = hyper[1], b0 = hyper[2], a1 = hyper[4], b1 = hyper[5];
       if ((rc = factor_prior(pl, a0, b0, pl->Wp0, pl->hld0, st))) break;
       if ((rc = factor_prior(pl, a1, b1, pl->Wp1, pl->hld1, st))) break;
+    }
+    {
+      const int nch = (S + pl->chunk - 1) / pl->chunk;
+      bool ok = cudaStreamCreateWithFlags(&pl->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&pl->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&pl->ev_start, cudaEventDisableTiming) == cudaSuccess;
+      for (int c = 0; ok && c < nch; ++c) {
+        cudaEvent_t e1 = nullptr, e2 = nullptr;
+        ok = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) == cudaSuccess;
+        if (e1) pl->ev_in.push_back(e1);
+        if (e2) pl->ev_done.push_back(e2);
+      }
+      if (!ok) { set_last_error("nmgp_plan_create: creating the copy streams failed"); rc = NMGP_ECUDA; break; }
     }
     if (pl->nprior) {
       if (cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -348,7 +386,7 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
 }
 
 static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st,
-                    float* phase_ms) {
+                    float* phase_ms, const ChunkSync* sync = nullptr) {
   long launches = 0;
   const int N = pl->N, M = pl->M, P = pl->P;
   cudaEvent_t ev[NMGP_NPHASES + 1];
@@ -367,6 +405,8 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     double* vs = vals + (size_t)s0 * NMGP_NVALS;
     double* gs = grad ? grad + (size_t)s0 * P : nullptr;
     int* is = info + s0;
+    const int ci = s0 / pl->chunk;
+    if (sync && sync->before) NMGP_CUDA_TRY(cudaStreamWaitEvent(st, sync->before[ci], 0));
     NMGP_MARK(0);
     if (pl->model == NMGP_NONSEPARABLE) {
       NMGP_TRY(svc_forward(cs, N, M, xs, ps, P, pl->hc, pl->w, b, st, &launches));
@@ -413,6 +453,7 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
       NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
     }
     NMGP_MARK(5);
+    if (sync && sync->after) NMGP_CUDA_TRY(cudaEventRecord(sync->after[ci], st));
     if (phase_ms) {
       NMGP_CUDA_TRY(cudaEventSynchronize(ev[NMGP_NPHASES]));
       for (int i = 0; i < NMGP_NPHASES; ++i) {
@@ -445,12 +486,36 @@ int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, 
   if (!pl || (pl->S > 0 && (!pars_h || !vals_h))) { set_last_error("nmgp_logpost_grad_host: null argument"); return NMGP_EINVAL; }
   if (pl->S == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t SP = (size_t)pl->S * pl->P;
-  NMGP_CUDA_TRY(cudaMemcpyAsync(pl->pars_d, pars_h, SP * sizeof(double), cudaMemcpyHostToDevice, st));
-  NMGP_TRY(nmgp_logpost_grad(pl, pl->pars_d, pl->vals_d, grad_h ? pl->grad_d : nullptr, pl->info_d, stream));
-  NMGP_CUDA_TRY(cudaMemcpyAsync(vals_h, pl->vals_d, (size_t)pl->S * NMGP_NVALS * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (grad_h) NMGP_CUDA_TRY(cudaMemcpyAsync(grad_h, pl->grad_d, SP * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (info_h) NMGP_CUDA_TRY(cudaMemcpyAsync(info_h, pl->info_d, (size_t)pl->S * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const int P = pl->P;
+  const int nch = (pl->S + pl->chunk - 1) / pl->chunk;
+  // fork the copy streams off `st`, so the call stays ordered after whatever the caller queued there
+  NMGP_CUDA_TRY(cudaEventRecord(pl->ev_start, st));
+  NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->copy_in, pl->ev_start, 0));
+  NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->copy_out, pl->ev_start, 0));
+  for (int c = 0; c < nch; ++c) {   // all H2D copies are queued up front: chunk c+1 arrives while chunk c is evaluated
+    const size_t s0 = (size_t)c * pl->chunk;
+    const size_t cs = (size_t)pl->S - s0 < (size_t)pl->chunk ? (size_t)pl->S - s0 : (size_t)pl->chunk;
+    NMGP_CUDA_TRY(cudaMemcpyAsync(pl->pars_d + s0 * P, pars_h + s0 * P, cs * P * sizeof(double), cudaMemcpyHostToDevice,
+                                  pl->copy_in));
+    NMGP_CUDA_TRY(cudaEventRecord(pl->ev_in[c], pl->copy_in));
+  }
+  ChunkSync sync;
+  sync.before = pl->ev_in.data();
+  sync.after = pl->ev_done.data();
+  NMGP_TRY(evaluate(pl, pl->pars_d, pl->vals_d, grad_h ? pl->grad_d : nullptr, pl->info_d, st, nullptr, &sync));
+  for (int c = 0; c < nch; ++c) {   // D2H of chunk c as soon as its evaluation is done, under the evaluation of c+1
+    const size_t s0 = (size_t)c * pl->chunk;
+    const size_t cs = (size_t)pl->S - s0 < (size_t)pl->chunk ? (size_t)pl->S - s0 : (size_t)pl->chunk;
+    NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->copy_out, pl->ev_done[c], 0));
+    NMGP_CUDA_TRY(cudaMemcpyAsync(vals_h + s0 * NMGP_NVALS, pl->vals_d + s0 * NMGP_NVALS, cs * NMGP_NVALS * sizeof(double),
+                                  cudaMemcpyDeviceToHost, pl->copy_out));
+    if (grad_h)
+      NMGP_CUDA_TRY(cudaMemcpyAsync(grad_h + s0 * P, pl->grad_d + s0 * P, cs * P * sizeof(double), cudaMemcpyDeviceToHost,
+                                    pl->copy_out));
+    if (info_h)
+      NMGP_CUDA_TRY(cudaMemcpyAsync(info_h + s0, pl->info_d + s0, cs * sizeof(int), cudaMemcpyDeviceToHost, pl->copy_out));
+  }
+  NMGP_CUDA_TRY(cudaStreamSynchronize(pl->copy_out));
   NMGP_CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
