@@ -102,7 +102,7 @@ def reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, 1),
+        "config": workload_config(a, a.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -287,8 +287,14 @@ def ours(a):
     f_potrf, f_potri = algorithmic_flops(a.model, a.N, a.M)
     t_fact = (phases["potrf"] + phases["potri"]) * 1e-3
     achieved = S * (f_potrf + f_potri) / t_fact / 1e12 if t_fact > 0 else 0.0
+    # DRAM traffic of the same kernels from the committed ncu pass (profiles/r01_launches_w.txt): 341 GB per sweep of
+    # 10 000 subjects over 168 engine launches (3 chunks x 56) -> bytes per launch, scaled to this rank's subjects
+    traffic = 341e9 / 168.0 * (S / 10000.0) if (a.model == "nonseparable" and a.N == 100 and a.M == 6) else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                "traffic_note": "average dram__bytes_read+write per launch over the 168 panel_gemm/diag64 launches of one "
+                                "sweep (ncu, profiles/r01_launches_w.txt); algorithmic minimum (every tile read once "
+                                "per use from L2-missing operands) is ~250 GB per sweep",
                 "kernel": "panel_gemm_kernel<mode> (left-looking potrf + Takahashi inverse, 64x64 DMMA.8x8x4 tiles "
                           "through a cp.async ring) + diag64_kernel; achieved = S*n^3 flop / (t_potrf + t_potri), "
                           "phase times from CUDA events inside nmgp_logpost_grad_profile",

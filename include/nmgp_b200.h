@@ -104,6 +104,17 @@ size_t nmgp_plan_device_bytes(const nmgp_plan* plan);
 int nmgp_plan_chunk(const nmgp_plan* plan);
 int nmgp_plan_block(const nmgp_plan* plan);
 
+/* Device-resident optimiser step for the drivers' MAP loops (`optimizer = torch.optim.Adam(...)`; `optimizer.step()`
+ * after `NegLog.backward()`: Stationary_model.py:112-126, Separable_model.py:158-166, Nonseparable_model_mpisim.py:177-190):
+ * one Adam update (torch.optim.Adam semantics: no weight decay, no amsgrad) of all S parameter vectors in place, so that
+ * `pars` and `grad` never leave the GPU between evaluations.  m, v: first / second moment estimates [S,P] (zero before
+ * step 1); step: 1-based iteration count; frozen: optional [P] bytes, non-zero = parameter is not optimised (the
+ * stationary drivers hold tilde_sigma fixed, Stationary_model.py:88,116); info: optional [S], subjects with
+ * info != 0 (failed factorisation, NaN gradient) are left untouched.  All pointers are device pointers. */
+int nmgp_adam_step(double* pars_dev, const double* grad_dev, double* m_dev, double* v_dev, const int* info_dev,
+                   const unsigned char* frozen_dev, long S, long P, double lr, double beta1, double beta2, double eps,
+                   long step, void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 const char* nmgp_last_error(void);
 

@@ -99,6 +99,9 @@ def _declare(lib):
     lib.nmgp_plan_chunk.argtypes = [c.c_void_p]
     lib.nmgp_plan_block.restype = c.c_int
     lib.nmgp_plan_block.argtypes = [c.c_void_p]
+    lib.nmgp_adam_step.restype = c.c_int
+    lib.nmgp_adam_step.argtypes = [dp, dp, dp, dp, ip, dp, c.c_long, c.c_long, c.c_double, c.c_double, c.c_double,
+                                   c.c_double, c.c_long, vp]
     lib.nmgp_rbf_cov.restype = c.c_int
     lib.nmgp_rbf_cov.argtypes = [dp, c.c_int, dp, c.c_int, c.c_double, c.c_double, dp, vp]
     lib.nmgp_gibbs_cov.restype = c.c_int
@@ -114,7 +117,7 @@ def _declare(lib):
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
-           "nmgp_plan_block", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
+           "nmgp_plan_block", "nmgp_adam_step", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 
 

@@ -182,6 +182,35 @@ class LogPosteriorPlan:
         value_and_grad_host(buf, pinned_io=True) to avoid an extra host copy."""
         return self._pinned_buffers()[0]
 
+    # ------------------------------------------------------------------ device-resident MAP loop
+    def map_fit(self, pars0, steps: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, frozen=None,
+                record_every: int = 1):
+        """The drivers' MAP loop (Adam on `nlogpos_obj*`: Stationary_model.py:106-131, Separable_model.py:149-231,
+        Nonseparable_model_mpisim.py:163-207) for all S subjects at once, entirely on the device: per iteration one
+        batched value+gradient evaluation and one `nmgp_adam_step`; `pars` and `grad` never cross PCIe.
+        pars0 [S,P] (host or device) -> (pars [S,P] CUDA, trace [steps/record_every, S, 6] CUDA of the value tuples
+        *before* each recorded update, info [S])."""
+        torch = _lib.require_cuda()
+        p = torch.as_tensor(pars0, dtype=torch.float64).to(self.device).reshape(self.S, self.P).clone().contiguous()
+        m = torch.zeros_like(p)
+        v = torch.zeros_like(p)
+        fz = None
+        if frozen is not None:
+            fz = torch.as_tensor(frozen, dtype=torch.bool).reshape(self.P).to(self.device).to(torch.uint8).contiguous()
+        trace = []
+        info = None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            for it in range(1, steps + 1):
+                vals, grad, info = self.value_and_grad(p)
+                if (it - 1) % record_every == 0:
+                    trace.append(vals)
+                rc = self.lib.nmgp_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), info.data_ptr(),
+                                             fz.data_ptr() if fz is not None else None, self.S, self.P, float(lr),
+                                             float(betas[0]), float(betas[1]), float(eps), it, ctypes.c_void_p(stream))
+                _lib.check(rc, "nmgp_adam_step")
+        return p, (torch.stack(trace) if trace else torch.empty((0, self.S, _lib.NVALS), device=self.device)), info
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
             self.lib.nmgp_plan_destroy(self._handle)

@@ -189,6 +189,28 @@ int factor_prior(nmgp_plan* pl, double alpha, double beta, double* Wp, double* h
   return 0;
 }
 
+// torch.optim.Adam's update, element-wise over all subjects (same operation order as torch's single-tensor path:
+// exp_avg.lerp_(grad, 1-beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2);
+// denom = exp_avg_sq.sqrt() / sqrt(bias_correction2) + eps; param.addcdiv_(exp_avg, denom, -lr / bias_correction1))
+__global__ void __launch_bounds__(256) adam_kernel(double* __restrict__ pars, const double* __restrict__ grad,
+                                                   double* __restrict__ m, double* __restrict__ v,
+                                                   const int* __restrict__ info, const unsigned char* __restrict__ frozen,
+                                                   long S, long P, double beta1, double beta2, double eps,
+                                                   double step_size, double sqrt_bc2) {
+  const long total = S * P;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long s = idx / P, j = idx - s * P;
+    if ((info && info[s] != 0) || (frozen && frozen[j])) continue;
+    const double g = grad[idx];
+    const double mi = m[idx] + (g - m[idx]) * (1.0 - beta1);
+    const double vi = v[idx] * beta2 + (1.0 - beta2) * g * g;
+    m[idx] = mi;
+    v[idx] = vi;
+    const double denom = sqrt(vi) / sqrt_bc2 + eps;
+    pars[idx] -= step_size * (mi / denom);
+  }
+}
+
 __global__ void pack_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, long strideA, int ld) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = blockIdx.y;
@@ -517,6 +539,20 @@ int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, 
   }
   NMGP_CUDA_TRY(cudaStreamSynchronize(pl->copy_out));
   NMGP_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int nmgp_adam_step(double* pars, const double* grad, double* m, double* v, const int* info, const unsigned char* frozen,
+                   long S, long P, double lr, double beta1, double beta2, double eps, long step, void* stream) {
+  if (!pars || !grad || !m || !v || S < 0 || P <= 0 || step < 1) { set_last_error("nmgp_adam_step: bad arguments"); return NMGP_EINVAL; }
+  if (S == 0) return 0;
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  const long total = S * P;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pars, grad, m, v, info, frozen, S, P, beta1, beta2, eps,
+                                                             lr / bc1, std::sqrt(bc2));
+  NMGP_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -1014,7 +1014,9 @@ int launch_prior_solve(const double* Lp, const double* rhs, double* out, int cs,
                        cudaStream_t st, long* launches) {
   if (cs <= 0 || nv <= 0) return 0;
   const int nvc32 = (nv + 31) / 32;
-  if ((long)cs * nvc32 >= 592) {   // >= one warp per SM sub-partition: the warp-per-problem kernel wins
+  // warp-per-problem kernel only when there are enough problems to fill the GPU (>= one warp per SM sub-partition); for
+  // a handful of subjects one warp's serial N^2/2 FMAs lose to the blocked path below (measured: N=500 4.9 vs 1.4 ms)
+  if ((long)cs * nvc32 >= 592) {
     const int grid = (int)(((long)cs * nvc32 + PWB - 1) / PWB);
     if (trans) prior_solve_warp_kernel<1><<<grid, 32 * PWB, 0, st>>>(Lp, rhs, out, cs, N, nv, nvc32);
     else prior_solve_warp_kernel<0><<<grid, 32 * PWB, 0, st>>>(Lp, rhs, out, cs, N, nv, nvc32);

@@ -25,7 +25,7 @@ __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-template <int LOAD, int SYNC, int WARPS, int KC, int STAGES, int MINB>
+template <int LOAD, int SYNC, int WARPS, int KC, int STAGES, int MINB, int NOMMA = 0, int PF = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_tile(const double* __restrict__ A, const double* __restrict__ B,
                                                            double* __restrict__ C, int nchunks, int ld) {
   extern __shared__ __align__(16) double smem[];
@@ -65,6 +65,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_tile(const double* __restr
     if (LOAD) cp_async_wait<STAGES - 2>();
     if (SYNC) __syncthreads();
     if (LOAD) { if (q + STAGES - 1 < nchunks) issue(q + STAGES - 1); cp_async_commit(); }
+    if (PF > 0 && q + PF < nchunks && threadIdx.x < NB) {   // one 128-byte line of the A panel per thread, PF chunks ahead
+      const double* pa = At + (long)threadIdx.x * ld + (q + PF) * KC;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+    }
+    if (NOMMA) { if (q == nchunks - 1) acc[0][0][0] = smem[(q % STAGES) * 2 * OPSZ + threadIdx.x]; continue; }
     const double* S = smem + (q % STAGES) * 2 * OPSZ;
     const double* pa = S + (m0 + lr) * LDK + lk;
     const double* pb = S + OPSZ + (n0 + lr) * LDK + lk;
@@ -93,9 +98,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_tile(const double* __restr
     }
 }
 
-template <int LOAD, int SYNC, int WARPS, int KC, int STAGES, int MINB>
+template <int LOAD, int SYNC, int WARPS, int KC, int STAGES, int MINB, int NOMMA = 0, int PF = 0>
 void run(const char* name, const double* A, const double* B, double* C, int ntiles, int K, int ld) {
-  auto kern = k_tile<LOAD, SYNC, WARPS, KC, STAGES, MINB>;
+  auto kern = k_tile<LOAD, SYNC, WARPS, KC, STAGES, MINB, NOMMA, PF>;
   const size_t smem = (size_t)STAGES * 2 * NB * (KC + 4) * sizeof(double);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -112,7 +117,8 @@ void run(const char* name, const double* A, const double* B, double* C, int ntil
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     if (ms < best) best = ms;
   }
-  printf("%-58s occ %d CTA/SM  %7.2f TF/s  (%.3f ms)\n", name, occ, 2.0 * NB * NB * (double)K * ntiles / best * 1e-9, best);
+  printf("%-58s occ %d CTA/SM  %7.2f TF/s  %6.2f TB/s of A-panel reads  (%.3f ms)\n", name, occ,
+         2.0 * NB * NB * (double)K * ntiles / best * 1e-9, (double)ntiles * NB * K * 8 / best * 1e-9, best);
 }
 
 int main() {
@@ -134,5 +140,12 @@ int main() {
   run<1, 1, 8, 16, 3, 2>("cp.async ring KC16 x3, barrier, 8 warps, 2 CTA/SM", A, B, C, ntiles, K, ld);
   run<1, 1, 8, 16, 3, 3>("cp.async ring KC16 x3, barrier, 8 warps, 3 CTA/SM", A, B, C, ntiles, K, ld);
   run<1, 1, 8, 32, 2, 3>("cp.async ring KC32 x2, barrier, 8 warps, 3 CTA/SM", A, B, C, ntiles, K, ld);
+  // streaming only (no MMA): what HBM rate can the ring sustain by itself, and does an L2 prefetch ahead of it help?
+  run<1, 1, 4, 16, 3, 3, 1, 0>("stream only: ring KC16 x3, 3 CTA/SM", A, B, C, ntiles, K, ld);
+  run<1, 1, 4, 16, 3, 3, 1, 8>("stream only: ring KC16 x3 + L2 prefetch 8 chunks ahead", A, B, C, ntiles, K, ld);
+  run<1, 1, 4, 16, 3, 3, 1, 16>("stream only: ring KC16 x3 + L2 prefetch 16 chunks ahead", A, B, C, ntiles, K, ld);
+  run<1, 1, 4, 32, 2, 3, 1, 0>("stream only: ring KC32 x2, 3 CTA/SM", A, B, C, ntiles, K, ld);
+  run<1, 1, 4, 16, 4, 2, 1, 0>("stream only: ring KC16 x4, 2 CTA/SM", A, B, C, ntiles, K, ld);
+  run<1, 1, 4, 16, 3, 3, 0, 8>("MMA + ring KC16 x3 + L2 prefetch 8 ahead", A, B, C, ntiles, K, ld);
   return 0;
 }
