@@ -110,7 +110,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   const size_t MT = pl->model == NMGP_NONSEPARABLE ? padded_M(pl->M) : 0;
   size_t d = 0;
   d += nm * nP * nP;            // A
-  d += 2 * nm * Kt * kNB * kNB; // Dinv, Pbuf
+  d += 3 * nm * Kt * kNB * kNB; // Dinv (W and W^T), Pbuf
   d += nm;                      // logdet
   d += 2 * N + 1;               // ell, sig, s2
   d += pl->model == NMGP_NONSEPARABLE ? n * MT : M * M;  // Lst
@@ -129,7 +129,7 @@ int alloc_workspace(nmgp_plan* pl) {
   BlockBatch& b = pl->bb;
   b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
   NMGP_TRY(dev_alloc(pl, &b.A, cs * nm * (size_t)pl->nP * pl->nP));
-  NMGP_TRY(dev_alloc(pl, &b.Dinv, cs * nm * (size_t)pl->Kt * kNB * kNB));
+  NMGP_TRY(dev_alloc(pl, &b.Dinv, cs * nm * (size_t)pl->Kt * 2 * kNB * kNB));
   NMGP_TRY(dev_alloc(pl, &b.Pbuf, cs * nm * (size_t)pl->Kt * kNB * kNB));
   // the left-looking engine multiplies padding / not-yet-written upper tiles by exact zeros: they must be finite
   NMGP_CUDA_TRY(cudaMemsetAsync(b.A, 0, cs * nm * (size_t)pl->nP * pl->nP * sizeof(double), 0));
@@ -462,7 +462,13 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     const bool ll = b.Pbuf != nullptr && (pl->engine_mode == 2 || (pl->engine_mode == 0 && prefer_left_looking(b)));
     if (ll) NMGP_TRY(engine_potrf_ll(b, st, &launches)); else NMGP_TRY(engine_potrf(b, st, &launches));
     NMGP_MARK(2);
-    if (ll) NMGP_TRY(engine_potri_ll(b, st, &launches)); else NMGP_TRY(engine_potri(b, st, &launches));
+    // The Takahashi sweep propagates the error of the trailing inverse block into every new block column, multiplied by
+    // |L(B,j) L_jj^-1| -- for smooth GP covariances that factor exceeds 1 and the error grows geometrically with the number
+    // of block columns (measured: exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64).  It is therefore used only up to
+    // kTakahashiMaxBlocks block columns; beyond, the inverse is formed as W^T W from the triangular inverse (backward
+    // stable) by the tile-task engine, on the factor the left-looking potrf produced (same layout).
+    if (ll && b.Kt <= kTakahashiMaxBlocks) NMGP_TRY(engine_potri_ll(b, st, &launches));
+    else NMGP_TRY(engine_potri(b, st, &launches));
     NMGP_MARK(3);
     if (overlap) NMGP_CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
     else NMGP_TRY(prior_solves());

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
 
   for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
     double* Am = g.A + (long)mat * g.strideA;
-    const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * NB * NB;
+    const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * 2 * NB * NB;   // slot 0: W_kk
     const double* srcA = (ai < 0) ? Dm : Am + ((long)ai * NB) * g.ld + (long)aj * NB;
     const double* srcB = (bi < 0) ? Dm : Am + ((long)bi * NB) * g.ld + (long)bj * NB;
     load_tile(SA, srcA, ai < 0 ? NB : g.ld);

@@ -8,11 +8,14 @@ namespace nmgp {
 //   A      [batch][nP][nP] row-major, nP = Kt*NB >= n; rows/cols >= n hold the identity, so the padded
 //          matrix is diag(Sigma, I): its factor is diag(L, I), its inverse diag(Sigma^-1, I), and no kernel
 //          needs edge predication.
-//   Dinv   [batch][Kt][NB*NB]  inverses of the diagonal blocks of L (full tiles, zero upper), written by potrf.
+//   Dinv   [batch][Kt][2][NB*NB]  W_kk = inverse of the diagonal block of L (full tile, zero upper) and its transpose
+//          W_kk^T, written by the diagonal-block kernel.  Both exist so that every operand of the left-looking
+//          engine is K-MAJOR (row = output index, column = summation index): one TMA box shape, one swizzle.
 struct BlockBatch {
   double* A = nullptr;
   double* Dinv = nullptr;
-  double* Pbuf = nullptr;    // [batch][Kt][NB*NB]  panel side buffer of the left-looking inverse (zero-initialised once)
+  double* Pbuf = nullptr;    // [batch][Kt][NB*NB]  panel side buffer of the left-looking inverse: P(c)^T tiles (zero-initialised once)
+  long strideP() const { return (long)Kt * NB * NB; }
   double* logdet = nullptr;  // [batch]
   int* info = nullptr;       // [batch]
   int n = 0;                 // logical dimension
@@ -21,7 +24,7 @@ struct BlockBatch {
   int NB = 64;
   int batch = 0;
   long strideA() const { return (long)nP * nP; }
-  long strideD() const { return (long)Kt * NB * NB; }
+  long strideD() const { return (long)Kt * 2 * NB * NB; }
 };
 
 constexpr int kNB = 64;
@@ -45,6 +48,8 @@ int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches
 // (the plan zero-fills the workspace once).
 int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches);
 int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches);
+// largest number of 64-blocks per side for which the Takahashi recursion of engine_potri_ll is used (see api.cu)
+constexpr int kTakahashiMaxBlocks = 16;
 
 // Heuristic: the left-looking path launches (Kt - k) * batch CTAs per block column, each a long K loop; it needs about
 // two waves of them (148 SMs x 3 resident CTAs) on average to keep the tensor pipes busy.  Measured on B200: n = 16 384

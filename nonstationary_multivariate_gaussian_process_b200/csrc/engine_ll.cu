@@ -1,133 +1,116 @@
-// Left-looking batched Cholesky + "Takahashi" inverse for many mid-size matrices (the 10 000 x (n=600) regime).
+// Left-looking batched Cholesky + "Takahashi" inverse for many mid-size matrices (the 10 000 x (n=600) regime) and for
+// batches of large ones.  FP64 tensor cores (DMMA.8x8x4) fed by TMA.
 //
-// The right-looking tile tasks of engine.cu read AND write every trailing tile at every block step: at n = 600 that is
-// ~80 MB of traffic per matrix and the kernels sit on the HBM roof at ~45 % of the FP64 tensor peak (profiles/r01).
-// Here every output tile is produced ONCE: a CTA accumulates its 64 x 64 tile over the whole K range in registers
-// (DMMA.8x8x4), streaming the two operand row-panels through a 3-stage cp.async pipeline in shared memory.
+// The right-looking tile tasks of engine.cu read AND write every trailing tile at every block step.  Here every output
+// tile is produced ONCE: a CTA accumulates its 64 x 64 tile over the whole K range in registers, streaming the two
+// operand row-panels through a shared-memory ring.
 //
 //   potrf, block column k:   A(i,k) <- A(i,k) - sum_{j<k} A(i,j) A(k,j)^T        (LL_UPDATE,  i >= k)
-//                            diag_kernel: A(k,k) = L L^T, W_kk = L^-1, log det
+//                            diag64_kernel: A(k,k) = L L^T, W_kk = L^-1, W_kk^T, log det
 //                            A(i,k) <- A(i,k) W_kk^T                              (LL_SOLVE,   i > k)
 //   inverse, block column j descending (Z = Sigma^-1, stored full symmetric, in place over L):
-//                            P(c)   = -L(c,j) W_jj                                (TK_PANEL,   c > j, side buffer)
+//                            P(c)   = -L(c,j) W_jj   (stored transposed)          (TK_PANEL,   c > j, side buffer)
 //                            Z(i,j) = sum_{c>j} Z(i,c) P(c),  Z(j,i) = Z(i,j)^T   (TK_COL,     i > j)
 //                            Z(j,j) = W_jj^T W_jj + sum_{c>j} P(c)^T Z(c,j)       (TK_DIAG)
-// Flops: n^3/3 + 2n^3/3, the same as potrf + potri; every A/B operand tile is read once per use, C never re-read.
+// Flops: n^3/3 + 2n^3/3, the same as potrf + potri; every operand tile is read once per use, C never re-read.
+//
+// Operand staging.  Every product is arranged so that BOTH operands are K-MAJOR tiles (row = output index, column =
+// summation index): W_kk^T and P(c)^T are stored beside / instead of W_kk and P(c), and Z(c,j) is read through its
+// mirror Z(j,c).  One TMA box shape (16 k x 64 rows = 64 rows of 128 bytes) then serves everything:
+// cp.async.bulk.tensor.3d {k, row, matrix} with the hardware 128-byte swizzle, issued by ONE elected thread per chunk,
+// completion signalled on an mbarrier -- no per-thread address arithmetic, no padding in shared memory (48 KB ring,
+// 3 stages).  The DMMA fragments are read bank-conflict free from the swizzled rows by choosing WHICH four k's a k-step
+// multiplies: {2s, 2s+1, 2s+8, 2s+9} for s = 0..3 (the order of the summation index is free as long as A and B agree).
+// tools/dmma_pipe.cu measures this ring at 35.7 TFLOP/s (96 % of the 37.15 DMMA peak) against 34.6 for the cp.async
+// ring with padded rows it replaces, bit-identical results.
+//
+// One CTA walks a LIST of output tiles of one matrix (tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of this launch) and
+// streams all their k-chunks through ONE ring: the loads of the next tile are already in flight while the current
+// tile's epilogue runs.  The epilogue works from registers only (the mirror of the symmetric inverse and P^T are
+// direct transposed stores: 8 lanes write 64 contiguous bytes), so shared memory belongs to the ring at all times.
+//
+// Measured dead ends (profiles/README.md): prefetch.global.L2 of the operand tiles 3 k-blocks ahead (-2 %), KC = 32 x 2
+// stages (-1 %), generating the covariance tile inside the LL_UPDATE epilogue instead of reading it (+8 ms in potrf for
+// 6 ms saved in the build kernel), fusing the diagonal-block factorisation into the panel-solve kernel (+7 ms: a CTA
+// slot idles in the pivot chain).
 #include "engine.cuh"
+
+#include <cuda.h>
+
+#include <cstdint>
+#include <mutex>
+#include <vector>
 
 namespace nmgp {
 
 namespace {
 
 constexpr int NB = kNB;      // 64
-constexpr int KC = 16;       // k-chunk per pipeline stage (tools/dmma_pipe.cu: 16 x 3 stages beats 32 x 2 and 8 x 4)
+constexpr int KC = 16;       // k-chunk per pipeline stage = one 128-byte swizzle row
+constexpr int CPB = NB / KC; // chunks per k-block
 constexpr int STAGES = 3;
-constexpr int LDK = KC + 4;  // k-major chunk [64][20]   (== 4 mod 16: conflict-free fragment loads)
-constexpr int LDM = NB + 4;  // m-major chunk [16][68]
-constexpr int OPSZ = NB * LDK;  // 1280 doubles >= KC*LDM = 1088
+constexpr int OPB = NB * KC * 8;   // bytes of one operand chunk in shared memory (dense, swizzled): 8192
 constexpr int THREADS = 128;
-constexpr size_t LL_SMEM = (size_t)STAGES * 2 * OPSZ * sizeof(double);  // 61 440 B -> 3 CTAs / SM
+constexpr size_t LL_SMEM = (size_t)STAGES * 2 * OPB + 64 + 1024;   // ring + mbarriers + slack for 1024-byte alignment
 
 enum LLMode : int { LL_UPDATE = 0, LL_SOLVE = 1, TK_PANEL = 2, TK_COL = 3, TK_DIAG = 4 };
 
 struct LLArgs {
   double* A;
-  double* Dinv;
   double* Pbuf;
-  long strideA, strideD, strideP;
+  long strideA, strideP;
   int ld, Kt, batch, step, n8, ntiles;
 };
 
-// cp.async with an L2 eviction-priority hint.  The streamed operand (tiles of the matrix that this launch reads once)
-// is marked evict_first, the operand every row tile of a block column re-reads (the P / row-s panel, the W_kk tile)
-// evict_last: without the hints the streamed tiles flush the shared panel out of the 126 MB L2 before its next use
-// (ncu: 157 GB of DRAM traffic per sweep in the Takahashi column kernel against 106 GB algorithmic).
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier PTX
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async16(double* smem, const double* gmem, unsigned long long policy) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "l"(policy));
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-// issue the copies of one k-chunk of one operand tile
-template <bool KM>
-__device__ __forceinline__ void issue_chunk(double* S, const double* tile, int ld, int kc, unsigned long long policy) {
-  constexpr int V = KC / 2;               // 16-byte vectors per row of a k-major chunk
-  constexpr int ITERS = NB * V / THREADS; // copies per thread (both layouts move NB*KC doubles)
-  if (KM) {  // rows 0..63, columns kc*KC .. +KC  ->  S[row][LDK]
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int idx = threadIdx.x + it * THREADS;
-      const int r = idx / V, c2 = idx % V;
-      cp_async16(S + r * LDK + 2 * c2, tile + (long)r * ld + kc * KC + 2 * c2, policy);
-    }
-  } else {   // rows kc*KC .. +KC, columns 0..63  ->  S[k][LDM]
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int idx = threadIdx.x + it * THREADS;
-      const int r = idx >> 5, c2 = idx & 31;
-      cp_async16(S + r * LDM + 2 * c2, tile + (long)(kc * KC + r) * ld + 2 * c2, policy);
-    }
-  }
+// one 16 (k) x 64 (rows) box of matrix / tile `c2`, landing as 64 swizzled 128-byte rows
+__device__ __forceinline__ void tma_load_chunk(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool A_KM, bool B_KM>
-__device__ __forceinline__ void mma_chunk(const double* __restrict__ SA, const double* __restrict__ SB, int m0, int n0,
-                                          double (&acc)[4][4][2]) {
-  const int lane = threadIdx.x & 31;
-  const int lr = lane >> 2, lk = lane & 3;
-  const double* pa = A_KM ? SA + (m0 + lr) * LDK + lk : SA + lk * LDM + m0 + lr;
-  const double* pb = B_KM ? SB + (n0 + lr) * LDK + lk : SB + lk * LDM + n0 + lr;
-  constexpr int a_sub = A_KM ? 8 * LDK : 8;
-  constexpr int b_sub = B_KM ? 8 * LDK : 8;
-  constexpr int a_k = A_KM ? 4 : 4 * LDM;
-  constexpr int b_k = B_KM ? 4 : 4 * LDM;
+// acc(32 x 32 of this warp) += A(32 x 16) * B(32 x 16)^T for one chunk.  SA / SB point at row (m0 + lr) / (n0 + lr) of the
+// operand chunks; off[s] is the lane's swizzled byte offset inside a 128-byte row for k-step s.
+__device__ __forceinline__ void mma_chunk(const unsigned char* __restrict__ SA, const unsigned char* __restrict__ SB,
+                                          const int (&off)[4], double (&acc)[4][4][2]) {
 #pragma unroll
-  for (int k = 0; k < KC; k += 4) {
+  for (int s = 0; s < 4; ++s) {
     double a[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      a[i] = pa[i * a_sub];
-      b[i] = pb[i * b_sub];
+      a[i] = *reinterpret_cast<const double*>(SA + i * 1024 + off[s]);   // next 8-row group: 8 rows x 128 B
+      b[i] = *reinterpret_cast<const double*>(SB + i * 1024 + off[s]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    pa += a_k;
-    pb += b_k;
   }
 }
 
-// Measured dead ends (profiles/README.md): prefetch.global.L2 of the operand tiles 3 k-blocks ahead (-2 % : slower),
-// KC = 32 x 2 stages (-1 %), generating the covariance tile inside the LL_UPDATE epilogue instead of reading it
-// (+8 ms in potrf for 6 ms saved in the build kernel: the epilogue's loads sit on the critical path of the tensor pipe).
-// Also measured: fusing the diagonal-block factorisation and the panel solve of a block column into one kernel
-// (one CTA per matrix: pivots, then the W_kk^T multiplies) is 7 ms SLOWER per sweep -- a CTA slot (1/3 of an SM at this
-// register / shared-memory footprint) sits in the latency-bound pivot chain for ~45 us; as its own kernel the chain runs
-// at 4-5 CTAs per SM.
-// One CTA walks a LIST of output tiles of one matrix (tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of this launch) and
-// streams all their k-chunks through ONE cp.async ring: the loads of the next tile are already in flight while the
-// current tile's epilogue runs, so the pipeline never drains between tiles (with one tile per CTA the fill/drain cost
-// 20-30 % of the short panel modes).  The epilogue works from registers only (the mirror of the symmetric inverse is a
-// direct transposed store: 8 lanes write 64 contiguous bytes), so shared memory belongs to the ring at all times.
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
-  extern __shared__ __align__(16) double smem[];
-  constexpr bool A_KM = (MODE == LL_UPDATE || MODE == LL_SOLVE || MODE == TK_PANEL || MODE == TK_COL);
-  constexpr bool B_KM = (MODE == LL_UPDATE || MODE == LL_SOLVE);
-  constexpr int CPB = NB / KC;   // chunks per k-block
+__global__ void __launch_bounds__(THREADS, 4) panel_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                const __grid_constant__ CUtensorMap mapD,
+                                                                const __grid_constant__ CUtensorMap mapP, LLArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
+
   const int s = g.step;
   const int last = g.Kt - 1;
   const int vlast = g.n8 - last * NB;  // valid rows/cols of the last block (multiple of 8)
@@ -145,12 +128,16 @@ __global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
   const int cols_valid = (j == last) ? vlast : NB;
 
   // Quarter of the tile owned by this warp.  The quarters do unequal work in the triangular modes below and every
-  // warp is pinned to one SM sub-partition (one DMMA pipe each), so the assignment is rotated per CTA: over the CTAs
-  // resident on an SM the light and heavy quarters then spread over all four pipes.
+  // warp is pinned to one SM sub-partition (one DMMA pipe each), so the assignment is rotated per CTA.
   const int warp = ((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & 3, lane = threadIdx.x & 31;
   const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
   const int r = lane >> 2, c = 2 * (lane & 3);
+  const int lr = lane >> 2, lk = lane & 3;
   const bool upper_quarter = (m0 == 0 && n0 == NB / 2);
+  // per-lane swizzled byte offsets of the four k-steps: 16-byte slot (s + 4*(lk>>1)) ^ (row & 7), half lk & 1
+  int off[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) off[ks] = (((ks + 4 * (lk >> 1)) ^ lr) << 4) + (lk & 1) * 8;
   // k-chunks that only multiply structural zeros of the triangular W = L_kk^-1 (W[a][b] = 0 for b > a):
   //   LL_SOLVE  C[m][n] = sum_k A[m][k] W[n][k]   -> columns n < 32 need k < 32 only
   //   TK_PANEL  C[m][n] = sum_k L[m][k] W[k][n]   -> columns n >= 32 need k >= 32 only
@@ -172,42 +159,53 @@ __global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
   const int nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int total = nmy * nchunks;
 
-  const unsigned long long pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int gq = 0;   // chunks consumed by this CTA so far (all matrices): ring slot and mbarrier phase follow it
+
   for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
     double* Am = g.A + (long)mat * g.strideA;
-    const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * NB * NB;
     double* Pm = g.Pbuf + (long)mat * g.strideP;
+    const int dslot = (mat * g.Kt + s) * 2;    // W_ss (slot + 0) and W_ss^T (slot + 1) in the Dinv tensor
+    const int pslot = mat * g.Kt;              // P(c)^T tiles of this matrix in the Pbuf tensor
 
+    // producer side (thread 0 only): the next chunk of this matrix -> ring slot `slot`
     int itt = 0, iqq = 0;   // tile / chunk-in-tile of the next chunk to be issued
-    auto issue = [&](int q) {
+    auto issue = [&](int slot) {
       const int tt = itt, qq = iqq;
       if (++iqq == nchunks) { iqq = 0; ++itt; }
       const int i = tile_row(tt);
-      const int kb = qq / CPB, kc = qq % CPB;
-      const double *ta, *tb;
-      int lda, ldb;
-      if (MODE == LL_UPDATE) {
-        ta = Am + ((long)i * NB) * g.ld + (long)kb * NB; lda = g.ld;
-        tb = Am + ((long)s * NB) * g.ld + (long)kb * NB; ldb = g.ld;
-      } else if (MODE == LL_SOLVE || MODE == TK_PANEL) {
-        ta = Am + ((long)i * NB) * g.ld + (long)s * NB; lda = g.ld;
-        tb = Dm; ldb = NB;
-      } else if (MODE == TK_COL) {
+      const int kb = qq / CPB, kcol = (qq % CPB) * KC;
+      unsigned char* SA = ring + slot * 2 * OPB;
+      unsigned char* SB = SA + OPB;
+      unsigned long long* bar = &full[slot];
+      mbar_expect_tx(bar, 2 * OPB);
+      if (MODE == LL_UPDATE) {          // A(i,kb) . A(s,kb)^T
+        tma_load_chunk(SA, &mapA, kb * NB + kcol, i * NB, mat, bar);
+        tma_load_chunk(SB, &mapA, kb * NB + kcol, s * NB, mat, bar);
+      } else if (MODE == LL_SOLVE) {    // A(i,s) . W^T          (B[n][k] = W[n][k])
+        tma_load_chunk(SA, &mapA, s * NB + kcol, i * NB, mat, bar);
+        tma_load_chunk(SB, &mapD, kcol, 0, dslot, bar);
+      } else if (MODE == TK_PANEL) {    // L(i,s) . W            (B[n][k] = W^T[n][k])
+        tma_load_chunk(SA, &mapA, s * NB + kcol, i * NB, mat, bar);
+        tma_load_chunk(SB, &mapD, kcol, 0, dslot + 1, bar);
+      } else if (MODE == TK_COL) {      // Z(i,cb) . P(cb)       (B[n][k] = P^T(cb)[n][k])
         const int cb = s + 1 + kb;
-        ta = Am + ((long)i * NB) * g.ld + (long)cb * NB; lda = g.ld;
-        tb = Pm + (long)cb * NB * NB; ldb = NB;
+        tma_load_chunk(SA, &mapA, cb * NB + kcol, i * NB, mat, bar);
+        tma_load_chunk(SB, &mapP, kcol, 0, pslot + cb, bar);
       } else {
-        if (kb == 0) { ta = Dm; lda = NB; tb = Dm; ldb = NB; }
-        else {
+        if (kb == 0) {                  // W^T W                 (A[m][k] = W^T[m][k], B[n][k] = W^T[n][k])
+          tma_load_chunk(SA, &mapD, kcol, 0, dslot + 1, bar);
+          tma_load_chunk(SB, &mapD, kcol, 0, dslot + 1, bar);
+        } else {                        // P(cb)^T Z(cb,s)       (A[m][k] = P^T(cb)[m][k], B[n][k] = Z(s,cb)[n][k])
           const int cb = s + kb;
-          ta = Pm + (long)cb * NB * NB; lda = NB;
-          tb = Am + ((long)cb * NB) * g.ld + (long)s * NB; ldb = g.ld;
+          tma_load_chunk(SA, &mapP, kcol, 0, pslot + cb, bar);
+          tma_load_chunk(SB, &mapA, cb * NB + kcol, s * NB, mat, bar);
         }
       }
-      double* S = smem + (q % STAGES) * 2 * OPSZ;
-      // which operand is the streamed one: A everywhere except TK_DIAG, where A is the shared P panel / W tile
-      issue_chunk<A_KM>(S, ta, lda, kc, MODE == TK_DIAG ? pol_keep : pol_stream);
-      issue_chunk<B_KM>(S + OPSZ, tb, ldb, kc, (MODE == TK_DIAG && kb > 0) ? pol_stream : pol_keep);
     };
 
     double acc[4][4][2];
@@ -216,38 +214,23 @@ __global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-#pragma unroll
-    for (int q = 0; q < STAGES - 1; ++q) {
-      if (q < total) issue(q);
-      cp_async_commit();
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll 1
+      for (int q = 0; q < STAGES - 1 && q < total; ++q) issue((gq + q) % STAGES);
     }
-    int tt = 0, qq = 0;
-    for (int q = 0; q < total; ++q) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      if (q + STAGES - 1 < total) issue(q + STAGES - 1);
-      cp_async_commit();
-      const int i = tile_row(tt);
-      const int rows_valid = (i == last) ? vlast : NB;
-      // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
-      // of A(k,k); Z(j,j) is symmetric and mirrored below)
-      const bool tri_skip = upper_quarter && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
-      const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
-      if (active && !zero_chunk(qq)) {
-        const double* S = smem + (q % STAGES) * 2 * OPSZ;
-        mma_chunk<A_KM, B_KM>(S, S + OPSZ, m0, n0, acc);
-      }
-      if (++qq < nchunks) continue;
-      // ---- epilogue of tile (i, j)
+    // ---- epilogue of tile (i, j): registers only
+    auto epilogue = [&](int i, bool active) {
       if (active) {
-        if (MODE == TK_PANEL) {
-          double* C = Pm + (long)i * NB * NB;
+        if (MODE == TK_PANEL) {   // P(i)^T = -(L(i,s) W)^T
+          double* PT = Pm + (long)i * NB * NB;
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              double2 v; v.x = -acc[a][b][0]; v.y = -acc[a][b][1];
-              *reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * NB + n0 + 8 * b + c) = v;
+              const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
+              PT[(long)col * NB + row] = -acc[a][b][0];
+              PT[(long)(col + 1) * NB + row] = -acc[a][b][1];
             }
         } else {
           double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
@@ -281,17 +264,101 @@ __global__ void __launch_bounds__(THREADS, 3) panel_gemm_kernel(LLArgs g) {
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    };
+
+    int tt = 0, qq = 0;
+    for (int q = 0; q < total; ++q) {
+      const int slot = (gq + q) % STAGES;
+      __syncthreads();                 // every warp is done with the previous chunk: its slot may be refilled
+      if (threadIdx.x == 0 && q + STAGES - 1 < total) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue((gq + q + STAGES - 1) % STAGES);
+      }
+      const int i = tile_row(tt);
+      const int rows_valid = (i == last) ? vlast : NB;
+      // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
+      // of A(k,k); Z(j,j) is symmetric and mirrored in the epilogue)
+      const bool tri_skip = upper_quarter && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
+      const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
+      mbar_wait(&full[slot], ((gq + q) / STAGES) & 1);
+      if (active && !zero_chunk(qq)) {
+        const unsigned char* SA = ring + slot * 2 * OPB;
+        mma_chunk(SA + (m0 + lr) * 128, SA + OPB + (n0 + lr) * 128, off, acc);
+      }
+      if (++qq < nchunks) continue;
+      epilogue(i, active);
       qq = 0;
       ++tt;
     }
-    cp_async_wait<0>();
-    __syncthreads();   // the ring is reused by the next matrix
+    gq += total;
+    __syncthreads();   // all warps have consumed the last chunk before the next matrix's prologue refills the ring
   }
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// {k (contiguous), row, tile-or-matrix} view of `count` row-major [rows][cols] matrices `stride` doubles apart
+int make_map(CUtensorMap* m, const double* base, long cols, long rows, long count, long stride) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled is not available from this driver"); return -2; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)count};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)stride * 8};
+  cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)NB, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return -2;
+  }
+  return 0;
+}
+
+struct MapSet {
+  const double *A, *D, *P;
+  int nP, Kt, batch;
+  CUtensorMap mA, mD, mP;
+};
+
+// tensor maps are pure functions of (pointers, layout): a tiny cache keyed by them (a plan reuses the same workspace)
+int get_maps(const BlockBatch& b, const MapSet** out) {
+  static std::mutex mu;
+  static std::vector<MapSet*> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (MapSet* ms : cache)
+    if (ms->A == b.A && ms->D == b.Dinv && ms->P == b.Pbuf && ms->nP == b.nP && ms->Kt == b.Kt && ms->batch >= b.batch) {
+      *out = ms;
+      return 0;
+    }
+  MapSet* ms = new MapSet();
+  ms->A = b.A; ms->D = b.Dinv; ms->P = b.Pbuf; ms->nP = b.nP; ms->Kt = b.Kt; ms->batch = b.batch;
+  int rc = make_map(&ms->mA, b.A, b.nP, b.nP, b.batch, b.strideA());
+  if (rc == 0) rc = make_map(&ms->mD, b.Dinv, NB, NB, (long)b.batch * b.Kt * 2, (long)NB * NB);
+  if (rc == 0) rc = make_map(&ms->mP, b.Pbuf, NB, NB, (long)b.batch * b.Kt, (long)NB * NB);
+  if (rc != 0) { delete ms; return rc; }
+  if (cache.size() >= 64) { delete cache.front(); cache.erase(cache.begin()); }
+  cache.push_back(ms);
+  *out = ms;
+  return 0;
 }
 
 // tiles of one matrix are split over gx CTAs; enough CTAs for ~8 waves of the 148 x 3 resident slots
 template <int MODE>
-int launch_ll(const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
+int launch_ll(const MapSet& ms, const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
   if (ntiles <= 0 || g0.batch <= 0) return 0;
   static bool configured = false;
   if (!configured) {
@@ -305,7 +372,7 @@ int launch_ll(const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, gy);
-  panel_gemm_kernel<MODE><<<grid, THREADS, LL_SMEM, st>>>(g);
+  panel_gemm_kernel<MODE><<<grid, THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -313,8 +380,8 @@ int launch_ll(const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
 
 LLArgs make_ll(const BlockBatch& b) {
   LLArgs g;
-  g.A = b.A; g.Dinv = b.Dinv; g.Pbuf = b.Pbuf;
-  g.strideA = b.strideA(); g.strideD = b.strideD(); g.strideP = b.strideD();
+  g.A = b.A; g.Pbuf = b.Pbuf;
+  g.strideA = b.strideA(); g.strideP = b.strideP();
   g.ld = b.nP; g.Kt = b.Kt; g.batch = b.batch; g.step = 0;
   g.n8 = (int)round_up(b.n, 8);
   g.ntiles = 0;
@@ -325,12 +392,15 @@ LLArgs make_ll(const BlockBatch& b) {
 
 int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
+  if (!b.Pbuf) { set_last_error("engine_potrf_ll: no panel buffer"); return -1; }
+  const MapSet* ms = nullptr;
+  NMGP_TRY(get_maps(b, &ms));
   LLArgs g = make_ll(b);
   for (int k = 0; k < b.Kt; ++k) {
     g.step = k;
-    if (k > 0) NMGP_TRY(launch_ll<LL_UPDATE>(g, b.Kt - k, st, launches));
+    if (k > 0) NMGP_TRY(launch_ll<LL_UPDATE>(*ms, g, b.Kt - k, st, launches));
     NMGP_TRY(engine_diag_step(b, k, st, launches));
-    NMGP_TRY(launch_ll<LL_SOLVE>(g, b.Kt - k - 1, st, launches));
+    NMGP_TRY(launch_ll<LL_SOLVE>(*ms, g, b.Kt - k - 1, st, launches));
   }
   return 0;
 }
@@ -338,12 +408,14 @@ int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
 int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
   if (!b.Pbuf) { set_last_error("engine_potri_ll: no panel buffer"); return -1; }
+  const MapSet* ms = nullptr;
+  NMGP_TRY(get_maps(b, &ms));
   LLArgs g = make_ll(b);
   for (int j = b.Kt - 1; j >= 0; --j) {
     g.step = j;
-    NMGP_TRY(launch_ll<TK_PANEL>(g, b.Kt - 1 - j, st, launches));
-    NMGP_TRY(launch_ll<TK_COL>(g, b.Kt - 1 - j, st, launches));
-    NMGP_TRY(launch_ll<TK_DIAG>(g, 1, st, launches));
+    NMGP_TRY(launch_ll<TK_PANEL>(*ms, g, b.Kt - 1 - j, st, launches));
+    NMGP_TRY(launch_ll<TK_COL>(*ms, g, b.Kt - 1 - j, st, launches));
+    NMGP_TRY(launch_ll<TK_DIAG>(*ms, g, 1, st, launches));
   }
   return 0;
 }

@@ -108,3 +108,27 @@ def test_separable_config2_against_dense_library_factorisation(cuda_device):
     ref = float(-torch.log(torch.diagonal(Lc)).sum() - 0.5 * (z * z).sum())
     assert abs(float(vals[0, 1]) - ref) / abs(ref) < 1e-10
     plan.close()
+
+
+@pytest.mark.parametrize("N,M,S", [(256, 8, 3), (512, 8, 2)])
+def test_batched_engine_is_stable_at_large_block_counts(N, M, S, cuda_device):
+    """n = 2048 / 4096 (32 / 64 block columns): the batched left-looking path must agree with the tile-task path.
+    (A Takahashi inverse sweep over that many block columns amplifies rounding errors geometrically -- 5e-7 at 32
+    columns, garbage at 64 -- so the plan switches the inverse to W^T W beyond 16 columns.)"""
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    subs = [_subject(N, M, 500 + s) for s in range(S)]
+    xs, Ys, ps = (np.stack(a) for a in zip(*subs))
+    res = {}
+    for mode in ("right", "left"):
+        plan = LogPosteriorPlan("nonseparable", xs, Ys, HYPER, prior=False)
+        plan.set_engine(mode)
+        v, g, i = plan.value_and_grad(torch.from_numpy(ps).cuda())
+        assert int(i.abs().sum()) == 0
+        res[mode] = (v.cpu().numpy(), g.cpu().numpy())
+        plan.close()
+    dv = np.abs(res["left"][0][:, 1] - res["right"][0][:, 1]) / np.abs(res["right"][0][:, 1])
+    dg = np.linalg.norm(res["left"][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
+    assert dv.max() < 1e-10, dv
+    assert dg.max() < 1e-8, dg
+    ref = _library_loglik(xs[0], ps[0], Ys[0], N, M)
+    assert abs(res["left"][0][0, 1] - ref) / abs(ref) < 1e-10
