@@ -93,7 +93,8 @@ int nmgp_logpost_grad_profile(nmgp_plan* plan, const double* pars_dev, double* v
                               int* info_dev, float* phase_ms, void* stream);
 
 /* Factorisation engine selection: 0 = automatic (left-looking accumulate-in-registers path for large batches,
- * right-looking tile tasks otherwise), 1 = force right-looking, 2 = force left-looking.  For tests and A/B timing. */
+ * right-looking tile tasks otherwise), 1 = force right-looking, 2 = force left-looking, 3 = left-looking with the
+ * W^T W inverse also where the Takahashi sweep would be used (<= 16 block columns).  For tests and A/B timing. */
 int nmgp_plan_set_engine(nmgp_plan* plan, int mode);
 
 /* Number of kernels the plan's last evaluation launched (bench.py's `gpu_launches`). */

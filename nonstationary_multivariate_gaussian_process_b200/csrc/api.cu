@@ -26,6 +26,7 @@ struct nmgp_plan {
   int nprior = 0; // GP-prior covariance matrices per subject (0 stationary, 2 otherwise)
   int nv1 = 1;    // right-hand sides for prior 1
   int engine_mode = 0;  // 0 auto, 1 force right-looking tile tasks, 2 force left-looking (tests / A-B timing)
+  int stable_inverse = 0;  // 1: W^T W inverse even where the Takahashi sweep would be allowed (engine mode 3)
   double hyper[NMGP_NHYPER] = {0};
   HyperConst hc{};
   std::vector<void*> allocs;
@@ -109,7 +110,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   const size_t N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat, nP = pl->nP, Kt = pl->Kt;
   const size_t MT = pl->model == NMGP_NONSEPARABLE ? padded_M(pl->M) : 0;
   size_t d = 0;
-  d += nm * nP * nP;            // A
+  d += 2 * nm * nP * nP;        // A, A2
   d += 3 * nm * Kt * kNB * kNB; // Dinv (W and W^T), Pbuf
   d += nm;                      // logdet
   d += 2 * N + 1;               // ell, sig, s2
@@ -129,6 +130,8 @@ int alloc_workspace(nmgp_plan* pl) {
   BlockBatch& b = pl->bb;
   b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
   NMGP_TRY(dev_alloc(pl, &b.A, cs * nm * (size_t)pl->nP * pl->nP));
+  NMGP_TRY(dev_alloc(pl, &b.A2, cs * nm * (size_t)pl->nP * pl->nP));
+  NMGP_CUDA_TRY(cudaMemsetAsync(b.A2, 0, cs * nm * (size_t)pl->nP * pl->nP * sizeof(double), 0));
   NMGP_TRY(dev_alloc(pl, &b.Dinv, cs * nm * (size_t)pl->Kt * 2 * kNB * kNB));
   NMGP_TRY(dev_alloc(pl, &b.Pbuf, cs * nm * (size_t)pl->Kt * kNB * kNB));
   // the left-looking engine multiplies padding / not-yet-written upper tiles by exact zeros: they must be finite
@@ -467,7 +470,8 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     // of block columns (measured: exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64).  It is therefore used only up to
     // kTakahashiMaxBlocks block columns; beyond, the inverse is formed as W^T W from the triangular inverse (backward
     // stable) by the tile-task engine, on the factor the left-looking potrf produced (same layout).
-    if (ll && b.Kt <= kTakahashiMaxBlocks) NMGP_TRY(engine_potri_ll(b, st, &launches));
+    if (ll && b.Kt <= kTakahashiMaxBlocks && !pl->stable_inverse) NMGP_TRY(engine_potri_ll(b, st, &launches));
+    else if (ll) NMGP_TRY(engine_potri_ll_stable(b, st, &launches));
     else NMGP_TRY(engine_potri(b, st, &launches));
     NMGP_MARK(3);
     if (overlap) NMGP_CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
@@ -563,8 +567,9 @@ int nmgp_adam_step(double* pars, const double* grad, double* m, double* v, const
 }
 
 int nmgp_plan_set_engine(nmgp_plan* pl, int mode) {
-  if (!pl || mode < 0 || mode > 2) return NMGP_EINVAL;
-  pl->engine_mode = mode;
+  if (!pl || mode < 0 || mode > 3) return NMGP_EINVAL;
+  pl->engine_mode = mode == 3 ? 2 : mode;
+  pl->stable_inverse = mode == 3;
   return 0;
 }
 

@@ -13,6 +13,7 @@ namespace nmgp {
 //          engine is K-MAJOR (row = output index, column = summation index): one TMA box shape, one swizzle.
 struct BlockBatch {
   double* A = nullptr;
+  double* A2 = nullptr;      // [batch][nP][nP]  second matrix buffer of the stable left-looking inverse (W^T tiles)
   double* Dinv = nullptr;
   double* Pbuf = nullptr;    // [batch][Kt][NB*NB]  panel side buffer of the left-looking inverse: P(c)^T tiles (zero-initialised once)
   long strideP() const { return (long)Kt * NB * NB; }
@@ -48,6 +49,9 @@ int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches
 // (the plan zero-fills the workspace once).
 int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches);
 int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches);
+// Same result as engine_potri_ll by W = L^-1 (row-wise, all rows in parallel) and Z = W^T W (all tiles in parallel): three
+// launches, no recursion over block columns, stable for any size.  Requires b.A2 (finite-initialised).
+int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches);
 // largest number of 64-blocks per side for which the Takahashi recursion of engine_potri_ll is used (see api.cu)
 constexpr int kTakahashiMaxBlocks = 16;
 

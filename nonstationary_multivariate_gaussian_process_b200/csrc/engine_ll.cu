@@ -57,6 +57,7 @@ enum LLMode : int { LL_UPDATE = 0, LL_SOLVE = 1, TK_PANEL = 2, TK_COL = 3, TK_DI
 
 struct LLArgs {
   double* A;
+  double* A2;
   double* Pbuf;
   long strideA, strideP;
   int ld, Kt, batch, step, n8, ntiles;
@@ -295,6 +296,188 @@ __global__ void __launch_bounds__(THREADS, 4) panel_gemm_kernel(const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ stable inverse
+// Z = W^T W with W = L^-1, in three launches over ALL block columns at once (no sweep, no error recursion: the Takahashi
+// sweep above amplifies rounding errors geometrically in the number of block columns and is only used for Kt <= 16):
+//   PANEL_ALL  Lh(c,j) = L(c,j) W_jj for every c > j            -> transposed into the upper tile (j,c) of A
+//   TRTRI_ROW  row i of W:  W(i,j) = -sum_{c=j+1..i} W(i,c) Lh(c,j),  j = i-1 .. 0  (W(i,i) = W_ii from the diagonal step)
+//              one CTA per row, its tiles in sequence; W(i,j) -> lower tile (i,j) of A (operand of the row's later
+//              tiles) and transposed -> upper tile (j,i) of A2 (operand of LAUUM)
+//   LAUUM      Z(i,j) = sum_{c>=i} W(c,i)^T W(c,j), i >= j      -> A, both triangles
+// Same ring, same K-major operands, same fragment addressing as panel_gemm_kernel; the tiles of a CTA now have different
+// K lengths, so producer and consumer each walk the (tile, chunk) sequence.
+enum InvMode : int { PANEL_ALL = 0, TRTRI_ROW = 1, LAUUM = 2 };
+
+struct Tile {
+  int i, j, nch;
+};
+
+__device__ __forceinline__ void tri_decode(int t, int& a, int& b) {
+  // t = a(a+1)/2 + b, 0 <= b <= a
+  a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long)a * (a + 1) / 2 > t) --a;
+  while ((long)(a + 1) * (a + 2) / 2 <= t) ++a;
+  b = t - a * (a + 1) / 2;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                             const __grid_constant__ CUtensorMap mapA2,
+                                                             const __grid_constant__ CUtensorMap mapD, LLArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
+
+  const int Kt = g.Kt, last = g.Kt - 1;
+  const int vlast = g.n8 - last * NB;
+  const int ragged_chunks = (vlast + KC - 1) / KC;
+  const int warp = ((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & 3, lane = threadIdx.x & 31;
+  const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
+  const int r = lane >> 2, c = 2 * (lane & 3);
+  const int lr = lane >> 2, lk = lane & 3;
+  int off[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) off[ks] = (((ks + 4 * (lk >> 1)) ^ lr) << 4) + (lk & 1) * 8;
+  constexpr int HALF = (NB / 2) / KC;
+
+  // tiles of this CTA
+  int nmy;
+  if (MODE == TRTRI_ROW) nmy = Kt - 1 - (int)blockIdx.x;        // CTA bx owns row i = Kt-1-bx (longest rows first)
+  else nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto tile_at = [&](int tt) -> Tile {
+    Tile t;
+    if (MODE == PANEL_ALL) {          // strictly lower pairs (c, j)
+      int a, b;
+      tri_decode(blockIdx.x + tt * gridDim.x, a, b);
+      t.i = a + 1; t.j = b; t.nch = CPB;
+    } else if (MODE == TRTRI_ROW) {   // row i, columns descending
+      t.i = Kt - 1 - (int)blockIdx.x; t.j = t.i - 1 - tt; t.nch = (t.i - t.j) * CPB;
+    } else {                          // lower pairs incl. diagonal; k-blocks c = i .. last, the last one ragged
+      tri_decode(blockIdx.x + tt * gridDim.x, t.i, t.j);
+      t.nch = (last - t.i) * CPB + ragged_chunks;
+    }
+    return t;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int gq = 0;
+
+  for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
+    double* Am = g.A + (long)mat * g.strideA;
+    double* A2m = g.A2 + (long)mat * g.strideA;
+    const int dbase = mat * Kt * 2;
+
+    // ---- producer (thread 0): walks the same (tile, chunk) sequence STAGES-1 chunks ahead of the consumers
+    int p_tt = 0, p_qq = 0;
+    Tile p_tile = tile_at(0);
+    auto produce = [&](int slot) {
+      const Tile t = p_tile;
+      const int kb = p_qq / CPB, kcol = (p_qq % CPB) * KC;
+      if (++p_qq == t.nch) { p_qq = 0; if (++p_tt < nmy) p_tile = tile_at(p_tt); }
+      unsigned char* SA = ring + slot * 2 * OPB;
+      unsigned char* SB = SA + OPB;
+      unsigned long long* bar = &full[slot];
+      mbar_expect_tx(bar, 2 * OPB);
+      if (MODE == PANEL_ALL) {           // L(i,j) . W_jj              (B[n][k] = W_jj^T[n][k])
+        tma_load_chunk(SA, &mapA, t.j * NB + kcol, t.i * NB, mat, bar);
+        tma_load_chunk(SB, &mapD, kcol, 0, dbase + 2 * t.j + 1, bar);
+      } else if (MODE == TRTRI_ROW) {    // W(i,cb) . Lh(cb,j),  cb = i, i-1, .., j+1   (B = upper tile (j,cb) of A)
+        const int cb = t.i - kb;
+        if (cb == t.i) tma_load_chunk(SA, &mapD, kcol, 0, dbase + 2 * t.i, bar);
+        else tma_load_chunk(SA, &mapA, cb * NB + kcol, t.i * NB, mat, bar);
+        tma_load_chunk(SB, &mapA, cb * NB + kcol, t.j * NB, mat, bar);
+      } else {                           // W(cb,i)^T . W(cb,j),  cb = i .. last       (upper tiles (i,cb), (j,cb) of A2)
+        const int cb = t.i + kb;
+        if (cb == t.i) tma_load_chunk(SA, &mapD, kcol, 0, dbase + 2 * t.i + 1, bar);
+        else tma_load_chunk(SA, &mapA2, cb * NB + kcol, t.i * NB, mat, bar);
+        if (cb == t.j) tma_load_chunk(SB, &mapD, kcol, 0, dbase + 2 * t.j + 1, bar);
+        else tma_load_chunk(SB, &mapA2, cb * NB + kcol, t.j * NB, mat, bar);
+      }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    if (threadIdx.x == 0 && nmy > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll 1
+      for (int q = 0; q < STAGES - 1 && p_tt < nmy; ++q) produce((gq + q) % STAGES);
+    }
+
+    for (int tt = 0; tt < nmy; ++tt) {
+      const Tile t = tile_at(tt);
+      const int rows_valid = (t.i == last) ? vlast : NB;
+      const int cols_valid = (t.j == last) ? vlast : NB;
+      const bool diag_tile = (MODE == LAUUM) && t.i == t.j;
+      const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !(diag_tile && m0 == 0 && n0 == NB / 2);
+      for (int qq = 0; qq < t.nch; ++qq, ++gq) {
+        const int slot = gq % STAGES;
+        __syncthreads();                 // every warp is done with the previous chunk: its slot may be refilled
+        if (threadIdx.x == 0 && p_tt < nmy) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          produce((gq + STAGES - 1) % STAGES);
+        }
+        // chunks of the first k-block that only meet structural zeros of the triangular diagonal inverse
+        bool zero = false;
+        if (qq < CPB) {
+          if (MODE == PANEL_ALL) zero = (n0 == NB / 2 && qq < HALF);                 // W_jj[k][n] = 0 for n > k
+          else if (MODE == TRTRI_ROW) zero = (m0 == 0 && qq >= HALF);                // W_ii[m][k] = 0 for k > m
+          else zero = (m0 == NB / 2 && qq < HALF) || (diag_tile && n0 == NB / 2 && qq < HALF);   // W_ii[k][m] = 0 for m > k
+        }
+        mbar_wait(&full[slot], (gq / STAGES) & 1);
+        if (active && !zero) {
+          const unsigned char* SA = ring + slot * 2 * OPB;
+          mma_chunk(SA + (m0 + lr) * 128, SA + OPB + (n0 + lr) * 128, off, acc);
+        }
+      }
+      // ---- epilogue
+      if (active) {
+        double* C = Am + ((long)t.i * NB) * g.ld + (long)t.j * NB;        // lower tile (i,j) of A
+        double* U = Am + ((long)t.j * NB) * g.ld + (long)t.i * NB;        // upper tile (j,i) of A
+        double* U2 = A2m + ((long)t.j * NB) * g.ld + (long)t.i * NB;      // upper tile (j,i) of A2
+        const bool mirror = !diag_tile || (m0 == NB / 2 && n0 == 0);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
+            if (MODE == PANEL_ALL) {          // Lh(i,j)^T -> upper tile (j,i) of A
+              U[(long)col * g.ld + row] = acc[a][b][0];
+              U[(long)(col + 1) * g.ld + row] = acc[a][b][1];
+            } else if (MODE == TRTRI_ROW) {   // W(i,j) -> lower tile of A, W(i,j)^T -> upper tile of A2
+              double2 v; v.x = -acc[a][b][0]; v.y = -acc[a][b][1];
+              *reinterpret_cast<double2*>(C + (long)row * g.ld + col) = v;
+              U2[(long)col * g.ld + row] = v.x;
+              U2[(long)(col + 1) * g.ld + row] = v.y;
+            } else {                          // Z(i,j) and its mirror -> A
+              double2 v; v.x = acc[a][b][0]; v.y = acc[a][b][1];
+              *reinterpret_cast<double2*>(C + (long)row * g.ld + col) = v;
+              if (mirror) {
+                U[(long)col * g.ld + row] = v.x;
+                U[(long)(col + 1) * g.ld + row] = v.y;
+              }
+            }
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      // the next tiles of this row read W(i,j) back through TMA: order this thread's global writes before later
+      // async-proxy reads (the barrier at the top of the next chunk orders the CTA's threads among themselves)
+      if (MODE == TRTRI_ROW) asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();   // all warps have consumed the last chunk before the next matrix's prologue refills the ring
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -329,9 +512,9 @@ int make_map(CUtensorMap* m, const double* base, long cols, long rows, long coun
 }
 
 struct MapSet {
-  const double *A, *D, *P;
+  const double *A, *A2, *D, *P;
   int nP, Kt, batch;
-  CUtensorMap mA, mD, mP;
+  CUtensorMap mA, mA2, mD, mP;
 };
 
 // tensor maps are pure functions of (pointers, layout): a tiny cache keyed by them (a plan reuses the same workspace)
@@ -340,13 +523,15 @@ int get_maps(const BlockBatch& b, const MapSet** out) {
   static std::vector<MapSet*> cache;
   std::lock_guard<std::mutex> lock(mu);
   for (MapSet* ms : cache)
-    if (ms->A == b.A && ms->D == b.Dinv && ms->P == b.Pbuf && ms->nP == b.nP && ms->Kt == b.Kt && ms->batch >= b.batch) {
+    if (ms->A == b.A && ms->A2 == b.A2 && ms->D == b.Dinv && ms->P == b.Pbuf && ms->nP == b.nP && ms->Kt == b.Kt &&
+        ms->batch >= b.batch) {
       *out = ms;
       return 0;
     }
   MapSet* ms = new MapSet();
-  ms->A = b.A; ms->D = b.Dinv; ms->P = b.Pbuf; ms->nP = b.nP; ms->Kt = b.Kt; ms->batch = b.batch;
+  ms->A = b.A; ms->A2 = b.A2; ms->D = b.Dinv; ms->P = b.Pbuf; ms->nP = b.nP; ms->Kt = b.Kt; ms->batch = b.batch;
   int rc = make_map(&ms->mA, b.A, b.nP, b.nP, b.batch, b.strideA());
+  if (rc == 0) rc = make_map(&ms->mA2, b.A2 ? b.A2 : b.A, b.nP, b.nP, b.batch, b.strideA());
   if (rc == 0) rc = make_map(&ms->mD, b.Dinv, NB, NB, (long)b.batch * b.Kt * 2, (long)NB * NB);
   if (rc == 0) rc = make_map(&ms->mP, b.Pbuf, NB, NB, (long)b.batch * b.Kt, (long)NB * NB);
   if (rc != 0) { delete ms; return rc; }
@@ -380,7 +565,7 @@ int launch_ll(const MapSet& ms, const LLArgs& g0, int ntiles, cudaStream_t st, l
 
 LLArgs make_ll(const BlockBatch& b) {
   LLArgs g;
-  g.A = b.A; g.Pbuf = b.Pbuf;
+  g.A = b.A; g.A2 = b.A2; g.Pbuf = b.Pbuf;
   g.strideA = b.strideA(); g.strideP = b.strideP();
   g.ld = b.nP; g.Kt = b.Kt; g.batch = b.batch; g.step = 0;
   g.n8 = (int)round_up(b.n, 8);
@@ -402,6 +587,49 @@ int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
     NMGP_TRY(engine_diag_step(b, k, st, launches));
     NMGP_TRY(launch_ll<LL_SOLVE>(*ms, g, b.Kt - k - 1, st, launches));
   }
+  return 0;
+}
+
+namespace {
+template <int MODE>
+int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launches) {
+  if (g0.batch <= 0) return 0;
+  LLArgs g = g0;
+  const int Kt = g.Kt;
+  const int ntiles = MODE == PANEL_ALL ? Kt * (Kt - 1) / 2 : (MODE == TRTRI_ROW ? Kt - 1 : Kt * (Kt + 1) / 2);
+  if (ntiles <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    NMGP_CUDA_TRY(cudaFuncSetAttribute(inverse_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+    configured = true;
+  }
+  g.ntiles = ntiles;
+  const int gy = g.batch < 65535 ? g.batch : 65535;
+  int gx;
+  if (MODE == TRTRI_ROW) gx = Kt - 1;          // one CTA per row (its tiles depend on each other)
+  else {
+    gx = (148 * 4 * 8 + gy - 1) / gy;          // ~8 waves of the 148 x 4 resident slots
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+  }
+  dim3 grid(gx, gy);
+  inverse_kernel<MODE><<<grid, THREADS, LL_SMEM, st>>>(ms.mA, ms.mA2, ms.mD, g);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+}  // namespace
+
+// A <- inverse (both triangles) from the factor and the diagonal inverses left by engine_potrf_ll; stable for any size.
+int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (b.batch <= 0) return 0;
+  if (!b.A2) { set_last_error("engine_potri_ll_stable: no second matrix buffer"); return -1; }
+  const MapSet* ms = nullptr;
+  NMGP_TRY(get_maps(b, &ms));
+  LLArgs g = make_ll(b);
+  NMGP_TRY(launch_inv<PANEL_ALL>(*ms, g, st, launches));
+  NMGP_TRY(launch_inv<TRTRI_ROW>(*ms, g, st, launches));
+  NMGP_TRY(launch_inv<LAUUM>(*ms, g, st, launches));
   return 0;
 }
 

@@ -30,9 +30,10 @@ def run_plan(g, engine="auto"):
     return vals.numpy()[0], grad.numpy()[0], int(info[0])
 
 
-# "auto" picks the right-looking tile engine for a single subject; "left" forces the batched left-looking / Takahashi
-# engine (with the covariance generated inside the factorisation) that the 10 000-subject sweep uses.
-@pytest.mark.parametrize("engine", ["auto", "left"])
+# "auto" picks the right-looking tile engine for a single subject; "left" forces the batched left-looking potrf with the
+# Takahashi inverse sweep (<= 16 block columns) that the 10 000-subject sweep uses; "left_stable" the left-looking potrf
+# with the W^T W inverse (PANEL_ALL / TRTRI_ROW / LAUUM) that larger matrices get.
+@pytest.mark.parametrize("engine", ["auto", "left", "left_stable"])
 @pytest.mark.parametrize("name", golden_cases())
 def test_cuda_matches_reference_golden(name, engine, cuda_device):
     g = load_golden(name)

@@ -1,5 +1,5 @@
 """Run one configuration through the plan API and print per-phase timings (GPU box).
-usage: python tools/run_config.py MODEL N M S [reps] [auto|left|right]"""
+usage: python tools/run_config.py MODEL N M S [reps] [auto|left|right|left_stable]"""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
