@@ -287,17 +287,17 @@ def ours(a):
     f_potrf, f_potri = algorithmic_flops(a.model, a.N, a.M)
     t_fact = (phases["potrf"] + phases["potri"]) * 1e-3
     achieved = S * (f_potrf + f_potri) / t_fact / 1e12 if t_fact > 0 else 0.0
-    # DRAM traffic of the same kernels from the committed ncu pass (profiles/r01_launches_w.txt): 341 GB per sweep of
+    # DRAM traffic of the same kernels from the committed ncu pass (profiles/r01_launches_final.txt): 353 GB per sweep of
     # 10 000 subjects over 168 engine launches (3 chunks x 56) -> bytes per launch, scaled to this rank's subjects
-    traffic = 341e9 / 168.0 * (S / 10000.0) if (a.model == "nonseparable" and a.N == 100 and a.M == 6) else None
+    traffic = 353e9 / 168.0 * (S / 10000.0) if (a.model == "nonseparable" and a.N == 100 and a.M == 6) else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
                 "traffic_note": "average dram__bytes_read+write per launch over the 168 panel_gemm/diag64 launches of one "
-                                "sweep (ncu, profiles/r01_launches_w.txt); algorithmic minimum (every tile read once "
+                                "sweep (ncu, profiles/r01_launches_final.txt); algorithmic minimum (every tile read once "
                                 "per use from L2-missing operands) is ~250 GB per sweep",
-                "kernel": "panel_gemm_kernel<mode> (left-looking potrf + Takahashi inverse, 64x64 DMMA.8x8x4 tiles "
-                          "through a cp.async ring) + diag64_kernel; achieved = S*n^3 flop / (t_potrf + t_potri), "
-                          "phase times from CUDA events inside nmgp_logpost_grad_profile",
+                "kernel": "panel_gemm_kernel<mode> (left-looking potrf + Takahashi inverse: 64x64 DMMA.8x8x4 tiles fed by "
+                          "TMA, cp.async.bulk.tensor + 128B swizzle + mbarrier ring) + diag64_kernel; achieved = S*n^3 flop / "
+                          "(t_potrf + t_potri), phase times from CUDA events inside nmgp_logpost_grad_profile",
                 "peak_source": "FP64 DMMA peak measured on this pool's B200 (tools/fp64_peak.cu, "
                                "profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
                 "algorithmic_flops_per_eval": f_potrf + f_potri,
