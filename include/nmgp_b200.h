@@ -116,6 +116,31 @@ int nmgp_adam_step(double* pars_dev, const double* grad_dev, double* m_dev, doub
                    const unsigned char* frozen_dev, long S, long P, double lr, double beta1, double beta2, double eps,
                    long step, void* stream);
 
+/* ---------------------------------------------------------------- posterior prediction (nonseparable model) ----
+ * Stand-ins for the device work inside `point_/pointwise_/test_predmap_inhomogeneous_sampling`
+ * (Utility/prediction.py:1038-1262; callers Nonseparable_Model/Nonseparable_model.py:377,387,399).  The reference draws,
+ * per new input x* and per sample: tilde_l* ~ N(mu_l, sigma2_l), uL* ~ N(mu_uL, sigma2_uL) (the GP priors conditioned on the
+ * MAP values), then y ~ N(mu_f, sigma2_y) given (tilde_l*, uL*).  The draws themselves stay on the host (torch's generator,
+ * so the reference's random stream is reproduced, see prediction.py of this package); the two calls below produce every
+ * quantity the draws need.  All pointers are device pointers; S subjects of the plan, G new inputs per subject.
+ *
+ * nmgp_predict_prior_moments  (prediction.py:1060-1092): xstar [S,G] ->
+ *     mu_l [S,G], s2_l [S,G]   conditional mean / variance of tilde_l at x*   (variance < 0 -> 1e-6, prediction.py:1066)
+ *     mu_uL [S,G,T], s2_uL [S,G]   same for the T columns of uL (one shared variance, prediction.py:1079-1081)
+ *   computed with the plan's cached Cholesky factors of the prior covariances (the reference LU-solves per call).
+ *
+ * nmgp_predict_moments  (prediction.py:1130-1165): tl_star [S,G,n_sample], uL_star [S,G,n_sample,T] (unconstrained) ->
+ *     mu_f [S,G,n_sample,M]   k_f^T Sigma^-1 y
+ *     s2_y [S,G,n_sample,M]   diag(A - k_f^T Sigma^-1 k_f) + sigma2_err   (values <= 0 -> 1e-6, prediction.py:1163)
+ *     info [S] (may be NULL)  as in nmgp_logpost_grad
+ *   Sigma is built, factored and inverted ONCE per subject by the hot-path engine (the reference repeats an n x n
+ *   `symeig` + `cholesky` per x* and per sample); see csrc/predict.cu for the sample-dependent part. */
+int nmgp_predict_prior_moments(nmgp_plan* plan, const double* pars_dev, const double* xstar_dev, int G, double* mu_l_dev,
+                               double* s2_l_dev, double* mu_uL_dev, double* s2_uL_dev, void* stream);
+int nmgp_predict_moments(nmgp_plan* plan, const double* pars_dev, const double* xstar_dev, int G, int n_sample,
+                         const double* tl_star_dev, const double* uL_star_dev, double* mu_f_dev, double* s2_y_dev,
+                         int* info_dev, void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 const char* nmgp_last_error(void);
 

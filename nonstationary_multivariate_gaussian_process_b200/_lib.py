@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
-SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "api.cu"]
+SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "api.cu"]
 HEADERS = ["common.cuh", "engine.cuh", "models.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -102,6 +102,10 @@ def _declare(lib):
     lib.nmgp_adam_step.restype = c.c_int
     lib.nmgp_adam_step.argtypes = [dp, dp, dp, dp, ip, dp, c.c_long, c.c_long, c.c_double, c.c_double, c.c_double,
                                    c.c_double, c.c_long, vp]
+    lib.nmgp_predict_prior_moments.restype = c.c_int
+    lib.nmgp_predict_prior_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, dp, dp, dp, dp, vp]
+    lib.nmgp_predict_moments.restype = c.c_int
+    lib.nmgp_predict_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, c.c_int, dp, dp, dp, dp, ip, vp]
     lib.nmgp_rbf_cov.restype = c.c_int
     lib.nmgp_rbf_cov.argtypes = [dp, c.c_int, dp, c.c_int, c.c_double, c.c_double, dp, vp]
     lib.nmgp_gibbs_cov.restype = c.c_int
@@ -117,7 +121,7 @@ def _declare(lib):
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
-           "nmgp_plan_block", "nmgp_adam_step", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
+           "nmgp_plan_block", "nmgp_adam_step", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 
 

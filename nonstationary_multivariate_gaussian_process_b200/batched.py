@@ -211,6 +211,60 @@ class LogPosteriorPlan:
                 _lib.check(rc, "nmgp_adam_step")
         return p, (torch.stack(trace) if trace else torch.empty((0, self.S, _lib.NVALS), device=self.device)), info
 
+    # ------------------------------------------------------------------ posterior prediction (nonseparable model)
+    def _xstar(self, xstar):
+        torch = _lib.require_cuda()
+        xs = torch.as_tensor(xstar, dtype=torch.float64).to(self.device)
+        if xs.dim() == 1:
+            xs = xs.unsqueeze(0).expand(self.S, -1)
+        if xs.dim() != 2 or xs.shape[0] != self.S:
+            raise ValueError(f"expected new inputs [G] or [S,G]; got {tuple(xs.shape)}")
+        return xs.contiguous()
+
+    def predict_prior_moments(self, pars, xstar):
+        """Conditional moments of the two GP priors at new inputs (Utility/prediction.py:1060-1092).
+        pars [S,P], xstar [G] or [S,G] -> (mu_l [S,G], s2_l [S,G], mu_uL [S,G,T], s2_uL [S,G]), CUDA tensors."""
+        torch = _lib.require_cuda()
+        if self.model != "nonseparable":
+            raise ValueError("prediction is implemented for the nonseparable model")
+        p = torch.as_tensor(pars, dtype=torch.float64).detach().to(self.device).reshape(self.S, self.P).contiguous()
+        xs = self._xstar(xstar)
+        G, T = int(xs.shape[1]), self.M * (self.M + 1) // 2
+        kw = dict(dtype=torch.float64, device=self.device)
+        mu_l, s2_l = torch.empty((self.S, G), **kw), torch.empty((self.S, G), **kw)
+        mu_u, s2_u = torch.empty((self.S, G, T), **kw), torch.empty((self.S, G), **kw)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_predict_prior_moments(self._handle, p.data_ptr(), xs.data_ptr(), G, mu_l.data_ptr(),
+                                                     s2_l.data_ptr(), mu_u.data_ptr(), s2_u.data_ptr(),
+                                                     ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_predict_prior_moments")
+        return mu_l, s2_l, mu_u, s2_u
+
+    def predict_moments(self, pars, xstar, tl_star, uL_star):
+        """Predictive mean and variance of the M outputs for sampled (tilde_l*, uL*) (Utility/prediction.py:1130-1165).
+        pars [S,P], xstar [G] or [S,G], tl_star [S,G,ns], uL_star [S,G,ns,T] ->
+        (mu_f [S,G,ns,M], s2_y [S,G,ns,M], info [S]), CUDA tensors."""
+        torch = _lib.require_cuda()
+        if self.model != "nonseparable":
+            raise ValueError("prediction is implemented for the nonseparable model")
+        p = torch.as_tensor(pars, dtype=torch.float64).detach().to(self.device).reshape(self.S, self.P).contiguous()
+        xs = self._xstar(xstar)
+        G, T = int(xs.shape[1]), self.M * (self.M + 1) // 2
+        tl = torch.as_tensor(tl_star, dtype=torch.float64).to(self.device).reshape(self.S, G, -1).contiguous()
+        ns = int(tl.shape[2])
+        ul = torch.as_tensor(uL_star, dtype=torch.float64).to(self.device).reshape(self.S, G, ns, T).contiguous()
+        kw = dict(dtype=torch.float64, device=self.device)
+        mu_f, s2_y = torch.empty((self.S, G, ns, self.M), **kw), torch.empty((self.S, G, ns, self.M), **kw)
+        info = torch.zeros((self.S,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_predict_moments(self._handle, p.data_ptr(), xs.data_ptr(), G, ns, tl.data_ptr(),
+                                               ul.data_ptr(), mu_f.data_ptr(), s2_y.data_ptr(), info.data_ptr(),
+                                               ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_predict_moments")
+        return mu_f, s2_y, info
+
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:
             self.lib.nmgp_plan_destroy(self._handle)

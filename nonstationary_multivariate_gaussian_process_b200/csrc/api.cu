@@ -42,6 +42,9 @@ struct nmgp_plan {
   // staging for the host-buffer call
   double *pars_d = nullptr, *vals_d = nullptr, *grad_d = nullptr;
   int* info_d = nullptr;
+  // lazily allocated scratch of the prediction entry points (not part of `allocs`)
+  double* pred_scratch = nullptr;
+  size_t pred_scratch_doubles = 0;
   // side stream: the GP-prior triangular solves are independent of the factorisation and run beside it
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -292,6 +295,7 @@ int nmgp_n_params(int model, int N, int M) {
 int nmgp_plan_destroy(nmgp_plan* pl) {
   if (!pl) return 0;
   for (void* p : pl->allocs) cudaFree(p);
+  if (pl->pred_scratch) cudaFree(pl->pred_scratch);
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_join) cudaEventDestroy(pl->ev_join);
   if (pl->side) cudaStreamDestroy(pl->side);
@@ -410,6 +414,25 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
   return 0;
 }
 
+// Engine selection shared by the evaluation and the prediction path.
+static bool use_left_looking(const nmgp_plan* pl, const BlockBatch& b) {
+  return b.Pbuf != nullptr && (pl->engine_mode == 2 || (pl->engine_mode == 0 && prefer_left_looking(b)));
+}
+static int run_potrf(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* launches) {
+  return use_left_looking(pl, b) ? engine_potrf_ll(b, st, launches) : engine_potrf(b, st, launches);
+}
+// The Takahashi sweep propagates the error of the trailing inverse block into every new block column, multiplied by
+// |L(B,j) L_jj^-1| -- for smooth GP covariances that factor exceeds 1 and the error grows geometrically with the number
+// of block columns (measured: exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64).  It is therefore used only up to
+// kTakahashiMaxBlocks block columns; beyond, the inverse is formed as W^T W from the triangular inverse (backward
+// stable) on the factor the left-looking potrf produced (same layout).
+static int run_potri(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* launches) {
+  const bool ll = use_left_looking(pl, b);
+  if (ll && b.Kt <= kTakahashiMaxBlocks && !pl->stable_inverse) return engine_potri_ll(b, st, launches);
+  if (ll) return engine_potri_ll_stable(b, st, launches);
+  return engine_potri(b, st, launches);
+}
+
 static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st,
                     float* phase_ms, const ChunkSync* sync = nullptr) {
   long launches = 0;
@@ -462,17 +485,9 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
       NMGP_TRY(prior_solves());
       NMGP_CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
     }
-    const bool ll = b.Pbuf != nullptr && (pl->engine_mode == 2 || (pl->engine_mode == 0 && prefer_left_looking(b)));
-    if (ll) NMGP_TRY(engine_potrf_ll(b, st, &launches)); else NMGP_TRY(engine_potrf(b, st, &launches));
+    NMGP_TRY(run_potrf(pl, b, st, &launches));
     NMGP_MARK(2);
-    // The Takahashi sweep propagates the error of the trailing inverse block into every new block column, multiplied by
-    // |L(B,j) L_jj^-1| -- for smooth GP covariances that factor exceeds 1 and the error grows geometrically with the number
-    // of block columns (measured: exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64).  It is therefore used only up to
-    // kTakahashiMaxBlocks block columns; beyond, the inverse is formed as W^T W from the triangular inverse (backward
-    // stable) by the tile-task engine, on the factor the left-looking potrf produced (same layout).
-    if (ll && b.Kt <= kTakahashiMaxBlocks && !pl->stable_inverse) NMGP_TRY(engine_potri_ll(b, st, &launches));
-    else if (ll) NMGP_TRY(engine_potri_ll_stable(b, st, &launches));
-    else NMGP_TRY(engine_potri(b, st, &launches));
+    NMGP_TRY(run_potri(pl, b, st, &launches));
     NMGP_MARK(3);
     if (overlap) NMGP_CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
     else NMGP_TRY(prior_solves());
@@ -563,6 +578,89 @@ int nmgp_adam_step(double* pars, const double* grad, double* m, double* v, const
   adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pars, grad, m, v, info, frozen, S, P, beta1, beta2, eps,
                                                              lr / bc1, std::sqrt(bc2));
   NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_pred_scratch(nmgp_plan* pl, size_t per_subject, int cs) {
+  const size_t cap = (2ull << 30) / sizeof(double);
+  size_t want = per_subject * (size_t)cs;
+  if (want > cap) want = cap > per_subject ? cap : per_subject;
+  if (pl->pred_scratch_doubles >= want) return 0;
+  if (pl->pred_scratch) { cudaFree(pl->pred_scratch); pl->pred_scratch = nullptr; pl->pred_scratch_doubles = 0; }
+  if (cudaMalloc(&pl->pred_scratch, want * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("prediction scratch: cudaMalloc of " + std::to_string(want * sizeof(double)) + " bytes failed");
+    return NMGP_ENOMEM;
+  }
+  pl->pred_scratch_doubles = want;
+  return 0;
+}
+
+int nmgp_predict_prior_moments(nmgp_plan* pl, const double* pars, const double* xstar, int G, double* mu_l, double* s2_l,
+                               double* mu_uL, double* s2_uL, void* stream) {
+  if (!pl || pl->model != NMGP_NONSEPARABLE || G < 0 || (pl->S > 0 && G > 0 && (!pars || !xstar || !mu_l || !s2_l || !mu_uL || !s2_uL))) {
+    set_last_error("nmgp_predict_prior_moments: needs a nonseparable plan and non-null buffers");
+    return NMGP_EINVAL;
+  }
+  if (pl->S == 0 || G == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl->N, M = pl->M, P = pl->P, T = pl->T;
+  long launches = 0;
+  const size_t per = predict_prior_scratch_per_subject(N, G);
+  NMGP_TRY(ensure_pred_scratch(pl, per, pl->chunk));
+  const long SB = (long)(pl->pred_scratch_doubles / per);
+  for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
+    const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
+    NMGP_TRY(launch_svc_prep(cs, N, M, pars + (size_t)s0 * P, P, pl->hc, pl->w, st, &launches));
+    const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
+    const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
+    NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
+    NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, T, 0, st, &launches));
+    for (int c0 = 0; c0 < cs; c0 += (int)SB) {
+      const int sb = cs - c0 < SB ? cs - c0 : (int)SB;
+      const size_t g0 = (size_t)(s0 + c0);
+      const double* xs = pl->x + g0 * N;
+      const double* xq = xstar + g0 * G;
+      NMGP_TRY(launch_predict_prior(xs, L0 + (size_t)c0 * N * N, pl->w.Z0 + (size_t)c0 * N, sb, N, 1, xq, G, pl->hyper[1],
+                                    pl->hyper[2], pl->hyper[0], pl->pred_scratch, mu_l + g0 * G, s2_l + g0 * G, st, &launches));
+      NMGP_TRY(launch_predict_prior(xs, L1 + (size_t)c0 * N * N, pl->w.Z1 + (size_t)c0 * N * T, sb, N, T, xq, G, pl->hyper[4],
+                                    pl->hyper[5], pl->hyper[3], pl->pred_scratch, mu_uL + g0 * G * T, s2_uL + g0 * G, st,
+                                    &launches));
+    }
+  }
+  pl->last_launches = launches;
+  return 0;
+}
+
+int nmgp_predict_moments(nmgp_plan* pl, const double* pars, const double* xstar, int G, int n_sample, const double* tl_star,
+                         const double* uL_star, double* mu_f, double* s2_y, int* info, void* stream) {
+  if (!pl || pl->model != NMGP_NONSEPARABLE || G < 0 || n_sample < 0 ||
+      (pl->S > 0 && G > 0 && n_sample > 0 && (!pars || !xstar || !tl_star || !uL_star || !mu_f || !s2_y))) {
+    set_last_error("nmgp_predict_moments: needs a nonseparable plan and non-null buffers");
+    return NMGP_EINVAL;
+  }
+  if (pl->S == 0 || G == 0 || n_sample == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl->N, M = pl->M, P = pl->P, T = pl->T;
+  const size_t C = (size_t)G * n_sample;
+  long launches = 0;
+  const size_t per = predict_scratch_per_subject(N, M, (long)C);
+  NMGP_TRY(ensure_pred_scratch(pl, per, pl->chunk));
+  for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
+    const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
+    BlockBatch b = pl->bb;
+    b.batch = cs;
+    const double* xs = pl->x + (size_t)s0 * N;
+    const double* Ys = pl->Y + (size_t)s0 * N * M;
+    NMGP_TRY(svc_forward(cs, N, M, xs, pars + (size_t)s0 * P, P, pl->hc, pl->w, b, st, &launches));
+    NMGP_TRY(run_potrf(pl, b, st, &launches));
+    NMGP_TRY(run_potri(pl, b, st, &launches));
+    if (info) NMGP_CUDA_TRY(cudaMemcpyAsync(info + s0, b.info, (size_t)cs * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    NMGP_TRY(predict_moments_chunk(cs, N, M, xs, Ys, pl->w, b, xstar + (size_t)s0 * G, tl_star + (size_t)s0 * C,
+                                   uL_star + (size_t)s0 * C * T, G, n_sample, pl->pred_scratch, pl->pred_scratch_doubles,
+                                   mu_f + (size_t)s0 * C * M, s2_y + (size_t)s0 * C * M, st, &launches));
+  }
+  pl->last_launches = launches;
   return 0;
 }
 

@@ -40,6 +40,27 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// -------------------------------------------------------------------------------- covariance functions
+// squared distance exactly as Utility/kernels.py:13-20 forms it: (x_i^2 + x_j^2) - 2.0*(x_i*x_j), no FMA contraction
+__device__ __forceinline__ double ref_sqdist(double xi, double xj) {
+  const double s = __dadd_rn(__dmul_rn(xi, xi), __dmul_rn(xj, xj));
+  return __dsub_rn(s, __dmul_rn(2.0, __dmul_rn(xi, xj)));
+}
+
+// Gibbs kernel value without jitter and its log-derivative factor w.r.t. tilde_l_i
+__device__ __forceinline__ void gibbs_pair(double xi, double xj, double li, double lj, double sij, double& k0,
+                                           double& cfac) {
+  const double d = ref_sqdist(xi, xj);
+  const double li2 = __dmul_rn(li, li);
+  const double A = __dadd_rn(li2, __dmul_rn(lj, lj));
+  const double Bm = __dmul_rn(li, lj);
+  const double root = sqrt(__ddiv_rn(__dmul_rn(2.0, Bm), A));
+  const double e = exp(__ddiv_rn(-d, A));
+  k0 = __dmul_rn(__dmul_rn(sij, root), e);            // (C*sqrt(2B/A))*exp(-d/A), kernels.py:72
+  const double q = li2 / A;
+  cfac = 0.5 - q + 2.0 * d * q / A;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -14,26 +14,6 @@ namespace {
 
 constexpr int NB = kNB;
 
-// squared distance exactly as Utility/kernels.py:13-20 forms it: (x_i^2 + x_j^2) - 2.0*(x_i*x_j), no FMA contraction
-__device__ __forceinline__ double ref_sqdist(double xi, double xj) {
-  const double s = __dadd_rn(__dmul_rn(xi, xi), __dmul_rn(xj, xj));
-  return __dsub_rn(s, __dmul_rn(2.0, __dmul_rn(xi, xj)));
-}
-
-// Gibbs kernel value without jitter and its log-derivative factor w.r.t. tilde_l_i
-__device__ __forceinline__ void gibbs_pair(double xi, double xj, double li, double lj, double sij, double& k0,
-                                           double& cfac) {
-  const double d = ref_sqdist(xi, xj);
-  const double li2 = __dmul_rn(li, li);
-  const double A = __dadd_rn(li2, __dmul_rn(lj, lj));
-  const double Bm = __dmul_rn(li, lj);
-  const double root = sqrt(__ddiv_rn(__dmul_rn(2.0, Bm), A));
-  const double e = exp(__ddiv_rn(-d, A));
-  k0 = __dmul_rn(__dmul_rn(sij, root), e);            // (C*sqrt(2B/A))*exp(-d/A), kernels.py:72
-  const double q = li2 / A;
-  cfac = 0.5 - q + 2.0 * d * q / A;
-}
-
 // ------------------------------------------------------------------------------------------ unit kernels
 __global__ void rbf_cov_kernel(const double* __restrict__ x1, int N1, const double* __restrict__ x2, int N2,
                                double alpha2, double beta, int self, double* __restrict__ out) {
@@ -1054,12 +1034,27 @@ int launch_nonseparable_cov_reference_order(const double* x, const double* pars,
   return 0;
 }
 
+int launch_svc_prep(int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w, cudaStream_t st,
+                    long* launches) {
+  if (cs <= 0) return 0;
+  svc_prep_kernel<<<cs, 256, 0, st>>>(pars, P, N, M, padded_M(M), h.mu0, h.mu1, w.ell, w.Lst, w.s2, w.R0, w.R1);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_symv(const BlockBatch& b, int n, const double* y, double* alpha, int batch, cudaStream_t st, long* launches) {
+  if (batch <= 0) return 0;
+  dim3 gs((n + 7) / 8, batch);
+  symv_kernel<<<gs, 256, 0, st>>>(b.A, b.strideA(), b.nP, n, y, alpha);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
 int svc_forward(int cs, int N, int M, const double* x, const double* pars, int P, const HyperConst& h, const Scratch& w,
                 const BlockBatch& b, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   const int MT = padded_M(M);
-  svc_prep_kernel<<<cs, 256, 0, st>>>(pars, P, N, M, MT, h.mu0, h.mu1, w.ell, w.Lst, w.s2, w.R0, w.R1);
-  NMGP_LAUNCH_CHECK();
+  NMGP_TRY(launch_svc_prep(cs, N, M, pars, P, h, w, st, launches));
   dim3 gk((N + 127) / 128, N, cs);
   kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, nullptr, N, w.Kx, w.CK);
   NMGP_LAUNCH_CHECK();

@@ -73,6 +73,25 @@ int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int 
 int launch_nonseparable_cov_reference_order(const double* x, const double* pars, int batch, int N, int M, double* out,
                                             cudaStream_t st);
 
+// pieces of the nonseparable pass used on their own by the prediction path
+int launch_svc_prep(int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w, cudaStream_t st,
+                    long* launches);   // pars -> ell, Lst, s2, prior residuals R0 / R1
+int launch_symv(const BlockBatch& b, int n, const double* y, double* alpha, int batch, cudaStream_t st, long* launches);
+
+// ---- posterior prediction, nonseparable model (Utility/prediction.py:1038-1262; predict.cu)
+// conditional moments of one GP prior at G new inputs per subject; scratch: predict_prior_scratch_per_subject doubles each
+size_t predict_prior_scratch_per_subject(int N, int G);
+int launch_predict_prior(const double* x, const double* Lp, const double* Z, int cs, int N, int nv, const double* xstar,
+                         int G, double alpha, double beta, double mu, double* scratch, double* mean_out, double* s2_out,
+                         cudaStream_t st, long* launches);
+// predictive mean / variance of the M outputs for G * ns (grid point, sample) columns per subject, after the chunk's
+// covariance has been built, factored and inverted in `b` (A = Sigma^-1) with `w` from svc_forward
+size_t predict_scratch_per_subject(int N, int M, long C);
+int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y, const Scratch& w, const BlockBatch& b,
+                          const double* xstar, const double* tl_star, const double* uL_star, int G, int ns,
+                          double* scratch, size_t scratch_doubles, double* mu_f, double* s2y, cudaStream_t st,
+                          long* launches);
+
 // ---- separable / stationary models (Utility/logpos.py:237-296, 405-462)
 int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,
                 const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches);

@@ -1,0 +1,131 @@
+"""CPU oracle for posterior prediction of the nonseparable model.  TEST INFRASTRUCTURE ONLY (see nmgp_oracle.py: only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU legs may import anything under `oracle/`).
+
+Restates the reference's algorithm, `Utility/prediction.py:1038-1262`
+(`point_/pointwise_/test_predmap_inhomogeneous_sampling`), in torch CPU float64 with the same dense operation
+sequence per grid point and sample:
+
+  conditional of the GP priors at x*:   proj = Sigma_p^-1 k_p (LU solve),  mu = mu_p + proj . (v - mu_p),
+                                        sigma2 = k_p(x*,x*) - proj . k_p,  clipped to 1e-6 when negative  (:1060-1092)
+  draws, in this order per sample:      tilde_l* (1), uL* (T), y (M)  from torch's global generator        (:1113-1169)
+  predictive moments:                   Sigma^-1 by `symeig`, mu_f = k_f^T Sigma^-1 y,
+                                        Sigma_f = A - (k_f^T chol(Sigma^-1)) (..)^T, sigma2_y = diag + sigma2_err,
+                                        values <= 0 clipped to 1e-6                                         (:1130-1167)
+
+The only liberty taken: Sigma^-1 and its Cholesky factor do not depend on the grid point or the sample, so they are formed
+once instead of G * n_sample times (the same LAPACK calls on the same matrix return the same bits).
+
+Parity pin: `tests/golden/predict_*.npz`, generated from the unmodified reference by `tests/golden/make_golden_predict.py`
+(every draw's loc / scale / value recorded); `tests/test_oracle_golden.py` checks this file against all of them.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import nmgp_oracle as O
+
+PRECISION = 1e-6  # Utility/settings.py:6
+
+
+def rbf_cross(x1: torch.Tensor, x2: torch.Tensor, alpha: float, beta: float) -> torch.Tensor:
+    """alpha^2 exp(-0.5 |(x1_i - x2_j)/beta|^2), no jitter (Utility/kernels.py:24-43 with X2 given)."""
+    a, b = x1 / beta, x2 / beta
+    d = ((a * a).view(-1, 1) + (b * b).view(1, -1)) - 2.0 * (a.view(-1, 1) * b.view(1, -1))
+    return torch.exp(-0.5 * d) * alpha ** 2
+
+
+def gibbs_cross(x1, ell1, x2, ell2) -> torch.Tensor:
+    """sqrt(2 l1_i l2_j / (l1_i^2 + l2_j^2)) exp(-d_ij / (l1_i^2 + l2_j^2)), no jitter (Utility/kernels.py:46-73, X2 given)."""
+    d = ((x1 * x1).view(-1, 1) + (x2 * x2).view(1, -1)) - 2.0 * (x1.view(-1, 1) * x2.view(1, -1))
+    A = (ell1 ** 2).view(-1, 1) + (ell2 ** 2).view(1, -1)
+    B = ell1.view(-1, 1) * ell2.view(1, -1)
+    return torch.sqrt(2.0 * B / A) * torch.exp(-d / A)
+
+
+def prior_conditional(x, x_star, v_cols, mu, alpha, beta):
+    """Conditional mean(s) and variance of a GP prior at x_star given its values v_cols [N, C] at x
+    (prediction.py:1060-1068 for tilde_l, :1070-1081 for the T columns of uL).  Returns (mu [C], sigma2 scalar)."""
+    Sigma = O.rbf_cov(x, alpha, beta)
+    k = rbf_cross(x, x_star.view(1), alpha, beta)                       # N x 1
+    proj = torch.linalg.solve(Sigma, k).view(-1)                         # torch.solve(input=k, A=Sigma)
+    mu_c = mu + (proj.view(-1, 1) * (v_cols - mu)).sum(0)
+    s2 = (alpha ** 2 + O.JITTER) - torch.dot(proj, k.view(-1))           # RBF_cov(x*)[0,0] = jitter + alpha^2
+    return mu_c, s2
+
+
+def predictive_moments(x, ell, Lmats, y_om, invS, invL, s2e, x_star, tilde_l_star, L_star):
+    """mu_f [M], sigma2_y [M] at one x_star for one sampled (tilde_l*, L*)  (prediction.py:1144-1165)."""
+    N, M = Lmats.shape[0], Lmats.shape[1]
+    order = torch.arange(N * M).view(N, M).t().reshape(-1)
+    l_star = torch.exp(tilde_l_star).view(1)
+    k_x = gibbs_cross(x, ell, x_star.view(1), l_star).view(-1)            # N
+    A_f = (k_x.view(N, 1, 1) * Lmats).reshape(N * M, M)                   # rows (i,m): k_i * L_i
+    k_f = (L_star @ A_f.t()).t()[order]                                   # NM x M, output-major rows
+    mu_f = k_f.t() @ (invS @ y_om)
+    Tm = k_f.t() @ invL
+    A = (1.0 + O.JITTER) * (L_star @ L_star.t())                          # Nonstationary_RBF_cov(x*)[0,0] = 1 + jitter
+    Sigma_y = A - Tm @ Tm.t() + s2e * torch.eye(M, dtype=O.DTYPE)
+    s2y = torch.diagonal(Sigma_y).clone()
+    s2y[s2y <= 0] = PRECISION
+    return mu_f, s2y
+
+
+def pointwise_predict(n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                      mu_L, alpha_L, beta_L, mode="y"):
+    """All draws of `pointwise_predmap_inhomogeneous_sampling` (prediction.py:1194-1235) with torch's global generator
+    consumed in the reference's order.  mode: "y" (default), "smoothness" (pred_smoothness=True), "cov" (pred_cov=True).
+    Returns a dict of arrays [G, ns, ...]: loc / scale / draw of every Normal the reference samples in that mode."""
+    N, M = Y.shape
+    T = O.tril_size(M)
+    G = grids.numel()
+    y_om = Y.t().reshape(-1)
+    ell = torch.exp(tilde_l)
+    s2e = torch.exp(tilde_sigma2_err)
+    Lmats = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(uL_vecs.view(N, T), M), M)
+    out = {k: [] for k in ("l_loc", "l_scale", "l_draw", "u_loc", "u_scale", "u_draw", "y_loc", "y_scale", "y_draw")}
+    if mode == "y":
+        Sigma = O.nonseparable_cov(x, tilde_l, uL_vecs, M)
+        w, V = torch.linalg.eigh(Sigma, UPLO="U")
+        invS = (V @ torch.diag(1.0 / (s2e + w))) @ V.t()                  # prediction.py:1144-1146
+        invL = torch.linalg.cholesky(invS)
+    for g in range(G):
+        xs = grids[g]
+        if mode in ("y", "smoothness"):
+            mu_l, s2_l = prior_conditional(x, xs, tilde_l.view(N, 1), mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+            mu_l = mu_l[0]
+            if s2_l < 0:
+                s2_l = torch.tensor(PRECISION, dtype=O.DTYPE)
+        if mode in ("y", "cov"):
+            mu_u, s2_u = prior_conditional(x, xs, uL_vecs.view(N, T), mu_L, alpha_L, beta_L)
+            s2_u = s2_u.expand(T).clone()
+            s2_u[s2_u < 0] = PRECISION
+        for _ in range(n_sample):
+            if mode in ("y", "smoothness"):
+                sc = torch.sqrt(s2_l)
+                tl_star = torch.empty((), dtype=O.DTYPE).normal_().mul(sc).add(mu_l)
+                out["l_loc"].append(float(mu_l)); out["l_scale"].append(float(sc)); out["l_draw"].append(float(tl_star))
+            if mode in ("y", "cov"):
+                sc = torch.sqrt(s2_u)
+                uL_star = torch.empty(T, dtype=O.DTYPE).normal_().mul(sc).add(mu_u)
+                out["u_loc"].append(mu_u.numpy().copy()); out["u_scale"].append(sc.numpy().copy())
+                out["u_draw"].append(uL_star.numpy().copy())
+            if mode == "y":
+                L_star = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(uL_star, M), M)
+                mu_f, s2y = predictive_moments(x, ell, Lmats, y_om, invS, invL, s2e, xs, tl_star, L_star)
+                sc = torch.sqrt(s2y)
+                yd = torch.empty(M, dtype=O.DTYPE).normal_().mul(sc).add(mu_f)
+                out["y_loc"].append(mu_f.numpy().copy()); out["y_scale"].append(sc.numpy().copy())
+                out["y_draw"].append(yd.numpy().copy())
+    res = {}
+    for k, v in out.items():
+        if v:
+            a = np.asarray(v)
+            res[k] = a.reshape(G, n_sample, *a.shape[1:])
+    return res
+
+
+def summarise(y_draw: np.ndarray):
+    """quantiles [G,2,M], mean [G,M], std [G,M] as the reference forms them per grid point (prediction.py:1186-1190)."""
+    q = np.stack([np.percentile(s, q=[2.5, 97.5], axis=0) for s in y_draw])
+    return q, y_draw.mean(axis=1), y_draw.std(axis=1)

@@ -18,7 +18,30 @@ def pytest_configure(config):
 
 
 def golden_cases():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """log-posterior + gradient fixtures (tests/golden/make_golden.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith("predict_"))
+
+
+def predict_cases():
+    """posterior-prediction fixtures (tests/golden/make_golden_predict.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "predict_*.npz")))
+
+
+def load_predict_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["hyper"] = json.loads(str(d["hyper"]))
+    for k in ("N", "M", "n_sample", "seed"):
+        d[k] = int(d[k])
+    return d
+
+
+def max_rel(a, b):
+    """max |a-b| / max |b|"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
 def load_golden(name):

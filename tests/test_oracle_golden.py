@@ -3,7 +3,7 @@ reference (tests/golden/make_golden.py).  CPU-only."""
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden, rel_err
+from conftest import golden_cases, load_golden, load_predict_golden, max_rel, predict_cases, rel_err
 from oracle import nmgp_oracle as O
 
 # The oracle restates the reference's algorithm op-for-op, so agreement is at rounding level for the
@@ -24,3 +24,32 @@ def test_oracle_matches_reference_golden(name):
         assert rel_err(vals[k], ref[k]) < VAL_TOL, (name, k, vals[k], ref[k])
     assert rel_err(grad.numpy(), g["grad"]) < GRAD_TOL, name
     assert grad.shape[0] == O.n_params(g["model"], g["N"], g["M"])
+
+
+@pytest.mark.parametrize("name", predict_cases())
+def test_predict_oracle_matches_reference_golden(name):
+    """oracle/nmgp_predict_oracle.py against every draw (loc, scale, value) the unmodified reference made
+    (Utility/prediction.py:1038-1262, recorded by tests/golden/make_golden_predict.py), same seed, same generator."""
+    import torch
+    from oracle import nmgp_predict_oracle as PO
+    g = load_predict_golden(name)
+    N, M = g["N"], g["M"]
+    T = M * (M + 1) // 2
+    pars = torch.from_numpy(g["pars"])
+    args = (g["n_sample"], pars[:N], pars[N:N + N * T], pars[-1], torch.from_numpy(g["Y"]), torch.from_numpy(g["x"]),
+            torch.from_numpy(g["grids"]))
+    torch.manual_seed(1000 + g["seed"])
+    r = PO.pointwise_predict(*args, **g["hyper"])
+    # same operations as the reference; LAPACK's eigh / LU results move at the 1e-11 level with the thread count
+    for k in ("l_loc", "l_scale", "l_draw", "u_loc", "u_scale", "u_draw", "y_loc", "y_scale", "y_draw"):
+        assert max_rel(r[k], g[k]) < VAL_TOL, (name, k, max_rel(r[k], g[k]))
+    q, mean, std = PO.summarise(r["y_draw"])
+    assert max_rel(q, g["quantiles"]) < VAL_TOL and max_rel(mean, g["mean"]) < VAL_TOL and max_rel(std, g["std"]) < VAL_TOL
+    torch.manual_seed(2000 + g["seed"])
+    r = PO.pointwise_predict(*args, mode="smoothness", **g["hyper"])
+    assert max_rel(r["l_draw"], g["smooth"]) < VAL_TOL
+    torch.manual_seed(3000 + g["seed"])
+    r = PO.pointwise_predict(*args, mode="cov", **g["hyper"])
+    from oracle import nmgp_oracle as O
+    Ls = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(torch.from_numpy(r["u_draw"]), M), M).numpy()
+    assert max_rel(Ls, g["cov"]) < VAL_TOL
