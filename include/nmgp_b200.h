@@ -129,7 +129,10 @@ int nmgp_adam_step(double* pars_dev, const double* grad_dev, double* m_dev, doub
  *     mu_uL [S,G,T], s2_uL [S,G]   same for the T columns of uL (one shared variance, prediction.py:1079-1081)
  *   computed with the plan's cached Cholesky factors of the prior covariances (the reference LU-solves per call).
  *
- * nmgp_predict_moments  (prediction.py:1130-1165): tl_star [S,G,n_sample], uL_star [S,G,n_sample,T] (unconstrained) ->
+ * nmgp_predict_moments  (prediction.py:1130-1165): tl_star [S,G,n_sample], uL_star [S,G,n_sample,T] ->
+ *     (uL_star is the unconstrained row-major triangle, exp() on its diagonal slots as utils.py:10-22; with
+ *      flags & NMGP_PRED_RAW_FACTOR it is used as the factor itself, which is what the posterior-sample variant
+ *      point_predsample_inhomogeneous does, prediction.py:1310-1311)
  *     mu_f [S,G,n_sample,M]   k_f^T Sigma^-1 y
  *     s2_y [S,G,n_sample,M]   diag(A - k_f^T Sigma^-1 k_f) + sigma2_err   (values <= 0 -> 1e-6, prediction.py:1163)
  *     info [S] (may be NULL)  as in nmgp_logpost_grad
@@ -137,9 +140,10 @@ int nmgp_adam_step(double* pars_dev, const double* grad_dev, double* m_dev, doub
  *   `symeig` + `cholesky` per x* and per sample); see csrc/predict.cu for the sample-dependent part. */
 int nmgp_predict_prior_moments(nmgp_plan* plan, const double* pars_dev, const double* xstar_dev, int G, double* mu_l_dev,
                                double* s2_l_dev, double* mu_uL_dev, double* s2_uL_dev, void* stream);
+#define NMGP_PRED_RAW_FACTOR 1
 int nmgp_predict_moments(nmgp_plan* plan, const double* pars_dev, const double* xstar_dev, int G, int n_sample,
-                         const double* tl_star_dev, const double* uL_star_dev, double* mu_f_dev, double* s2_y_dev,
-                         int* info_dev, void* stream);
+                         const double* tl_star_dev, const double* uL_star_dev, int flags, double* mu_f_dev,
+                         double* s2_y_dev, int* info_dev, void* stream);
 
 /* Last error message of the calling thread ("" if none). */
 const char* nmgp_last_error(void);

@@ -24,6 +24,7 @@ NHYPER = 9
 NPHASES = 5
 PHASE_NAMES = ("build", "potrf", "potri", "prior_solves", "contract")
 STATIONARY, SEPARABLE, NONSEPARABLE = 0, 1, 2
+PRED_RAW_FACTOR = 1
 
 _lock = threading.Lock()
 _lib = None
@@ -105,7 +106,7 @@ def _declare(lib):
     lib.nmgp_predict_prior_moments.restype = c.c_int
     lib.nmgp_predict_prior_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, dp, dp, dp, dp, vp]
     lib.nmgp_predict_moments.restype = c.c_int
-    lib.nmgp_predict_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, c.c_int, dp, dp, dp, dp, ip, vp]
+    lib.nmgp_predict_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, c.c_int, dp, dp, c.c_int, dp, dp, ip, vp]
     lib.nmgp_rbf_cov.restype = c.c_int
     lib.nmgp_rbf_cov.argtypes = [dp, c.c_int, dp, c.c_int, c.c_double, c.c_double, dp, vp]
     lib.nmgp_gibbs_cov.restype = c.c_int

@@ -241,10 +241,11 @@ class LogPosteriorPlan:
         _lib.check(rc, "nmgp_predict_prior_moments")
         return mu_l, s2_l, mu_u, s2_u
 
-    def predict_moments(self, pars, xstar, tl_star, uL_star):
+    def predict_moments(self, pars, xstar, tl_star, uL_star, raw_factor: bool = False):
         """Predictive mean and variance of the M outputs for sampled (tilde_l*, uL*) (Utility/prediction.py:1130-1165).
         pars [S,P], xstar [G] or [S,G], tl_star [S,G,ns], uL_star [S,G,ns,T] ->
-        (mu_f [S,G,ns,M], s2_y [S,G,ns,M], info [S]), CUDA tensors."""
+        (mu_f [S,G,ns,M], s2_y [S,G,ns,M], info [S]), CUDA tensors.  raw_factor=True: uL_star is the factor's triangle
+        itself (no exp on the diagonal), as in point_predsample_inhomogeneous (prediction.py:1310-1311)."""
         torch = _lib.require_cuda()
         if self.model != "nonseparable":
             raise ValueError("prediction is implemented for the nonseparable model")
@@ -260,7 +261,8 @@ class LogPosteriorPlan:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             rc = self.lib.nmgp_predict_moments(self._handle, p.data_ptr(), xs.data_ptr(), G, ns, tl.data_ptr(),
-                                               ul.data_ptr(), mu_f.data_ptr(), s2_y.data_ptr(), info.data_ptr(),
+                                               ul.data_ptr(), _lib.PRED_RAW_FACTOR if raw_factor else 0, mu_f.data_ptr(),
+                                               s2_y.data_ptr(), info.data_ptr(),
                                                ctypes.c_void_p(stream))
         _lib.check(rc, "nmgp_predict_moments")
         return mu_f, s2_y, info

@@ -633,7 +633,7 @@ int nmgp_predict_prior_moments(nmgp_plan* pl, const double* pars, const double* 
 }
 
 int nmgp_predict_moments(nmgp_plan* pl, const double* pars, const double* xstar, int G, int n_sample, const double* tl_star,
-                         const double* uL_star, double* mu_f, double* s2_y, int* info, void* stream) {
+                         const double* uL_star, int flags, double* mu_f, double* s2_y, int* info, void* stream) {
   if (!pl || pl->model != NMGP_NONSEPARABLE || G < 0 || n_sample < 0 ||
       (pl->S > 0 && G > 0 && n_sample > 0 && (!pars || !xstar || !tl_star || !uL_star || !mu_f || !s2_y))) {
     set_last_error("nmgp_predict_moments: needs a nonseparable plan and non-null buffers");
@@ -657,7 +657,8 @@ int nmgp_predict_moments(nmgp_plan* pl, const double* pars, const double* xstar,
     NMGP_TRY(run_potri(pl, b, st, &launches));
     if (info) NMGP_CUDA_TRY(cudaMemcpyAsync(info + s0, b.info, (size_t)cs * sizeof(int), cudaMemcpyDeviceToDevice, st));
     NMGP_TRY(predict_moments_chunk(cs, N, M, xs, Ys, pl->w, b, xstar + (size_t)s0 * G, tl_star + (size_t)s0 * C,
-                                   uL_star + (size_t)s0 * C * T, G, n_sample, pl->pred_scratch, pl->pred_scratch_doubles,
+                                   uL_star + (size_t)s0 * C * T, G, n_sample, (flags & NMGP_PRED_RAW_FACTOR) ? 1 : 0,
+                                   pl->pred_scratch, pl->pred_scratch_doubles,
                                    mu_f + (size_t)s0 * C * M, s2_y + (size_t)s0 * C * M, st, &launches));
   }
   pl->last_launches = launches;

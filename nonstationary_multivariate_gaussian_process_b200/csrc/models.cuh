@@ -89,8 +89,8 @@ int launch_predict_prior(const double* x, const double* Lp, const double* Z, int
 size_t predict_scratch_per_subject(int N, int M, long C);
 int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y, const Scratch& w, const BlockBatch& b,
                           const double* xstar, const double* tl_star, const double* uL_star, int G, int ns,
-                          double* scratch, size_t scratch_doubles, double* mu_f, double* s2y, cudaStream_t st,
-                          long* launches);
+                          int raw_factor, double* scratch, size_t scratch_doubles, double* mu_f, double* s2y,
+                          cudaStream_t st, long* launches);
 
 // ---- separable / stationary models (Utility/logpos.py:237-296, 405-462)
 int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,

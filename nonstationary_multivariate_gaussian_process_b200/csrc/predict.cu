@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128) pred_finish_kernel(const double* __restri
                                                           const double* __restrict__ U, const double* __restrict__ Q,
                                                           int Cpad, const double* __restrict__ uL_star,
                                                           const double* __restrict__ s2v, int N, int M, int MT, int T,
-                                                          int C, int c0, double* __restrict__ mu_f,
+                                                          int C, int c0, int raw_factor, double* __restrict__ mu_f,
                                                           double* __restrict__ s2y) {
   const int col = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(128) pred_finish_kernel(const double* __restri
   const double* Qc = Q + (long)cc * T * Cpad + col;
   double l[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) l[k] = (k < mp) ? us[k] : (k == mp ? exp(us[k]) : 0.0);   // utils.py:10-22
+  for (int k = 0; k < 16; ++k)   // utils.py:10-22; the history variant uses the sampled vector as the factor itself (:1311)
+    l[k] = (k < mp) ? us[k] : (k == mp ? (raw_factor ? us[k] : exp(us[k])) : 0.0);
   double mu = 0.0, ll = 0.0, B = 0.0;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -336,8 +337,8 @@ size_t predict_scratch_per_subject(int N, int M, long C) { return pred_layout(N,
 
 int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y, const Scratch& w, const BlockBatch& b,
                           const double* xstar, const double* tl_star, const double* uL_star, int G, int ns,
-                          double* scratch, size_t scratch_doubles, double* mu_f, double* s2y, cudaStream_t st,
-                          long* launches) {
+                          int raw_factor, double* scratch, size_t scratch_doubles, double* mu_f, double* s2y,
+                          cudaStream_t st, long* launches) {
   if (cs <= 0 || G <= 0 || ns <= 0) return 0;
   const int n = N * M, MT = padded_M(M);
   const long C = (long)G * ns;
@@ -371,7 +372,7 @@ int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y
     NMGP_LAUNCH_CHECK();
     dim3 gf((unsigned)((C + 3) / 4), sb);
     pred_finish_kernel<<<gf, 128, 0, st>>>(KXT, (long)pl.kx, pl.Npad, w.Ua, Qb, pl.Cpad, uL_star, w.s2, N, M, MT, pl.T,
-                                           (int)C, c0, mu_f, s2y);
+                                           (int)C, c0, raw_factor, mu_f, s2y);
     NMGP_LAUNCH_CHECK();
   }
   return 0;

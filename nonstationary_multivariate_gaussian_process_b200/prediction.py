@@ -4,6 +4,8 @@
     point_predmap_inhomogeneous_sampling     (n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_star, **hyper)  :1038
     pointwise_predmap_inhomogeneous_sampling (n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, grids,  **hyper)  :1194
     test_predmap_inhomogeneous_sampling      (n_sample, tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_test, **hyper)  :1237
+    point_/pointwise_/test_predmap_inhomogeneous      (plug-in of the conditional means, no sampling)               :912-1036
+    point_/pointwise_/test_predsample_inhomogeneous   (one draw per posterior sample of an HMC history)             :1265-1400
 
 (callers: Nonseparable_Model/Nonseparable_model.py:377, 387, 399 with n_sample = 100 and 201 grid points.)
 
@@ -130,3 +132,124 @@ def test_predmap_inhomogeneous_sampling(n_sample, tilde_l, uL_vecs, tilde_sigma2
 
 
 test_predmap_inhomogeneous_sampling.__test__ = False   # not a pytest test
+
+
+# ------------------------------------------------------------------------------------- plug-in variant (no sampling)
+def pointwise_predmap_inhomogeneous(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                                    mu_L, alpha_L, beta_L, *args, **kwargs):
+    """Plug-in prediction (prediction.py:990-1012): tilde_l* and uL* are set to their conditional means.
+    Returns (percentiles [G,3,M] = mu_f -/+ 1.96 sd, L* vectors [G,T]) as CPU tensors."""
+    torch = _lib.require_cuda()
+    plan, pars = _plan_and_pars(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L,
+                                alpha_L, beta_L, kwargs)
+    g = torch.as_tensor(grids, dtype=torch.float64).reshape(-1)
+    mu_l, _, mu_u, _ = plan.predict_prior_moments(pars, g)
+    mu_f, s2_y, info = plan.predict_moments(pars, g, mu_l.unsqueeze(2), mu_u.unsqueeze(2))
+    if int(info[0]) != 0:
+        raise _lib.NmgpError(f"prediction: the covariance is not positive definite (pivot {int(info[0])})")
+    mu_f, sd = mu_f[0, :, 0].cpu(), torch.sqrt(s2_y[0, :, 0]).cpu()
+    pct = torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd], dim=1)        # prediction.py:984
+    return pct, utils.uLvec2Lvec(mu_u[0].cpu(), plan.M)
+
+
+def point_predmap_inhomogeneous(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, x_star, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                                mu_L, alpha_L, beta_L, *args, **kwargs):
+    """(prediction.py:912-988): (percentiles [3,M], L* vector [T])."""
+    pct, Lv = pointwise_predmap_inhomogeneous(tilde_l, uL_vecs, tilde_sigma2_err, Y, x,
+                                              np.asarray(x_star, dtype=np.float64).reshape(1), mu_tilde_l, alpha_tilde_l,
+                                              beta_tilde_l, mu_L, alpha_L, beta_L, **kwargs)
+    return pct[0], Lv[0]
+
+
+def test_predmap_inhomogeneous(tilde_l, L_vecs, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L,
+                               alpha_L, beta_L, *args, **kwargs):
+    """(prediction.py:1014-1036)"""
+    return pointwise_predmap_inhomogeneous(tilde_l, L_vecs, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l,
+                                           beta_tilde_l, mu_L, alpha_L, beta_L, **kwargs)
+
+
+test_predmap_inhomogeneous.__test__ = False
+
+
+# ------------------------------------------------------------------------------------- posterior-sample variant
+_HIST_PLANS = {}
+
+
+def _history_plan(H, Y, x, hyper):
+    """One plan whose H 'subjects' are the same data under H different parameter vectors (an HMC history)."""
+    torch = _lib.require_cuda()
+    from .batched import LogPosteriorPlan
+    Y = torch.as_tensor(Y, dtype=torch.float64)
+    x = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
+    key = (H, logpos._fingerprint(Y), logpos._fingerprint(x), tuple(sorted((k, float(v)) for k, v in hyper.items())),
+           torch.cuda.current_device())
+    plan = _HIST_PLANS.get(key)
+    if plan is None:
+        for old in _HIST_PLANS.values():
+            old.close()
+        _HIST_PLANS.clear()
+        plan = LogPosteriorPlan("nonseparable", x.unsqueeze(0).expand(H, -1), Y.unsqueeze(0).expand(H, -1, -1), hyper)
+        _HIST_PLANS[key] = plan
+    return plan
+
+
+def pointwise_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l,
+                                       alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, *args, **kwargs):
+    """One predictive draw per posterior sample of a parameter history, at every new input (prediction.py:1359-1378):
+    returns a numpy array [G, N_sample, M].  Every history entry has its own covariance: the entries are evaluated as the
+    'subjects' of ONE batched plan (one factorisation + inverse each), all new inputs at once.
+    As in the reference (prediction.py:1300-1311) the L* conditional is taken on the CONSTRAINED triangles L_vecs and the
+    drawn vector is used as the factor itself."""
+    torch = _lib.require_cuda()
+    f64 = torch.float64
+    tl_h = torch.as_tensor(tilde_l_hist, dtype=f64)[-N_sample:]
+    ul_h = torch.as_tensor(uL_vecs_hist, dtype=f64)[-N_sample:]
+    ts_h = torch.as_tensor(tilde_sigma2_err_hist, dtype=f64).reshape(-1)[-N_sample:]
+    H, N = int(tl_h.shape[0]), int(tl_h.shape[1])
+    hyper = dict(mu_tilde_l=mu_tilde_l, alpha_tilde_l=alpha_tilde_l, beta_tilde_l=beta_tilde_l, mu_L=mu_L, alpha_L=alpha_L,
+                 beta_L=beta_L, a=kwargs.get("a", 1), b=kwargs.get("b", 1))
+    plan = _history_plan(H, Y, x, hyper)
+    M = plan.M
+    T = M * (M + 1) // 2
+    g = torch.as_tensor(grids, dtype=f64).reshape(-1)
+    G = int(g.numel())
+    pars = torch.cat([tl_h, ul_h, ts_h.unsqueeze(1)], dim=1).detach()
+    L_h = utils.uLvec2Lvec(ul_h.reshape(H * N, T), M).reshape(H, N * T)
+    pars_L = torch.cat([tl_h, L_h, ts_h.unsqueeze(1)], dim=1).detach()          # residuals L_vecs - mu_L, prediction.py:1302
+    mu_l, s2_l, _, _ = (t.cpu() for t in plan.predict_prior_moments(pars, g))    # [H,G]
+    _, _, mu_L_c, s2_L_c = (t.cpu() for t in plan.predict_prior_moments(pars_L, g))
+    z_l = torch.empty((G, H), dtype=f64)
+    z_u = torch.empty((G, H, T), dtype=f64)
+    z_y = torch.empty((G, H, M), dtype=f64)
+    for gi in range(G):          # the reference's order: per new input, per history entry: tilde_l*, L*, y
+        for h in range(H):
+            z_l[gi, h] = torch.empty((), dtype=f64).normal_()
+            z_u[gi, h] = torch.empty(T, dtype=f64).normal_()
+            z_y[gi, h] = torch.empty(M, dtype=f64).normal_()
+    tl_star = z_l.t().mul(torch.sqrt(s2_l)).add(mu_l)                            # [H,G]
+    L_star = z_u.transpose(0, 1).mul(torch.sqrt(s2_L_c).unsqueeze(2)).add(mu_L_c)   # [H,G,T]
+    mu_f, s2_y, info = plan.predict_moments(pars, g, tl_star.unsqueeze(2), L_star.unsqueeze(2), raw_factor=True)
+    if int(info.abs().sum()) != 0:
+        raise _lib.NmgpError("prediction: a covariance of the history is not positive definite")
+    mu_f, sd = mu_f[:, :, 0].cpu().transpose(0, 1), torch.sqrt(s2_y[:, :, 0]).cpu().transpose(0, 1)   # [G,H,M]
+    return z_y.mul(sd).add(mu_f).numpy()
+
+
+def point_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, x_star, mu_tilde_l, alpha_tilde_l,
+                                   beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, *args, **kwargs):
+    """(prediction.py:1265-1357): tensor [N_sample, M]."""
+    torch = _lib.require_cuda()
+    res = pointwise_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x,
+                                             np.asarray(x_star, dtype=np.float64).reshape(1), mu_tilde_l, alpha_tilde_l,
+                                             beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, **kwargs)
+    return torch.from_numpy(res[0])
+
+
+def test_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l, alpha_tilde_l,
+                                  beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, *args, **kwargs):
+    """(prediction.py:1380-1399)"""
+    return pointwise_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l,
+                                              alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, N_sample, **kwargs)
+
+
+test_predsample_inhomogeneous.__test__ = False

@@ -129,3 +129,75 @@ def summarise(y_draw: np.ndarray):
     """quantiles [G,2,M], mean [G,M], std [G,M] as the reference forms them per grid point (prediction.py:1186-1190)."""
     q = np.stack([np.percentile(s, q=[2.5, 97.5], axis=0) for s in y_draw])
     return q, y_draw.mean(axis=1), y_draw.std(axis=1)
+
+
+def pointwise_predict_plugin(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L,
+                             alpha_L, beta_L):
+    """`pointwise_predmap_inhomogeneous` (prediction.py:912-1012): conditional means plugged in, no draws.
+    Returns (percentiles [G,3,M], L* vectors [G,T]) as numpy arrays."""
+    N, M = Y.shape
+    T = O.tril_size(M)
+    y_om = Y.t().reshape(-1)
+    ell, s2e = torch.exp(tilde_l), torch.exp(tilde_sigma2_err)
+    Lmats = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(uL_vecs.view(N, T), M), M)
+    w, V = torch.linalg.eigh(O.nonseparable_cov(x, tilde_l, uL_vecs, M), UPLO="U")
+    invS = (V @ torch.diag(1.0 / (s2e + w))) @ V.t()
+    invL = torch.linalg.cholesky(invS)
+    pct, Lv = [], []
+    for xs in grids:
+        mu_l, _ = prior_conditional(x, xs, tilde_l.view(N, 1), mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+        mu_u, _ = prior_conditional(x, xs, uL_vecs.view(N, T), mu_L, alpha_L, beta_L)
+        Lvec = O.unconstrained_to_tril_vec(mu_u, M)
+        mu_f, s2y = predictive_moments(x, ell, Lmats, y_om, invS, invL, s2e, xs, mu_l[0], O.tril_vec_to_matrix(Lvec, M))
+        sd = torch.sqrt(s2y)
+        pct.append(torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd]).numpy())
+        Lv.append(Lvec.numpy())
+    return np.stack(pct), np.stack(Lv)
+
+
+def pointwise_predict_history(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l, alpha_tilde_l,
+                              beta_tilde_l, mu_L, alpha_L, beta_L, N_sample):
+    """`pointwise_predsample_inhomogeneous` (prediction.py:1265-1378): per new input, per history entry (its own covariance):
+    tilde_l* ~ conditional of the tilde_l prior, L* ~ conditional taken on the CONSTRAINED triangles (prediction.py:1302) and
+    used as the factor itself (:1311), then y.  Returns a dict of [G, H, ...] arrays like `pointwise_predict`."""
+    N, M = Y.shape
+    T = O.tril_size(M)
+    y_om = Y.t().reshape(-1)
+    tl_h, ul_h, ts_h = tilde_l_hist[-N_sample:], uL_vecs_hist[-N_sample:], tilde_sigma2_err_hist[-N_sample:]
+    H, G = tl_h.shape[0], grids.numel()
+    pre = []
+    for h in range(H):
+        s2e = torch.exp(ts_h[h])
+        w, V = torch.linalg.eigh(O.nonseparable_cov(x, tl_h[h], ul_h[h], M), UPLO="U")
+        invS = (V @ torch.diag(1.0 / (s2e + w))) @ V.t()
+        Lvecs = O.unconstrained_to_tril_vec(ul_h[h].view(N, T), M)
+        pre.append((invS, torch.linalg.cholesky(invS), s2e, Lvecs, O.tril_vec_to_matrix(Lvecs, M)))
+    out = {k: [] for k in ("l_loc", "l_scale", "l_draw", "u_loc", "u_scale", "u_draw", "y_loc", "y_scale", "y_draw")}
+    for g in range(G):
+        xs = grids[g]
+        for h in range(H):
+            invS, invL, s2e, Lvecs, Lmats = pre[h]
+            mu_l, s2_l = prior_conditional(x, xs, tl_h[h].view(N, 1), mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+            if s2_l < 0:
+                s2_l = torch.tensor(PRECISION, dtype=O.DTYPE)
+            sc_l = torch.sqrt(s2_l)
+            tl_star = torch.empty((), dtype=O.DTYPE).normal_().mul(sc_l).add(mu_l[0])
+            mu_u, s2_u = prior_conditional(x, xs, Lvecs, mu_L, alpha_L, beta_L)
+            s2_u = s2_u.expand(T).clone()
+            s2_u[s2_u < 0] = PRECISION
+            sc_u = torch.sqrt(s2_u)
+            L_star_vec = torch.empty(T, dtype=O.DTYPE).normal_().mul(sc_u).add(mu_u)
+            mu_f, s2y = predictive_moments(x, torch.exp(tl_h[h]), Lmats, y_om, invS, invL, s2e, xs, tl_star,
+                                           O.tril_vec_to_matrix(L_star_vec, M))
+            sc_y = torch.sqrt(s2y)
+            yd = torch.empty(M, dtype=O.DTYPE).normal_().mul(sc_y).add(mu_f)
+            for k, v in (("l_loc", mu_l[0]), ("l_scale", sc_l), ("l_draw", tl_star)):
+                out[k].append(float(v))
+            for k, v in (("u_loc", mu_u), ("u_scale", sc_u), ("u_draw", L_star_vec), ("y_loc", mu_f), ("y_scale", sc_y),
+                         ("y_draw", yd)):
+                out[k].append(v.numpy().copy())
+    res = {}
+    for k, v in out.items():
+        a = np.asarray(v)
+        res[k] = a.reshape(G, H, *a.shape[1:])
+    return res

@@ -14,6 +14,10 @@ of the sampled outputs.  One .npz per case: inputs, the seed, the function's ret
     l_loc, l_scale, l_draw      [G, ns]       tilde_l_star ~ Normal(mu_l, sqrt(sigma2_l))        prediction.py:1113
     u_loc, u_scale, u_draw      [G, ns, T]    uL_vec_star  ~ Normal(mu_uL_vec, sqrt(sigma2_uL))  prediction.py:1124
     y_loc, y_scale, y_draw      [G, ns, M]    sampled_y    ~ Normal(mu_f, sqrt(sigma2_y))        prediction.py:1169
+
+plus `map_percentiles`, `map_Lvecs` (pointwise_predmap_inhomogeneous, prediction.py:990-1012: plug-in of the conditional
+means, no sampling) and `hist_*` (pointwise_predsample_inhomogeneous, prediction.py:1359-1378: one draw per posterior
+sample of a short synthetic parameter history; the same triplets with the history index in place of the sample index).
 """
 import json
 import os
@@ -74,6 +78,10 @@ CASES = [
 ]
 
 
+H_HIST = 3   # posterior samples used by the history variant (the history holds one more: `[-N_sample:]` is exercised)
+G_HIST = 3   # new inputs for the history variant
+
+
 def stack(records, width):
     loc = np.stack([np.broadcast_to(r[0].numpy(), (width,)) for r in records])
     sc = np.stack([np.broadcast_to(r[1].numpy(), (width,)) for r in records])
@@ -112,10 +120,33 @@ def main():
             RECORD.clear()
             torch.manual_seed(4000 + seed)
             tq, tmean, tstd = prediction.test_predmap_inhomogeneous_sampling(ns, tl, uL, ts, Yt, xt, grids[:2], **hyper)
+            # plug-in (no sampling) variant, prediction.py:912-1036
+            RECORD.clear()
+            map_pct, map_Lvecs = prediction.pointwise_predmap_inhomogeneous(tl, uL, ts, Yt, xt, grids, **hyper)
+            # posterior-sample variant, prediction.py:1265-1400: a short synthetic history of parameter vectors
+            hist = np.stack([synth.start_point("nonseparable", N, M, 100 + seed + h, noise) for h in range(H_HIST + 1)])
+            ht = torch.from_numpy(hist)
+            RECORD.clear()
+            torch.manual_seed(5000 + seed)
+            hist_y = prediction.pointwise_predsample_inhomogeneous(ht[:, :N], ht[:, N:N + N * T], ht[:, -1], Yt, xt,
+                                                                   grids[:G_HIST], N_sample=H_HIST, **hyper)
+            hrec = list(RECORD)
         finally:
             sys.stdout.close()
             sys.stdout = _stdout
         assert len(rec) == 3 * G * ns
+        Gh = min(G_HIST, G)
+        assert len(hrec) == 3 * Gh * H_HIST and hist_y.shape == (Gh, H_HIST, M)
+        hl = stack(hrec[0::3], 1)
+        hu = stack(hrec[1::3], T)
+        hy = stack(hrec[2::3], M)
+        out.update(
+            map_percentiles=map_pct.numpy(), map_Lvecs=map_Lvecs.numpy(), hist_pars=hist, hist_n_sample=H_HIST,
+            hist_grids=grids[:G_HIST].numpy(), hist_y=hist_y,
+            hist_l_loc=hl[0].reshape(Gh, H_HIST), hist_l_scale=hl[1].reshape(Gh, H_HIST), hist_l_draw=hl[2].reshape(Gh, H_HIST),
+            hist_u_loc=hu[0].reshape(Gh, H_HIST, T), hist_u_scale=hu[1].reshape(Gh, H_HIST, T),
+            hist_u_draw=hu[2].reshape(Gh, H_HIST, T),
+            hist_y_loc=hy[0].reshape(Gh, H_HIST, M), hist_y_scale=hy[1].reshape(Gh, H_HIST, M))
         l_loc, l_scale, l_draw = stack(rec[0::3], 1)
         u_loc, u_scale, u_draw = stack(rec[1::3], T)
         y_loc, y_scale, y_draw = stack(rec[2::3], M)

@@ -95,6 +95,42 @@ def test_reference_signature_reproduces_the_seeded_run(name, cuda_device):
     assert pq.shape == (2, M) and max_rel(pq, g["test_quantiles"][0]) < tol and max_rel(pmean, g["test_mean"][0]) < tol
 
 
+@pytest.mark.parametrize("name", predict_cases())
+def test_plugin_and_history_variants(name, cuda_device):
+    """pointwise_predmap_inhomogeneous (no sampling) and pointwise_predsample_inhomogeneous (one draw per entry of a
+    parameter history, each entry with its own covariance) against the reference's outputs."""
+    from nonstationary_multivariate_gaussian_process_b200 import prediction
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    g = load_predict_golden(name)
+    N, M = g["N"], g["M"]
+    T = M * (M + 1) // 2
+    pars = torch.from_numpy(g["pars"])
+    Y, x = torch.from_numpy(g["Y"]), torch.from_numpy(g["x"])
+    tol = 1e-8 if well_conditioned(name) else 5e-3
+    pct, Lv = prediction.pointwise_predmap_inhomogeneous(pars[:N], pars[N:N + N * T], pars[-1], Y, x,
+                                                         torch.from_numpy(g["grids"]), **g["hyper"])
+    assert tuple(pct.shape) == g["map_percentiles"].shape and tuple(Lv.shape) == g["map_Lvecs"].shape
+    assert max_rel(pct.numpy(), g["map_percentiles"]) < tol and max_rel(Lv.numpy(), g["map_Lvecs"]) < tol
+    p1, L1 = prediction.point_predmap_inhomogeneous(pars[:N], pars[N:N + N * T], pars[-1], Y, x, torch.tensor(g["grids"][1]),
+                                                    **g["hyper"])
+    assert max_rel(p1.numpy(), g["map_percentiles"][1]) < tol and max_rel(L1.numpy(), g["map_Lvecs"][1]) < tol
+    # history variant: moments for exactly the reference's draws (tight), then the seeded end-to-end call
+    hp = torch.from_numpy(g["hist_pars"])
+    H = int(g["hist_n_sample"])
+    hg = torch.from_numpy(g["hist_grids"])
+    plan = LogPosteriorPlan("nonseparable", x.expand(H, -1), Y.expand(H, -1, -1), dict(g["hyper"], a=1, b=1))
+    mu_f, s2_y, info = plan.predict_moments(hp[-H:], hg, torch.from_numpy(g["hist_l_draw"]).t().unsqueeze(2),
+                                            torch.from_numpy(g["hist_u_draw"]).transpose(0, 1).unsqueeze(2), raw_factor=True)
+    plan.close()
+    assert int(info.abs().sum()) == 0
+    assert max_rel(mu_f[:, :, 0].cpu().transpose(0, 1).numpy(), g["hist_y_loc"]) < TOL_MOMENTS
+    assert max_rel(np.sqrt(s2_y[:, :, 0].cpu().transpose(0, 1).numpy()), g["hist_y_scale"]) < TOL_MOMENTS
+    torch.manual_seed(5000 + g["seed"])
+    hy = prediction.pointwise_predsample_inhomogeneous(hp[:, :N], hp[:, N:N + N * T], hp[:, -1], Y, x, hg, N_sample=H,
+                                                       **g["hyper"])
+    assert hy.shape == g["hist_y"].shape and max_rel(hy, g["hist_y"]) < tol
+
+
 def test_batched_subjects_match_single_subject_plans(cuda_device):
     """S = 5 subjects in one plan (several sub-batches of the scratch are NOT forced here; see the next test) against the
     same subjects one by one, and against the CPU oracle's dense formula for a few columns."""

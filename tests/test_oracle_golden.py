@@ -53,3 +53,14 @@ def test_predict_oracle_matches_reference_golden(name):
     from oracle import nmgp_oracle as O
     Ls = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(torch.from_numpy(r["u_draw"]), M), M).numpy()
     assert max_rel(Ls, g["cov"]) < VAL_TOL
+    # plug-in variant (prediction.py:912-1012) and posterior-sample variant (:1265-1378)
+    pct, Lv = PO.pointwise_predict_plugin(*args[1:], **g["hyper"])
+    assert max_rel(pct, g["map_percentiles"]) < VAL_TOL and max_rel(Lv, g["map_Lvecs"]) < VAL_TOL
+    hp = torch.from_numpy(g["hist_pars"])
+    torch.manual_seed(5000 + g["seed"])
+    r = PO.pointwise_predict_history(hp[:, :N], hp[:, N:N + N * T], hp[:, -1], torch.from_numpy(g["Y"]),
+                                     torch.from_numpy(g["x"]), torch.from_numpy(g["hist_grids"]),
+                                     N_sample=int(g["hist_n_sample"]), **g["hyper"])
+    for k in ("l_loc", "l_scale", "l_draw", "u_loc", "u_scale", "u_draw", "y_loc", "y_scale"):
+        assert max_rel(r[k], g["hist_" + k]) < VAL_TOL, (name, "hist_" + k, max_rel(r[k], g["hist_" + k]))
+    assert max_rel(r["y_draw"], g["hist_y"]) < VAL_TOL
