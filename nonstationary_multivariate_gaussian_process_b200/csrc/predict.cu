@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(128) pred_quad_kernel(const double* __restrict
     __syncthreads();
     const double* SA = &As[buf][(m0 + lr) * QLD + lk];
     const double* SB = &Bs[buf][(n0 + lr) * QLD + lk];
+    // a warp whose 32 rows are all padding (N = 100: rows 96..127 of the second row tile) has nothing to add
+    if ((q / nK) * QT + m0 < N)
 #pragma unroll
     for (int ks = 0; ks < QK / 4; ++ks) {
       double a[4], b[4];
