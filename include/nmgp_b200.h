@@ -94,7 +94,8 @@ int nmgp_logpost_grad_profile(nmgp_plan* plan, const double* pars_dev, double* v
 
 /* Factorisation engine selection: 0 = automatic (left-looking accumulate-in-registers path for large batches,
  * right-looking tile tasks otherwise), 1 = force right-looking, 2 = force left-looking, 3 = left-looking with the
- * W^T W inverse also where the Takahashi sweep would be used (<= 16 block columns).  For tests and A/B timing. */
+ * W^T W inverse also where the Takahashi sweep would be used (<= 16 block columns), 4 = automatic potrf with the
+ * level-synchronous recursive triangular inverse + W^T W (the path for a few large matrices).  For tests and A/B timing. */
 int nmgp_plan_set_engine(nmgp_plan* plan, int mode);
 
 /* Number of kernels the plan's last evaluation launched (bench.py's `gpu_launches`). */

@@ -98,7 +98,7 @@ class LogPosteriorPlan:
 
     def set_engine(self, mode: str):
         """'auto' | 'right' (right-looking tile tasks) | 'left' (left-looking / Takahashi): tests and A/B timing."""
-        _lib.check(self.lib.nmgp_plan_set_engine(self._handle, {"auto": 0, "right": 1, "left": 2, "left_stable": 3}[mode]),
+        _lib.check(self.lib.nmgp_plan_set_engine(self._handle, {"auto": 0, "right": 1, "left": 2, "left_stable": 3, "recursive": 4}[mode]),
                    "nmgp_plan_set_engine")
 
     # ------------------------------------------------------------------ evaluation

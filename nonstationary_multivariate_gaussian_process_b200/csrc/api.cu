@@ -416,20 +416,36 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
 
 // Engine selection shared by the evaluation and the prediction path.
 static bool use_left_looking(const nmgp_plan* pl, const BlockBatch& b) {
-  return b.Pbuf != nullptr && (pl->engine_mode == 2 || (pl->engine_mode == 0 && prefer_left_looking(b)));
+  return b.Pbuf != nullptr && (pl->engine_mode == 2 || ((pl->engine_mode == 0 || pl->engine_mode == 4) && prefer_left_looking(b)));
 }
 static int run_potrf(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* launches) {
   return use_left_looking(pl, b) ? engine_potrf_ll(b, st, launches) : engine_potrf(b, st, launches);
 }
-// The Takahashi sweep propagates the error of the trailing inverse block into every new block column, multiplied by
-// |L(B,j) L_jj^-1| -- for smooth GP covariances that factor exceeds 1 and the error grows geometrically with the number
-// of block columns (measured: exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64).  It is therefore used only up to
-// kTakahashiMaxBlocks block columns; beyond, the inverse is formed as W^T W from the triangular inverse (backward
-// stable) on the factor the left-looking potrf produced (same layout).
+// Inverse from the factor.  Three formulations, chosen by regime (measured on B200, profiles/r01_inverse_ab.txt):
+//  * Takahashi sweep (engine_potri_ll): fewest bytes per matrix; best for thousands of mid-size matrices (10 000 x n = 600:
+//    19.5 ms vs 21.2 ms per 3334).  It propagates the error of the trailing inverse block into every new block column,
+//    multiplied by |L(B,j) L_jj^-1| -- for smooth GP covariances that factor exceeds 1 and the error grows geometrically
+//    with the number of block columns (exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64) -- so only up to
+//    kTakahashiMaxBlocks block columns.
+//  * level-synchronous recursive triangular inverse + W^T W (engine_potri_ll_recursive): backward stable, 2 log2(Kt) + 1
+//    launches of independent long-K tiles; everything else (n = 5000 single: 26 TFLOP/s instead of 10.9 for the tile tasks;
+//    n = 16 384: 34 TFLOP/s single and batched).
+//  * right-looking tile tasks (engine_potri): unit entry points without the second matrix buffer, and engine mode 1.
+constexpr int kTakahashiMinBatch = 1024;
 static int run_potri(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* launches) {
   const bool ll = use_left_looking(pl, b);
-  if (ll && b.Kt <= kTakahashiMaxBlocks && !pl->stable_inverse) return engine_potri_ll(b, st, launches);
-  if (ll) return engine_potri_ll_stable(b, st, launches);
+  const bool can_recurse = b.A2 != nullptr && b.Pbuf != nullptr;
+  switch (pl->engine_mode) {
+    case 1: return engine_potri(b, st, launches);
+    case 2:
+      if (!ll) return engine_potri(b, st, launches);
+      if (pl->stable_inverse || b.Kt > kTakahashiMaxBlocks) return engine_potri_ll_stable(b, st, launches);
+      return engine_potri_ll(b, st, launches);
+    case 4: return can_recurse ? engine_potri_ll_recursive(b, st, launches) : engine_potri(b, st, launches);
+    default: break;
+  }
+  if (ll && b.Kt <= kTakahashiMaxBlocks && b.batch >= kTakahashiMinBatch) return engine_potri_ll(b, st, launches);
+  if (can_recurse && b.Kt > 1) return engine_potri_ll_recursive(b, st, launches);
   return engine_potri(b, st, launches);
 }
 
@@ -666,8 +682,8 @@ int nmgp_predict_moments(nmgp_plan* pl, const double* pars, const double* xstar,
 }
 
 int nmgp_plan_set_engine(nmgp_plan* pl, int mode) {
-  if (!pl || mode < 0 || mode > 3) return NMGP_EINVAL;
-  pl->engine_mode = mode == 3 ? 2 : mode;
+  if (!pl || mode < 0 || mode > 4) return NMGP_EINVAL;
+  pl->engine_mode = mode == 3 ? 2 : mode;   // 4: automatic potrf, level-synchronous recursive inverse
   pl->stable_inverse = mode == 3;
   return 0;
 }

@@ -52,6 +52,9 @@ int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches);
 // Same result as engine_potri_ll by W = L^-1 (row-wise, all rows in parallel) and Z = W^T W (all tiles in parallel): three
 // launches, no recursion over block columns, stable for any size.  Requires b.A2 (finite-initialised).
 int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches);
+// Same result with W = L^-1 formed level by level (two launches of independent long-K tiles per level): for a few large
+// matrices.  Accepts the factor of either potrf engine.  Requires b.A2 and b.Pbuf (tensor maps).
+int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launches);
 // largest number of 64-blocks per side for which the Takahashi recursion of engine_potri_ll is used (see api.cu)
 constexpr int kTakahashiMaxBlocks = 16;
 

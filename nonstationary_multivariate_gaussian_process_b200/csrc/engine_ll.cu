@@ -306,10 +306,20 @@ __global__ void __launch_bounds__(THREADS, 4) panel_gemm_kernel(const __grid_con
 //   LAUUM      Z(i,j) = sum_{c>=i} W(c,i)^T W(c,j), i >= j      -> A, both triangles
 // Same ring, same K-major operands, same fragment addressing as panel_gemm_kernel; the tiles of a CTA now have different
 // K lengths, so producer and consumer each walk the (tile, chunk) sequence.
-enum InvMode : int { PANEL_ALL = 0, TRTRI_ROW = 1, LAUUM = 2 };
+//
+// Recursive (level-synchronous) triangular inverse, for a handful of LARGE matrices where one CTA per block row is far too
+// little parallelism:  with L = [[L11, 0], [L21, L22]],  W = [[W11, 0], [-W22 (L21 W11), W22]].  Level s = 1, 2, 4, ...
+// (half-size in blocks) handles ALL pairs of adjacent s-blocks at once in two launches whose tiles are all independent:
+//   REC_T   T(i,j)  = sum_{c=j..e} L(i,c) W(c,j)      i in the pair's second half, j in its first half [.., e]
+//                     -> transposed into the upper tile (j,i) of A            (W(c,j)^T: upper tiles of A2, W_jj^T from Dinv)
+//   REC_W   W(i,j)  = -sum_{c=b..i} W(i,c) T(c,j)     b = first block of the second half
+//                     -> lower tile (i,j) of A (over L21) and transposed -> upper tile (j,i) of A2 (operand of LAUUM)
+// 2 log2(Kt) launches instead of a 3 Kt sweep, every tile a long-K accumulation in registers.
+enum InvMode : int { PANEL_ALL = 0, TRTRI_ROW = 1, LAUUM = 2, REC_T = 3, REC_W = 4 };
 
 struct Tile {
   int i, j, nch;
+  int c0;   // REC_T: first k-block (ascending);  REC_W: first k-block (descending from i)
 };
 
 __device__ __forceinline__ void tri_decode(int t, int& a, int& b) {
@@ -342,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
 
   // tiles of this CTA
   int nmy;
+  const int hs = g.step;                                          // REC_*: half-size of the level, in blocks
   if (MODE == TRTRI_ROW) nmy = Kt - 1 - (int)blockIdx.x;        // CTA bx owns row i = Kt-1-bx (longest rows first)
   else nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   auto tile_at = [&](int tt) -> Tile {
@@ -352,6 +363,18 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
       t.i = a + 1; t.j = b; t.nch = CPB;
     } else if (MODE == TRTRI_ROW) {   // row i, columns descending
       t.i = Kt - 1 - (int)blockIdx.x; t.j = t.i - 1 - tt; t.nch = (t.i - t.j) * CPB;
+    } else if (MODE == REC_T || MODE == REC_W) {
+      // full pairs hold hs x hs tiles; only the last pair can have a shorter (or no) second half
+      const int tl = blockIdx.x + tt * gridDim.x;
+      const int per = hs * hs;
+      const int full = (Kt / (2 * hs)) * per;   // tiles of the complete pairs
+      int pidx, a, b;
+      if (tl < full) { pidx = tl / per; const int rem = tl - pidx * per; a = rem / hs; b = rem - a * hs; }
+      else { pidx = Kt / (2 * hs); const int rem = tl - full; a = rem / hs; b = rem - a * hs; }
+      const int base = pidx * 2 * hs;
+      t.i = base + hs + a; t.j = base + b;
+      if (MODE == REC_T) { t.c0 = t.j; t.nch = (hs - b) * CPB; }          // c = j .. base+hs-1
+      else { t.c0 = t.i; t.nch = (a + 1) * CPB; }                          // c = i .. base+hs (descending)
     } else {                          // lower pairs incl. diagonal; k-blocks c = i .. last, the last one ragged
       tri_decode(blockIdx.x + tt * gridDim.x, t.i, t.j);
       t.nch = (last - t.i) * CPB + ragged_chunks;
@@ -387,6 +410,16 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
         tma_load_chunk(SB, &mapD, kcol, 0, dbase + 2 * t.j + 1, bar);
       } else if (MODE == TRTRI_ROW) {    // W(i,cb) . Lh(cb,j),  cb = i, i-1, .., j+1   (B = upper tile (j,cb) of A)
         const int cb = t.i - kb;
+        if (cb == t.i) tma_load_chunk(SA, &mapD, kcol, 0, dbase + 2 * t.i, bar);
+        else tma_load_chunk(SA, &mapA, cb * NB + kcol, t.i * NB, mat, bar);
+        tma_load_chunk(SB, &mapA, cb * NB + kcol, t.j * NB, mat, bar);
+      } else if (MODE == REC_T) {        // L(i,cb) . W(cb,j),  cb = j, j+1, ..        (B = W(cb,j)^T: upper tile (j,cb) of A2)
+        const int cb = t.c0 + kb;
+        tma_load_chunk(SA, &mapA, cb * NB + kcol, t.i * NB, mat, bar);
+        if (cb == t.j) tma_load_chunk(SB, &mapD, kcol, 0, dbase + 2 * t.j + 1, bar);
+        else tma_load_chunk(SB, &mapA2, cb * NB + kcol, t.j * NB, mat, bar);
+      } else if (MODE == REC_W) {        // W(i,cb) . T(cb,j),  cb = i, i-1, ..        (B = T(cb,j)^T: upper tile (j,cb) of A)
+        const int cb = t.c0 - kb;
         if (cb == t.i) tma_load_chunk(SA, &mapD, kcol, 0, dbase + 2 * t.i, bar);
         else tma_load_chunk(SA, &mapA, cb * NB + kcol, t.i * NB, mat, bar);
         tma_load_chunk(SB, &mapA, cb * NB + kcol, t.j * NB, mat, bar);
@@ -427,8 +460,8 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
         // chunks of the first k-block that only meet structural zeros of the triangular diagonal inverse
         bool zero = false;
         if (qq < CPB) {
-          if (MODE == PANEL_ALL) zero = (n0 == NB / 2 && qq < HALF);                 // W_jj[k][n] = 0 for n > k
-          else if (MODE == TRTRI_ROW) zero = (m0 == 0 && qq >= HALF);                // W_ii[m][k] = 0 for k > m
+          if (MODE == PANEL_ALL || MODE == REC_T) zero = (n0 == NB / 2 && qq < HALF);   // W_jj[k][n] = 0 for n > k
+          else if (MODE == TRTRI_ROW || MODE == REC_W) zero = (m0 == 0 && qq >= HALF);  // W_ii[m][k] = 0 for k > m
           else zero = (m0 == NB / 2 && qq < HALF) || (diag_tile && n0 == NB / 2 && qq < HALF);   // W_ii[k][m] = 0 for m > k
         }
         mbar_wait(&full[slot], (gq / STAGES) & 1);
@@ -448,10 +481,10 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
-            if (MODE == PANEL_ALL) {          // Lh(i,j)^T -> upper tile (j,i) of A
+            if (MODE == PANEL_ALL || MODE == REC_T) {   // Lh(i,j)^T / T(i,j)^T -> upper tile (j,i) of A
               U[(long)col * g.ld + row] = acc[a][b][0];
               U[(long)(col + 1) * g.ld + row] = acc[a][b][1];
-            } else if (MODE == TRTRI_ROW) {   // W(i,j) -> lower tile of A, W(i,j)^T -> upper tile of A2
+            } else if (MODE == TRTRI_ROW || MODE == REC_W) {   // W(i,j) -> lower tile of A, W(i,j)^T -> upper tile of A2
               double2 v; v.x = -acc[a][b][0]; v.y = -acc[a][b][1];
               *reinterpret_cast<double2*>(C + (long)row * g.ld + col) = v;
               U2[(long)col * g.ld + row] = v.x;
@@ -592,11 +625,18 @@ int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
 
 namespace {
 template <int MODE>
-int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launches) {
+int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launches, int hs = 0) {
   if (g0.batch <= 0) return 0;
   LLArgs g = g0;
   const int Kt = g.Kt;
-  const int ntiles = MODE == PANEL_ALL ? Kt * (Kt - 1) / 2 : (MODE == TRTRI_ROW ? Kt - 1 : Kt * (Kt + 1) / 2);
+  int ntiles;
+  if (MODE == REC_T || MODE == REC_W) {   // level of half-size hs: complete pairs + the (shorter) second half of the last one
+    const int full = Kt / (2 * hs), rest = Kt - full * 2 * hs;
+    ntiles = full * hs * hs + (rest > hs ? (rest - hs) * hs : 0);
+    g.step = hs;
+  } else {
+    ntiles = MODE == PANEL_ALL ? Kt * (Kt - 1) / 2 : (MODE == TRTRI_ROW ? Kt - 1 : Kt * (Kt + 1) / 2);
+  }
   if (ntiles <= 0) return 0;
   static bool configured = false;
   if (!configured) {
@@ -629,6 +669,24 @@ int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches)
   LLArgs g = make_ll(b);
   NMGP_TRY(launch_inv<PANEL_ALL>(*ms, g, st, launches));
   NMGP_TRY(launch_inv<TRTRI_ROW>(*ms, g, st, launches));
+  NMGP_TRY(launch_inv<LAUUM>(*ms, g, st, launches));
+  return 0;
+}
+
+// Same result with the triangular inverse formed level by level (REC_T / REC_W, 2 log2(Kt) launches of independent
+// long-K tiles) instead of row by row: the path for a few large matrices (n = 5000 ... 16 384 with batch < 8), where one
+// CTA per block row leaves most of the GPU idle.  Works on the factor of either potrf engine (needs L in the lower tiles of
+// A and W_kk / W_kk^T in Dinv); uses the upper tiles of A as scratch and A2 for the transposed inverse.
+int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (b.batch <= 0) return 0;
+  if (!b.A2 || !b.Pbuf) { set_last_error("engine_potri_ll_recursive: no second matrix buffer"); return -1; }
+  const MapSet* ms = nullptr;
+  NMGP_TRY(get_maps(b, &ms));
+  LLArgs g = make_ll(b);
+  for (int hs = 1; hs < b.Kt; hs *= 2) {
+    NMGP_TRY(launch_inv<REC_T>(*ms, g, st, launches, hs));
+    NMGP_TRY(launch_inv<REC_W>(*ms, g, st, launches, hs));
+  }
   NMGP_TRY(launch_inv<LAUUM>(*ms, g, st, launches));
   return 0;
 }

@@ -73,13 +73,14 @@ def test_left_and_right_looking_engines_agree(N, M, S, cuda_device):
     plan = LogPosteriorPlan("nonseparable", np.stack(xs), np.stack(Ys), hyper)
     p = torch.from_numpy(np.stack(ps)).cuda()
     res = {}
-    for mode in ("right", "left"):
+    for mode in ("right", "left", "left_stable", "recursive"):
         plan.set_engine(mode)
         v, g, i = plan.value_and_grad(p)
         torch.cuda.synchronize()
         assert int(i.abs().sum()) == 0
         res[mode] = (v.cpu().numpy(), g.cpu().numpy())
-    dv = np.abs(res["left"][0][:, 1] - res["right"][0][:, 1]) / np.abs(res["right"][0][:, 1])
-    dg = np.linalg.norm(res["left"][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
-    assert dv.max() < 1e-12, dv
-    assert dg.max() < 1e-11, dg
+    for mode in ("left", "left_stable", "recursive"):
+        dv = np.abs(res[mode][0][:, 1] - res["right"][0][:, 1]) / np.abs(res["right"][0][:, 1])
+        dg = np.linalg.norm(res[mode][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
+        assert dv.max() < 1e-12, (mode, dv)
+        assert dg.max() < 1e-11, (mode, dg)

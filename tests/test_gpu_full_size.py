@@ -119,16 +119,17 @@ def test_batched_engine_is_stable_at_large_block_counts(N, M, S, cuda_device):
     subs = [_subject(N, M, 500 + s) for s in range(S)]
     xs, Ys, ps = (np.stack(a) for a in zip(*subs))
     res = {}
-    for mode in ("right", "left"):
+    for mode in ("right", "left", "recursive"):
         plan = LogPosteriorPlan("nonseparable", xs, Ys, HYPER, prior=False)
         plan.set_engine(mode)
         v, g, i = plan.value_and_grad(torch.from_numpy(ps).cuda())
         assert int(i.abs().sum()) == 0
         res[mode] = (v.cpu().numpy(), g.cpu().numpy())
         plan.close()
-    dv = np.abs(res["left"][0][:, 1] - res["right"][0][:, 1]) / np.abs(res["right"][0][:, 1])
-    dg = np.linalg.norm(res["left"][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
-    assert dv.max() < 1e-10, dv
-    assert dg.max() < 1e-8, dg
+    for mode in ("left", "recursive"):
+        dv = np.abs(res[mode][0][:, 1] - res["right"][0][:, 1]) / np.abs(res["right"][0][:, 1])
+        dg = np.linalg.norm(res[mode][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
+        assert dv.max() < 1e-10, (mode, dv)
+        assert dg.max() < 1e-8, (mode, dg)
     ref = _library_loglik(xs[0], ps[0], Ys[0], N, M)
     assert abs(res["left"][0][0, 1] - ref) / abs(ref) < 1e-10

@@ -32,8 +32,9 @@ def run_plan(g, engine="auto"):
 
 # "auto" picks the right-looking tile engine for a single subject; "left" forces the batched left-looking potrf with the
 # Takahashi inverse sweep (<= 16 block columns) that the 10 000-subject sweep uses; "left_stable" the left-looking potrf
-# with the W^T W inverse (PANEL_ALL / TRTRI_ROW / LAUUM) that larger matrices get.
-@pytest.mark.parametrize("engine", ["auto", "left", "left_stable"])
+# with the W^T W inverse (PANEL_ALL / TRTRI_ROW / LAUUM) that larger matrices get; "recursive" the automatic potrf with the
+# level-synchronous recursive triangular inverse (REC_T / REC_W / LAUUM) that a few large matrices get.
+@pytest.mark.parametrize("engine", ["auto", "left", "left_stable", "recursive"])
 @pytest.mark.parametrize("name", golden_cases())
 def test_cuda_matches_reference_golden(name, engine, cuda_device):
     g = load_golden(name)
