@@ -139,6 +139,21 @@ int nmgp_adam_step(double* pars_dev, const double* grad_dev, double* m_dev, doub
  *     info [S] (may be NULL)  as in nmgp_logpost_grad
  *   Sigma is built, factored and inverted ONCE per subject by the hot-path engine (the reference repeats an n x n
  *   `symeig` + `cholesky` per x* and per sample); see csrc/predict.cu for the sample-dependent part. */
+/* The separable model's predictors (prediction.py:34-460) condition tilde_l and tilde_sigma the same way:
+ * nmgp_predict_prior_moments on a separable plan returns, in the same four buffers, the moments of tilde_l ([S,G], [S,G]) and
+ * of tilde_sigma ([S,G,1], [S,G]).
+ *
+ * nmgp_predict_moments_sep  (separable: prediction.py:82-118, 226-266, 372-398; stationary: prediction.py:1587-1596):
+ *     tl_star, ts_star [S,G,n_sample]   tilde_l* and tilde_sigma* at every (new input, sample); the stationary model and the
+ *                                       plug-in predictors pass their fixed values
+ *     mu_f [S,G,n_sample,M]             k_f^T Sigma^-1 y with k_f = B (x) k_x
+ *     quad [S,G,n_sample,M]             diag(k_f^T Sigma^-1 k_f); the caller forms sigma2_y = a2 - quad + sigma2_err with the
+ *                                       variant's own a2 (prediction.py:103 vs :254) and clipping rule
+ *   Sigma = B (x) K_x + sigma2 I is never formed: B = V diag(lam) V^T gives M independent N x N problems
+ *   S_m = lam_m K_x + sigma2 I, factored and inverted once per subject by the hot-path engine. */
+int nmgp_predict_moments_sep(nmgp_plan* plan, const double* pars_dev, const double* xstar_dev, int G, int n_sample,
+                             const double* tl_star_dev, const double* ts_star_dev, double* mu_f_dev, double* quad_dev,
+                             int* info_dev, void* stream);
 int nmgp_predict_prior_moments(nmgp_plan* plan, const double* pars_dev, const double* xstar_dev, int G, double* mu_l_dev,
                                double* s2_l_dev, double* mu_uL_dev, double* s2_uL_dev, void* stream);
 #define NMGP_PRED_RAW_FACTOR 1

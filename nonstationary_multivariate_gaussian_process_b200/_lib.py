@@ -107,6 +107,8 @@ def _declare(lib):
     lib.nmgp_predict_prior_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, dp, dp, dp, dp, vp]
     lib.nmgp_predict_moments.restype = c.c_int
     lib.nmgp_predict_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, c.c_int, dp, dp, c.c_int, dp, dp, ip, vp]
+    lib.nmgp_predict_moments_sep.restype = c.c_int
+    lib.nmgp_predict_moments_sep.argtypes = [c.c_void_p, dp, dp, c.c_int, c.c_int, dp, dp, dp, dp, ip, vp]
     lib.nmgp_rbf_cov.restype = c.c_int
     lib.nmgp_rbf_cov.argtypes = [dp, c.c_int, dp, c.c_int, c.c_double, c.c_double, dp, vp]
     lib.nmgp_gibbs_cov.restype = c.c_int
@@ -122,7 +124,7 @@ def _declare(lib):
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
-           "nmgp_plan_block", "nmgp_adam_step", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
+           "nmgp_plan_block", "nmgp_adam_step", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 
 

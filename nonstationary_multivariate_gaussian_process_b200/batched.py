@@ -222,14 +222,15 @@ class LogPosteriorPlan:
         return xs.contiguous()
 
     def predict_prior_moments(self, pars, xstar):
-        """Conditional moments of the two GP priors at new inputs (Utility/prediction.py:1060-1092).
-        pars [S,P], xstar [G] or [S,G] -> (mu_l [S,G], s2_l [S,G], mu_uL [S,G,T], s2_uL [S,G]), CUDA tensors."""
+        """Conditional moments of the two GP priors at new inputs (Utility/prediction.py:1060-1092; separable model: :53-69).
+        pars [S,P], xstar [G] or [S,G] -> (mu_l [S,G], s2_l [S,G], mu_uL [S,G,T], s2_uL [S,G]), CUDA tensors; for a
+        separable plan the second pair is the conditional of tilde_sigma ([S,G,1], [S,G])."""
         torch = _lib.require_cuda()
-        if self.model != "nonseparable":
-            raise ValueError("prediction is implemented for the nonseparable model")
+        if self.model == "stationary":
+            raise ValueError("the stationary model has no GP priors to condition")
         p = torch.as_tensor(pars, dtype=torch.float64).detach().to(self.device).reshape(self.S, self.P).contiguous()
         xs = self._xstar(xstar)
-        G, T = int(xs.shape[1]), self.M * (self.M + 1) // 2
+        G, T = int(xs.shape[1]), (self.M * (self.M + 1) // 2 if self.model == "nonseparable" else 1)
         kw = dict(dtype=torch.float64, device=self.device)
         mu_l, s2_l = torch.empty((self.S, G), **kw), torch.empty((self.S, G), **kw)
         mu_u, s2_u = torch.empty((self.S, G, T), **kw), torch.empty((self.S, G), **kw)
@@ -266,6 +267,30 @@ class LogPosteriorPlan:
                                                ctypes.c_void_p(stream))
         _lib.check(rc, "nmgp_predict_moments")
         return mu_f, s2_y, info
+
+    def predict_moments_sep(self, pars, xstar, tl_star, ts_star):
+        """Separable / stationary predictive moments (Utility/prediction.py:82-118, 226-266, 372-398, 1587-1596).
+        pars [S,P], xstar [G] or [S,G], tl_star / ts_star [S,G,ns] (tilde_l*, tilde_sigma* per new input and sample) ->
+        (mu_f [S,G,ns,M] = k_f^T Sigma^-1 y, quad [S,G,ns,M] = diag(k_f^T Sigma^-1 k_f), info [S]), CUDA tensors."""
+        torch = _lib.require_cuda()
+        if self.model == "nonseparable":
+            raise ValueError("use predict_moments for the nonseparable model")
+        p = torch.as_tensor(pars, dtype=torch.float64).detach().to(self.device).reshape(self.S, self.P).contiguous()
+        xs = self._xstar(xstar)
+        G = int(xs.shape[1])
+        tl = torch.as_tensor(tl_star, dtype=torch.float64).to(self.device).reshape(self.S, G, -1).contiguous()
+        ns = int(tl.shape[2])
+        ts = torch.as_tensor(ts_star, dtype=torch.float64).to(self.device).reshape(self.S, G, ns).contiguous()
+        kw = dict(dtype=torch.float64, device=self.device)
+        mu_f, quad = torch.empty((self.S, G, ns, self.M), **kw), torch.empty((self.S, G, ns, self.M), **kw)
+        info = torch.zeros((self.S,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_predict_moments_sep(self._handle, p.data_ptr(), xs.data_ptr(), G, ns, tl.data_ptr(),
+                                                   ts.data_ptr(), mu_f.data_ptr(), quad.data_ptr(), info.data_ptr(),
+                                                   ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_predict_moments_sep")
+        return mu_f, quad, info
 
     def close(self):
         if getattr(self, "_handle", None) is not None and self._handle.value:

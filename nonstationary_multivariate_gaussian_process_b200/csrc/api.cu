@@ -614,24 +614,32 @@ static int ensure_pred_scratch(nmgp_plan* pl, size_t per_subject, int cs) {
 
 int nmgp_predict_prior_moments(nmgp_plan* pl, const double* pars, const double* xstar, int G, double* mu_l, double* s2_l,
                                double* mu_uL, double* s2_uL, void* stream) {
-  if (!pl || pl->model != NMGP_NONSEPARABLE || G < 0 || (pl->S > 0 && G > 0 && (!pars || !xstar || !mu_l || !s2_l || !mu_uL || !s2_uL))) {
-    set_last_error("nmgp_predict_prior_moments: needs a nonseparable plan and non-null buffers");
+  if (!pl || pl->nprior != 2 || G < 0 || (pl->S > 0 && G > 0 && (!pars || !xstar || !mu_l || !s2_l || !mu_uL || !s2_uL))) {
+    set_last_error("nmgp_predict_prior_moments: needs a separable or nonseparable plan and non-null buffers");
     return NMGP_EINVAL;
   }
   if (pl->S == 0 || G == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int N = pl->N, M = pl->M, P = pl->P, T = pl->T;
+  const int N = pl->N, M = pl->M, P = pl->P, nv1 = pl->nv1;
   long launches = 0;
   const size_t per = predict_prior_scratch_per_subject(N, G);
   NMGP_TRY(ensure_pred_scratch(pl, per, pl->chunk));
   const long SB = (long)(pl->pred_scratch_doubles / per);
   for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
     const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
-    NMGP_TRY(launch_svc_prep(cs, N, M, pars + (size_t)s0 * P, P, pl->hc, pl->w, st, &launches));
+    const double* ps = pars + (size_t)s0 * P;
+    if (pl->model == NMGP_NONSEPARABLE) {
+      NMGP_TRY(launch_svc_prep(cs, N, M, ps, P, pl->hc, pl->w, st, &launches));
+    } else {   // the separable prep also rotates the observations; only its residuals R0 / R1 are used here
+      BlockBatch b = pl->bb;
+      b.batch = cs * pl->nmat;
+      NMGP_TRY(sep_forward(pl->model, cs, N, M, pl->x + (size_t)s0 * N, pl->Y + (size_t)s0 * N * M, ps, P, pl->hc, pl->w, b, st,
+                           &launches));
+    }
     const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
     const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
     NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
-    NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, T, 0, st, &launches));
+    NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, nv1, 0, st, &launches));
     for (int c0 = 0; c0 < cs; c0 += (int)SB) {
       const int sb = cs - c0 < SB ? cs - c0 : (int)SB;
       const size_t g0 = (size_t)(s0 + c0);
@@ -639,10 +647,43 @@ int nmgp_predict_prior_moments(nmgp_plan* pl, const double* pars, const double* 
       const double* xq = xstar + g0 * G;
       NMGP_TRY(launch_predict_prior(xs, L0 + (size_t)c0 * N * N, pl->w.Z0 + (size_t)c0 * N, sb, N, 1, xq, G, pl->hyper[1],
                                     pl->hyper[2], pl->hyper[0], pl->pred_scratch, mu_l + g0 * G, s2_l + g0 * G, st, &launches));
-      NMGP_TRY(launch_predict_prior(xs, L1 + (size_t)c0 * N * N, pl->w.Z1 + (size_t)c0 * N * T, sb, N, T, xq, G, pl->hyper[4],
-                                    pl->hyper[5], pl->hyper[3], pl->pred_scratch, mu_uL + g0 * G * T, s2_uL + g0 * G, st,
-                                    &launches));
+      NMGP_TRY(launch_predict_prior(xs, L1 + (size_t)c0 * N * N, pl->w.Z1 + (size_t)c0 * N * nv1, sb, N, nv1, xq, G,
+                                    pl->hyper[4], pl->hyper[5], pl->hyper[3], pl->pred_scratch, mu_uL + g0 * G * nv1,
+                                    s2_uL + g0 * G, st, &launches));
     }
+  }
+  pl->last_launches = launches;
+  return 0;
+}
+
+int nmgp_predict_moments_sep(nmgp_plan* pl, const double* pars, const double* xstar, int G, int n_sample,
+                             const double* tl_star, const double* ts_star, double* mu_f, double* quad, int* info,
+                             void* stream) {
+  if (!pl || pl->model == NMGP_NONSEPARABLE || G < 0 || n_sample < 0 ||
+      (pl->S > 0 && G > 0 && n_sample > 0 && (!pars || !xstar || !tl_star || !ts_star || !mu_f || !quad))) {
+    set_last_error("nmgp_predict_moments_sep: needs a stationary or separable plan and non-null buffers");
+    return NMGP_EINVAL;
+  }
+  if (pl->S == 0 || G == 0 || n_sample == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl->N, M = pl->M, P = pl->P;
+  const size_t C = (size_t)G * n_sample;
+  long launches = 0;
+  const size_t per = predict_sep_scratch_per_subject(N, M, (long)C);
+  NMGP_TRY(ensure_pred_scratch(pl, per, pl->chunk));
+  for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
+    const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
+    BlockBatch b = pl->bb;
+    b.batch = cs * pl->nmat;
+    const double* xs = pl->x + (size_t)s0 * N;
+    NMGP_TRY(sep_forward(pl->model, cs, N, M, xs, pl->Y + (size_t)s0 * N * M, pars + (size_t)s0 * P, P, pl->hc, pl->w, b, st,
+                         &launches));
+    NMGP_TRY(run_potrf(pl, b, st, &launches));
+    NMGP_TRY(run_potri(pl, b, st, &launches));
+    if (info) NMGP_TRY(launch_reduce_info(b.info, cs, M, info + s0, st, &launches));
+    NMGP_TRY(predict_moments_sep_chunk(cs, N, M, xs, pl->w, b, xstar + (size_t)s0 * G, tl_star + (size_t)s0 * C,
+                                       ts_star + (size_t)s0 * C, G, n_sample, pl->pred_scratch, pl->pred_scratch_doubles,
+                                       mu_f + (size_t)s0 * C * M, quad + (size_t)s0 * C * M, st, &launches));
   }
   pl->last_launches = launches;
   return 0;

@@ -1034,6 +1034,23 @@ int launch_nonseparable_cov_reference_order(const double* x, const double* pars,
   return 0;
 }
 
+namespace {
+__global__ void reduce_info_kernel(const int* __restrict__ in, int cs, int nmat, int* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cs) return;
+  int f = 0;
+  for (int m = 0; m < nmat && f == 0; ++m) f = in[c * nmat + m];
+  out[c] = f;
+}
+}  // namespace
+
+int launch_reduce_info(const int* info_mat, int cs, int nmat, int* info_out, cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  reduce_info_kernel<<<(cs + 127) / 128, 128, 0, st>>>(info_mat, cs, nmat, info_out);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_svc_prep(int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w, cudaStream_t st,
                     long* launches) {
   if (cs <= 0) return 0;

@@ -76,6 +76,7 @@ int launch_nonseparable_cov_reference_order(const double* x, const double* pars,
 // pieces of the nonseparable pass used on their own by the prediction path
 int launch_svc_prep(int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w, cudaStream_t st,
                     long* launches);   // pars -> ell, Lst, s2, prior residuals R0 / R1
+int launch_reduce_info(const int* info_mat, int cs, int nmat, int* info_out, cudaStream_t st, long* launches);
 int launch_symv(const BlockBatch& b, int n, const double* y, double* alpha, int batch, cudaStream_t st, long* launches);
 
 // ---- posterior prediction, nonseparable model (Utility/prediction.py:1038-1262; predict.cu)
@@ -91,6 +92,15 @@ int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y
                           const double* xstar, const double* tl_star, const double* uL_star, int G, int ns,
                           int raw_factor, double* scratch, size_t scratch_doubles, double* mu_f, double* s2y,
                           cudaStream_t st, long* launches);
+
+// separable / stationary models (prediction.py:34-460, 1566-1692): after sep_forward + factorisation + inverse of the chunk's
+// M matrices per subject; tl_star / ts_star [cs][G*ns] are the (sampled or plugged-in) tilde_l* / tilde_sigma*; returns
+// mu_f = k_f^T Sigma^-1 y and quad = diag(k_f^T Sigma^-1 k_f), both [cs][G*ns][M]
+size_t predict_sep_scratch_per_subject(int N, int M, long C);
+int predict_moments_sep_chunk(int cs, int N, int M, const double* x, const Scratch& w, const BlockBatch& b,
+                              const double* xstar, const double* tl_star, const double* ts_star, int G, int ns,
+                              double* scratch, size_t scratch_doubles, double* mu_f, double* quad, cudaStream_t st,
+                              long* launches);
 
 // ---- separable / stationary models (Utility/logpos.py:237-296, 405-462)
 int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,

@@ -128,8 +128,10 @@ __global__ void __launch_bounds__(128) pred_h_kernel(const double* __restrict__ 
 
 // KXT[cc][col][j] = Gibbs(x_j, x*_g; l_j, l*_col) (no jitter: cross-covariance, kernels.py:62-63), col = g * ns + s;
 // zero for padded j / col.
+// Separable / stationary models: sig != NULL, the pair carries sigma_j * exp(tilde_sigma*_col) (kernels.py:71).
 __global__ void __launch_bounds__(128) pred_kx_kernel(const double* __restrict__ x, const double* __restrict__ ell,
-                                                      const double* __restrict__ xstar, const double* __restrict__ tl_star,
+                                                      const double* __restrict__ sig, const double* __restrict__ xstar,
+                                                      const double* __restrict__ tl_star, const double* __restrict__ ts_star,
                                                       int N, int Npad, int G, int ns, int C, int c0,
                                                       double* __restrict__ KXT, long kx_stride) {
   const int col = blockIdx.x;
@@ -139,8 +141,9 @@ __global__ void __launch_bounds__(128) pred_kx_kernel(const double* __restrict__
   double v = 0.0;
   if (j < N && col < C) {
     const double ls = exp(tl_star[(long)c * C + col]);
+    const double sij = sig ? __dmul_rn(sig[(long)c * N + j], exp(ts_star[(long)c * C + col])) : 1.0;
     double cf;
-    gibbs_pair(x[(long)c * N + j], xstar[(long)c * G + col / ns], ell[(long)c * N + j], ls, 1.0, v, cf);
+    gibbs_pair(x[(long)c * N + j], xstar[(long)c * G + col / ns], ell[(long)c * N + j], ls, sij, v, cf);
   }
   KXT[(long)cc * kx_stride + (long)col * Npad + j] = v;
 }
@@ -295,6 +298,60 @@ __global__ void __launch_bounds__(128) pred_finish_kernel(const double* __restri
   s2y[((long)c * C + col) * M + mp] = v;
 }
 
+// ------------------------------------------------------------------------------------------------ separable / stationary
+// The M inverses S_m^-1 = (lam_m Kx + sigma2 I)^-1 of a subject out of the engine's padded layout into the table layout of
+// pred_quad_kernel ([M][Ni64][Npad], zero padded).
+__global__ void __launch_bounds__(128) pred_copy_inv_kernel(const double* __restrict__ A, long strideA, int ld, int N,
+                                                            int M, int Ni64, int Npad, int c0,
+                                                            double* __restrict__ Hm, long hm_stride) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int i = blockIdx.y / M, m = blockIdx.y % M;
+  const int cc = blockIdx.z, c = c0 + cc;
+  if (j >= Npad) return;
+  const double v = (i < N && j < N) ? A[((long)c * M + m) * strideA + (long)i * ld + j] : 0.0;
+  Hm[(long)cc * hm_stride + ((long)m * Ni64 + i) * Npad + j] = v;
+}
+
+// One warp per column: q1[m] = kx . alpha_m, q2[m] = kx^T S_m^-1 kx (from pred_quad_kernel); lanes m' < M then form
+//   mu_f[m'] = sum_m lam_m V[m'][m] q1[m],   quad[m'] = sum_m (lam_m V[m'][m])^2 q2[m]
+// (k_f = B (x) k_x, Sigma^-1 = sum_m v_m v_m^T (x) S_m^-1: prediction.py:95-110, 241-262, 1591-1596 in block form).
+__global__ void __launch_bounds__(128) pred_finish_sep_kernel(const double* __restrict__ KXT, long kx_stride, int Npad,
+                                                              const double* __restrict__ alpha,
+                                                              const double* __restrict__ lam, const double* __restrict__ Vec,
+                                                              const double* __restrict__ Q, int Cpad, int N, int M, int C,
+                                                              int c0, double* __restrict__ mu_f, double* __restrict__ quad) {
+  const int col = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int cc = blockIdx.y, c = c0 + cc;
+  if (col >= C) return;
+  const double* kx = KXT + (long)cc * kx_stride + (long)col * Npad;
+  const double* al = alpha + (long)c * M * N;
+  double q1[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) q1[m] = 0.0;
+  for (int j = lane; j < N; j += 32) {
+    const double kv = kx[j];
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+      if (m < M) q1[m] += kv * al[(long)m * N + j];
+  }
+#pragma unroll
+  for (int m = 0; m < 16; ++m)
+    if (m < M) q1[m] = warp_sum(q1[m]);
+  if (lane >= M) return;
+  const int mp = lane;
+  double mu = 0.0, qd = 0.0;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    if (m >= M) continue;
+    const double f = lam[(long)c * M + m] * Vec[(long)c * M * M + mp * M + m];
+    mu += f * q1[m];
+    qd += f * f * Q[((long)cc * M + m) * Cpad + col];
+  }
+  mu_f[((long)c * C + col) * M + mp] = mu;
+  quad[((long)c * C + col) * M + mp] = qd;
+}
+
 }  // namespace
 
 // =================================================================================================== host side
@@ -367,7 +424,8 @@ int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y
     pred_h_kernel<<<gh, 128, 0, st>>>(b.A, b.strideA(), b.nP, w.Lst, N, M, MT, pl.Ni64, pl.Npad, c0, Hm, (long)pl.hm);
     NMGP_LAUNCH_CHECK();
     dim3 gk(pl.Cpad, (pl.Npad + 127) / 128, sb);
-    pred_kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, xstar, tl_star, N, pl.Npad, G, ns, (int)C, c0, KXT, (long)pl.kx);
+    pred_kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, nullptr, xstar, tl_star, nullptr, N, pl.Npad, G, ns, (int)C, c0, KXT,
+                                       (long)pl.kx);
     NMGP_LAUNCH_CHECK();
     dim3 gq(pl.Cpad / QT, pl.T, sb);
     pred_quad_kernel<<<gq, 128, 0, st>>>(Hm, (long)pl.hm, pl.Ni64, pl.Npad, KXT, (long)pl.kx, pl.Cpad, Qb, pl.T, N);
@@ -378,6 +436,52 @@ int predict_moments_chunk(int cs, int N, int M, const double* x, const double* Y
     NMGP_LAUNCH_CHECK();
   }
   return 0;
+}
+
+int predict_moments_sep_chunk(int cs, int N, int M, const double* x, const Scratch& w, const BlockBatch& b,
+                              const double* xstar, const double* tl_star, const double* ts_star, int G, int ns,
+                              double* scratch, size_t scratch_doubles, double* mu_f, double* quad, cudaStream_t st,
+                              long* launches) {
+  if (cs <= 0 || G <= 0 || ns <= 0) return 0;
+  const long C = (long)G * ns;
+  if (C > 0x7fffffffL / 2) { set_last_error("predict: too many (grid point, sample) columns"); return -1; }
+  PredLayout pl = pred_layout(N, M, C);
+  pl.T = M;                                  // M tables (one inverse per eigen-direction of B) instead of M(M+1)/2
+  pl.hm = (size_t)M * pl.Ni64 * pl.Npad;
+  pl.q = (size_t)M * pl.Cpad;
+  if ((long)pl.Ni64 * M > 65535) { set_last_error("predict: N * M too large for the table kernel's grid"); return -1; }
+  long SB = (long)(scratch_doubles / pl.per_subject());
+  if (SB < 1) { set_last_error("predict: scratch smaller than one subject"); return -3; }
+  if (SB > cs) SB = cs;
+  if (SB > 65535) SB = 65535;
+  // alpha_m = S_m^-1 (Y v_m) for the whole chunk (w.yv holds the rotated observations)
+  NMGP_TRY(launch_symv(b, N, w.yv, w.alpha, cs * M, st, launches));
+  for (int c0 = 0; c0 < cs; c0 += (int)SB) {
+    const int sb = cs - c0 < SB ? cs - c0 : (int)SB;
+    double* Hm = scratch;
+    double* KXT = Hm + (size_t)sb * pl.hm;
+    double* Qb = KXT + (size_t)sb * pl.kx;
+    dim3 gh((pl.Npad + 127) / 128, pl.Ni64 * M, sb);
+    pred_copy_inv_kernel<<<gh, 128, 0, st>>>(b.A, b.strideA(), b.nP, N, M, pl.Ni64, pl.Npad, c0, Hm, (long)pl.hm);
+    NMGP_LAUNCH_CHECK();
+    dim3 gk(pl.Cpad, (pl.Npad + 127) / 128, sb);
+    pred_kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, w.sig, xstar, tl_star, ts_star, N, pl.Npad, G, ns, (int)C, c0, KXT,
+                                       (long)pl.kx);
+    NMGP_LAUNCH_CHECK();
+    dim3 gq(pl.Cpad / QT, M, sb);
+    pred_quad_kernel<<<gq, 128, 0, st>>>(Hm, (long)pl.hm, pl.Ni64, pl.Npad, KXT, (long)pl.kx, pl.Cpad, Qb, M, N);
+    NMGP_LAUNCH_CHECK();
+    dim3 gf((unsigned)((C + 3) / 4), sb);
+    pred_finish_sep_kernel<<<gf, 128, 0, st>>>(KXT, (long)pl.kx, pl.Npad, w.alpha, w.lam, w.Vec, Qb, pl.Cpad, N, M, (int)C,
+                                               c0, mu_f, quad);
+    NMGP_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+size_t predict_sep_scratch_per_subject(int N, int M, long C) {
+  PredLayout pl = pred_layout(N, M, C);
+  return (size_t)M * pl.Ni64 * pl.Npad + pl.kx + (size_t)M * pl.Cpad;
 }
 
 }  // namespace nmgp

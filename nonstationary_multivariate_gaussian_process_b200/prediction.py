@@ -7,6 +7,11 @@
     point_/pointwise_/test_predmap_inhomogeneous      (plug-in of the conditional means, no sampling)               :912-1036
     point_/pointwise_/test_predsample_inhomogeneous   (one draw per posterior sample of an HMC history)             :1265-1400
 
+and of the separable and stationary models (block form of the Kronecker covariance, `nmgp_predict_moments_sep`):
+
+    point_/pointwise_/test_predmap, ..._predmap_sampling, ..._predsample                                            :34-459
+    pointwise_predmap_S, test_predmap_S, pointwise_predsample_S, test_predsample_S                                  :1566-1692
+
 (callers: Nonseparable_Model/Nonseparable_model.py:377, 387, 399 with n_sample = 100 and 201 grid points.)
 
 What runs where.  The reference draws, per new input and per sample, tilde_l* and uL* from the GP priors conditioned on
@@ -22,7 +27,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib, logpos, utils
+from . import _lib, logpos, settings, utils
 
 
 def _plan_and_pars(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L,
@@ -176,21 +181,7 @@ _HIST_PLANS = {}
 
 
 def _history_plan(H, Y, x, hyper):
-    """One plan whose H 'subjects' are the same data under H different parameter vectors (an HMC history)."""
-    torch = _lib.require_cuda()
-    from .batched import LogPosteriorPlan
-    Y = torch.as_tensor(Y, dtype=torch.float64)
-    x = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
-    key = (H, logpos._fingerprint(Y), logpos._fingerprint(x), tuple(sorted((k, float(v)) for k, v in hyper.items())),
-           torch.cuda.current_device())
-    plan = _HIST_PLANS.get(key)
-    if plan is None:
-        for old in _HIST_PLANS.values():
-            old.close()
-        _HIST_PLANS.clear()
-        plan = LogPosteriorPlan("nonseparable", x.unsqueeze(0).expand(H, -1), Y.unsqueeze(0).expand(H, -1, -1), hyper)
-        _HIST_PLANS[key] = plan
-    return plan
+    return _replicated_plan("nonseparable", H, Y, x, hyper)
 
 
 def pointwise_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l,
@@ -253,3 +244,264 @@ def test_predsample_inhomogeneous(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_h
 
 
 test_predsample_inhomogeneous.__test__ = False
+
+
+# ===================================================================================== separable model (prediction.py:34-459)
+def _B_diag(uL_vec, M):
+    """diag(L L^T) for the unconstrained triangle(s) uL_vec [..., T]  (prediction.py:87-88)."""
+    torch = _lib.require_cuda()
+    uL = torch.as_tensor(uL_vec, dtype=torch.float64)
+    Lv = utils.uLvec2Lvec(uL.reshape(-1, uL.shape[-1]), M)
+    idx = torch.tril_indices(M, M)
+    L = torch.zeros((Lv.shape[0], M, M), dtype=torch.float64)
+    L[:, idx[0], idx[1]] = Lv
+    return torch.diagonal(L @ L.transpose(1, 2), dim1=1, dim2=2).reshape(*uL.shape[:-1], M)
+
+
+def _sep_hyper(mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, kwargs):
+    return dict(mu_tilde_l=mu_tilde_l, alpha_tilde_l=alpha_tilde_l, beta_tilde_l=beta_tilde_l, mu_tilde_sigma=mu_tilde_sigma,
+                alpha_tilde_sigma=alpha_tilde_sigma, beta_tilde_sigma=beta_tilde_sigma, a=kwargs.get("a", 1),
+                b=kwargs.get("b", 1), c=kwargs.get("c", 10))
+
+
+def _sep_plan_and_pars(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, hyper):
+    torch = _lib.require_cuda()
+    plan = logpos._get_plan("separable", Y, x, hyper, True)
+    f64 = torch.float64
+    pars = torch.cat([torch.as_tensor(tilde_l, dtype=f64).reshape(-1), torch.as_tensor(tilde_sigma, dtype=f64).reshape(-1),
+                      torch.as_tensor(uL_vec, dtype=f64).reshape(-1),
+                      torch.as_tensor(tilde_sigma2_err, dtype=f64).reshape(1)]).detach()
+    return plan, pars
+
+
+def _check_info(info):
+    if int(info.abs().sum()) != 0:
+        raise _lib.NmgpError("prediction: a covariance is not positive definite")
+
+
+def pointwise_predmap(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                      mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """Plug-in prediction of the separable model (prediction.py:337-430): tensor [G,3,M] = mu_f -/+ 1.96 sd."""
+    torch = _lib.require_cuda()
+    hyper = _sep_hyper(mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, kwargs)
+    plan, pars = _sep_plan_and_pars(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, hyper)
+    g = torch.as_tensor(grids, dtype=torch.float64).reshape(-1)
+    mu_l, _, mu_s, _ = plan.predict_prior_moments(pars, g)
+    mu_f, quad, info = plan.predict_moments_sep(pars, g, mu_l.unsqueeze(2), mu_s)
+    _check_info(info)
+    mu_f, quad = mu_f[0, :, 0].cpu(), quad[0, :, 0].cpu()
+    s2e = torch.exp(torch.as_tensor(tilde_sigma2_err, dtype=torch.float64))
+    sig_star = torch.exp(mu_s[0, :, 0].cpu())
+    a2 = _B_diag(uL_vec, plan.M).reshape(1, -1) * (settings.jitter + sig_star * sig_star).unsqueeze(1)   # prediction.py:389-393
+    s2y = a2 - quad + s2e
+    s2y[s2y <= 0] = settings.precision
+    sd = torch.sqrt(s2y)
+    return torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd], dim=1)
+
+
+def point_predmap(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_star, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                  mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """(prediction.py:337-408): tensor [3,M]."""
+    return pointwise_predmap(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x,
+                             np.asarray(x_star, dtype=np.float64).reshape(1), mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                             mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, **kwargs)[0]
+
+
+def test_predmap(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                 mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """(prediction.py:432-459)"""
+    return pointwise_predmap(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l,
+                             beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, **kwargs)
+
+
+test_predmap.__test__ = False
+
+
+def pointwise_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, mu_tilde_l,
+                               alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args,
+                               **kwargs):
+    """Sampling prediction of the separable model from MAP estimates (prediction.py:189-306): per new input and sample
+    tilde_l* (1 draw), tilde_sigma* (1), y (M); returns (quantiles [G,2,M], mean [G,M], std [G,M])."""
+    torch = _lib.require_cuda()
+    f64 = torch.float64
+    hyper = _sep_hyper(mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, kwargs)
+    plan, pars = _sep_plan_and_pars(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, hyper)
+    M = plan.M
+    g = torch.as_tensor(grids, dtype=f64).reshape(-1)
+    G = int(g.numel())
+    mu_l, s2_l, mu_s, s2_s = (t[0].cpu() for t in plan.predict_prior_moments(pars, g))
+    z_l, z_s, z_y = torch.empty((G, n_sample), dtype=f64), torch.empty((G, n_sample), dtype=f64), torch.empty((G, n_sample, M), dtype=f64)
+    for gi in range(G):
+        for s in range(n_sample):
+            z_l[gi, s] = torch.empty((), dtype=f64).normal_()      # prediction.py:213
+            z_s[gi, s] = torch.empty((), dtype=f64).normal_()      # :223
+            z_y[gi, s] = torch.empty(M, dtype=f64).normal_()       # :266
+    tl_star = z_l.mul(torch.sqrt(s2_l).unsqueeze(1)).add(mu_l.unsqueeze(1))
+    ts_star = z_s.mul(torch.sqrt(s2_s).unsqueeze(1)).add(mu_s[:, 0].unsqueeze(1))
+    mu_f, quad, info = plan.predict_moments_sep(pars, g, tl_star.unsqueeze(0), ts_star.unsqueeze(0))
+    _check_info(info)
+    mu_f, quad = mu_f[0].cpu(), quad[0].cpu()
+    s2e = torch.exp(torch.as_tensor(tilde_sigma2_err, dtype=f64))
+    sig_star = torch.exp(ts_star)
+    a2 = (sig_star ** 2).unsqueeze(2) * _B_diag(uL_vec, M).reshape(1, 1, -1)                            # prediction.py:254
+    s2y = a2 - quad + s2e
+    s2y[s2y <= 0] = settings.precision
+    return _summaries(z_y.mul(torch.sqrt(s2y)).add(mu_f))
+
+
+def point_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_star, mu_tilde_l, alpha_tilde_l,
+                           beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """(prediction.py:189-277): (quantiles [2,M], mean [M], std [M])."""
+    q, m, sd = pointwise_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x,
+                                          np.asarray(x_star, dtype=np.float64).reshape(1), mu_tilde_l, alpha_tilde_l,
+                                          beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, **kwargs)
+    return q[0], m[0], sd[0]
+
+
+def test_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test, mu_tilde_l, alpha_tilde_l,
+                          beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, *args, **kwargs):
+    """(prediction.py:308-335)"""
+    return pointwise_predmap_sampling(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, x_test, mu_tilde_l,
+                                      alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, **kwargs)
+
+
+test_predmap_sampling.__test__ = False
+
+
+def _replicated_plan(model, H, Y, x, hyper):
+    """One plan whose H 'subjects' are the same data under H different parameter vectors (a posterior history)."""
+    torch = _lib.require_cuda()
+    from .batched import LogPosteriorPlan
+    Y = torch.as_tensor(Y, dtype=torch.float64)
+    x = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
+    key = (model, H, logpos._fingerprint(Y), logpos._fingerprint(x), tuple(sorted((k, float(v)) for k, v in hyper.items())),
+           torch.cuda.current_device())
+    plan = _HIST_PLANS.get(key)
+    if plan is None:
+        for old in _HIST_PLANS.values():
+            old.close()
+        _HIST_PLANS.clear()
+        plan = LogPosteriorPlan(model, x.unsqueeze(0).expand(H, -1), Y.unsqueeze(0).expand(H, -1, -1), hyper)
+        _HIST_PLANS[key] = plan
+    return plan
+
+
+def pointwise_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l,
+                         alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample, *args,
+                         **kwargs):
+    """One predictive draw per entry of a posterior history of the separable model, at every new input
+    (prediction.py:34-157): numpy array [G, N_sample, M].  The entries are the 'subjects' of one batched plan."""
+    torch = _lib.require_cuda()
+    f64 = torch.float64
+    tl_h = torch.as_tensor(tilde_l_hist, dtype=f64)[-N_sample:]
+    ts_h = torch.as_tensor(tilde_sigma_hist, dtype=f64)[-N_sample:]
+    ul_h = torch.as_tensor(uL_vec_hist, dtype=f64)[-N_sample:]
+    te_h = torch.as_tensor(tilde_sigma2_err_hist, dtype=f64).reshape(-1)[-N_sample:]
+    H = int(tl_h.shape[0])
+    hyper = _sep_hyper(mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, kwargs)
+    plan = _replicated_plan("separable", H, Y, x, hyper)
+    M = plan.M
+    g = torch.as_tensor(grids, dtype=f64).reshape(-1)
+    G = int(g.numel())
+    pars = torch.cat([tl_h, ts_h, ul_h, te_h.unsqueeze(1)], dim=1).detach()
+    mu_l, s2_l, mu_s, s2_s = (t.cpu() for t in plan.predict_prior_moments(pars, g))       # [H,G], [H,G], [H,G,1], [H,G]
+    z_l, z_s, z_y = torch.empty((G, H), dtype=f64), torch.empty((G, H), dtype=f64), torch.empty((G, H, M), dtype=f64)
+    for gi in range(G):          # per new input, per history entry: tilde_l*, tilde_sigma*, y  (prediction.py:60, 70, 118)
+        for h in range(H):
+            z_l[gi, h] = torch.empty((), dtype=f64).normal_()
+            z_s[gi, h] = torch.empty((), dtype=f64).normal_()
+            z_y[gi, h] = torch.empty(M, dtype=f64).normal_()
+    tl_star = z_l.t().mul(torch.sqrt(s2_l)).add(mu_l)                                     # [H,G]
+    ts_star = z_s.t().mul(torch.sqrt(s2_s)).add(mu_s[:, :, 0])
+    mu_f, quad, info = plan.predict_moments_sep(pars, g, tl_star.unsqueeze(2), ts_star.unsqueeze(2))
+    _check_info(info)
+    mu_f, quad = mu_f[:, :, 0].cpu(), quad[:, :, 0].cpu()                                 # [H,G,M]
+    sig_star = torch.exp(ts_star)
+    a2 = _B_diag(ul_h, M).unsqueeze(1) * (settings.jitter + sig_star * sig_star).unsqueeze(2)   # prediction.py:101
+    s2y = a2 - quad + torch.exp(te_h).reshape(H, 1, 1)
+    s2y[s2y <= 0] = settings.precision
+    return z_y.mul(torch.sqrt(s2y).transpose(0, 1)).add(mu_f.transpose(0, 1)).numpy()
+
+
+def point_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, x_star, mu_tilde_l,
+                     alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample, *args,
+                     **kwargs):
+    """(prediction.py:34-131): tensor [N_sample, M]."""
+    torch = _lib.require_cuda()
+    res = pointwise_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x,
+                               np.asarray(x_star, dtype=np.float64).reshape(1), mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                               mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample, **kwargs)
+    return torch.from_numpy(res[0])
+
+
+def test_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l,
+                    alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample, *args, **kwargs):
+    """(prediction.py:159-187)"""
+    return pointwise_predsample(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, x_test, mu_tilde_l,
+                                alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample,
+                                **kwargs)
+
+
+test_predsample.__test__ = False
+
+
+# ===================================================================================== stationary model (prediction.py:1566-1692)
+_S_HYPER = dict(mu_tilde_l=0.0, sigma_tilde_l=1.0, a=1, b=1, c=10)   # priors do not enter the predictive moments
+
+
+def _stationary_moments(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, grids):
+    """mu_f, sigma2_y [H,G,M] for H stationary parameter sets (prediction.py:1587-1596), CPU tensors."""
+    torch = _lib.require_cuda()
+    f64 = torch.float64
+    tl = torch.as_tensor(tilde_ls, dtype=f64).reshape(-1)
+    ts = torch.as_tensor(tilde_sigmas, dtype=f64).reshape(-1)
+    H = int(tl.numel())
+    ul = torch.as_tensor(uL_vecs, dtype=f64).reshape(H, -1)
+    te = torch.as_tensor(tilde_sigma2_errs, dtype=f64).reshape(-1)
+    plan = logpos._get_plan("stationary", Y, x, _S_HYPER, True) if H == 1 else _replicated_plan("stationary", H, Y, x, _S_HYPER)
+    g = torch.as_tensor(grids, dtype=f64).reshape(-1)
+    G = int(g.numel())
+    pars = torch.cat([tl.unsqueeze(1), ts.unsqueeze(1), ul, te.unsqueeze(1)], dim=1).detach()
+    mu_f, quad, info = plan.predict_moments_sep(pars, g, tl.reshape(H, 1, 1).expand(H, G, 1), ts.reshape(H, 1, 1).expand(H, G, 1))
+    _check_info(info)
+    mu_f, quad = mu_f[:, :, 0].cpu(), quad[:, :, 0].cpu()
+    sigma = torch.exp(ts)
+    s2y = ((sigma ** 2).reshape(H, 1) * _B_diag(ul, plan.M)).unsqueeze(1) - quad + torch.exp(te).reshape(H, 1, 1)
+    s2y[s2y < 0] = settings.precision                                                     # prediction.py:1595
+    return mu_f, s2y
+
+
+def pointwise_predmap_S(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, *args, **kwargs):
+    """(prediction.py:1566-1598): tensor [G,3,M] = mu_f -/+ 1.96 sd."""
+    torch = _lib.require_cuda()
+    mu_f, s2y = _stationary_moments(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids)
+    sd = torch.sqrt(s2y[0])
+    return torch.stack([mu_f[0] - 1.96 * sd, mu_f[0], mu_f[0] + 1.96 * sd], dim=1)
+
+
+def test_predmap_S(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, test_x, *args, **kwargs):
+    """(prediction.py:1601-1638): (mean [G,M], std [G,M]) tensors."""
+    torch = _lib.require_cuda()
+    mu_f, s2y = _stationary_moments(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, test_x)
+    return mu_f[0], torch.sqrt(s2y[0])
+
+
+test_predmap_S.__test__ = False
+
+
+def pointwise_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, grids, *args, **kwargs):
+    """One draw per posterior sample and new input, numpy's global generator, one scalar per (sample, input) shared by the M
+    outputs (prediction.py:1640-1665): numpy array [H, G, M]."""
+    torch = _lib.require_cuda()
+    mu_f, s2y = _stationary_moments(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, grids)
+    H, G, _ = mu_f.shape
+    z = torch.from_numpy(np.array([[np.random.randn() for _ in range(G)] for _ in range(H)], dtype=np.float64).reshape(H, G, 1))
+    return (mu_f + z * torch.sqrt(s2y)).numpy()
+
+
+def test_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, test_x, *args, **kwargs):
+    """(prediction.py:1667-1692)"""
+    return pointwise_predsample_S(tilde_ls, tilde_sigmas, uL_vecs, tilde_sigma2_errs, Y, x, test_x)
+
+
+test_predsample_S.__test__ = False

@@ -201,3 +201,133 @@ def pointwise_predict_history(tilde_l_hist, uL_vecs_hist, tilde_sigma2_err_hist,
         a = np.asarray(v)
         res[k] = a.reshape(G, H, *a.shape[1:])
     return res
+
+
+# ===================================================================================== separable / stationary models
+def gibbs_cross_sigma(x1, sig1, ell1, x2, sig2, ell2) -> torch.Tensor:
+    """sig1_i sig2_j sqrt(2 l1_i l2_j/(l1_i^2+l2_j^2)) exp(-d_ij/(l1_i^2+l2_j^2))  (Utility/kernels.py:46-73, X2 given)."""
+    return (sig1.view(-1, 1) * sig2.view(1, -1)) * gibbs_cross(x1, ell1, x2, ell2)
+
+
+def _sep_setup(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x):
+    N, M = Y.shape
+    L = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(uL_vec, M), M)
+    B_f = L @ L.t()
+    ell, sig, s2e = torch.exp(tilde_l), torch.exp(tilde_sigma), torch.exp(tilde_sigma2_err)
+    K_x = O.gibbs_cov(x, ell, sig)
+    wB, vB = torch.linalg.eigh(B_f, UPLO="U")                                    # prediction.py:95-96
+    wK, vK = torch.linalg.eigh(K_x, UPLO="U")
+    Kt = torch.kron(vB.t(), vK.t())                                              # what kron_mv(v_B.t(), v_K.t(), .) applies
+    w = 1.0 / (s2e + torch.kron(wB, wK))                                         # kronecker_product_diag, :99-100
+    b = Kt @ Y.t().reshape(-1)
+    return dict(B_f=B_f, ell=ell, sig=sig, s2e=s2e, Kt=Kt, w=w, b=b, M=M, N=N)
+
+
+def sep_predictive_moments(su, x, x_star, tilde_l_star, tilde_sigma_star, jitter_in_a2):
+    """mu_f [M], sigma2_y [M] of the separable model at one x_star (prediction.py:97-116 / 241-261 / 381-398).
+    jitter_in_a2: a2 = diag(B_f (x) Nonstationary_RBF_cov(x*)) = diag(B_f) (1e-6 + sigma*^2)  (:101, :389) versus
+    a2 = sigma*^2 diag(B_f) (:254)."""
+    l_star, sig_star = torch.exp(tilde_l_star).view(1), torch.exp(tilde_sigma_star).view(1)
+    k_x = gibbs_cross_sigma(x, su["sig"], su["ell"], x_star.view(1), sig_star, l_star)      # N x 1
+    k_f = torch.kron(su["B_f"], k_x)                                                          # NM x M
+    A = (su["Kt"] @ k_f).t()                                                                  # M x NM
+    mu_f = A @ (su["b"] * su["w"])
+    var_star = (O.JITTER + sig_star * sig_star) if jitter_in_a2 else sig_star ** 2
+    a2 = torch.diagonal(su["B_f"]) * var_star
+    s2y = a2 - (A * su["w"] * A).sum(dim=1) + su["s2e"]
+    s2y = s2y.clone()
+    s2y[s2y <= 0] = PRECISION
+    return mu_f, s2y
+
+
+def _clip_neg(s2):
+    return s2 if s2 >= 0 else torch.tensor(PRECISION, dtype=O.DTYPE)
+
+
+def sep_pointwise_plugin(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                         mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma):
+    """`pointwise_predmap` (prediction.py:337-430): numpy [G,3,M]."""
+    su = _sep_setup(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x)
+    N = su["N"]
+    out = []
+    for xs in grids:
+        mu_l, _ = prior_conditional(x, xs, tilde_l.view(N, 1), mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+        mu_s, _ = prior_conditional(x, xs, tilde_sigma.view(N, 1), mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma)
+        mu_f, s2y = sep_predictive_moments(su, x, xs, mu_l[0], mu_s[0], True)
+        sd = torch.sqrt(s2y)
+        out.append(torch.stack([mu_f - 1.96 * sd, mu_f, mu_f + 1.96 * sd]).numpy())
+    return np.stack(out)
+
+
+def sep_pointwise_predict(n_sample, tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids, mu_tilde_l, alpha_tilde_l,
+                          beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma):
+    """`pointwise_predmap_sampling` (prediction.py:189-306): all draws [G,ns,...], generator consumed in the reference's order
+    (per new input, per sample: tilde_l*, tilde_sigma*, y)."""
+    su = _sep_setup(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x)
+    N, M = su["N"], su["M"]
+    keys = ("l_loc", "l_scale", "l_draw", "s_loc", "s_scale", "s_draw", "y_loc", "y_scale", "y_draw")
+    out = {k: [] for k in keys}
+    for xs in grids:
+        mu_l, s2_l = prior_conditional(x, xs, tilde_l.view(N, 1), mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+        mu_s, s2_s = prior_conditional(x, xs, tilde_sigma.view(N, 1), mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma)
+        sc_l, sc_s = torch.sqrt(_clip_neg(s2_l)), torch.sqrt(_clip_neg(s2_s))
+        for _ in range(n_sample):
+            tl_star = torch.empty((), dtype=O.DTYPE).normal_().mul(sc_l).add(mu_l[0])
+            ts_star = torch.empty((), dtype=O.DTYPE).normal_().mul(sc_s).add(mu_s[0])
+            mu_f, s2y = sep_predictive_moments(su, x, xs, tl_star, ts_star, False)
+            sc_y = torch.sqrt(s2y)
+            yd = torch.empty(M, dtype=O.DTYPE).normal_().mul(sc_y).add(mu_f)
+            for k, v in zip(keys, (mu_l[0], sc_l, tl_star, mu_s[0], sc_s, ts_star)):
+                out[k].append(float(v))
+            for k, v in zip(keys[6:], (mu_f, sc_y, yd)):
+                out[k].append(v.numpy().copy())
+    G = grids.numel()
+    return {k: np.asarray(v).reshape(G, n_sample, *np.asarray(v).shape[1:]) for k, v in out.items()}
+
+
+def sep_pointwise_history(tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist, Y, x, grids, mu_tilde_l,
+                          alpha_tilde_l, beta_tilde_l, mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, N_sample):
+    """`pointwise_predsample` (prediction.py:34-157): per new input, per history entry: tilde_l*, tilde_sigma*, y."""
+    tl_h, ts_h, ul_h, te_h = (t[-N_sample:] for t in (tilde_l_hist, tilde_sigma_hist, uL_vec_hist, tilde_sigma2_err_hist))
+    H, G = tl_h.shape[0], grids.numel()
+    sus = [_sep_setup(tl_h[h], ts_h[h], ul_h[h], te_h[h], Y, x) for h in range(H)]
+    N, M = sus[0]["N"], sus[0]["M"]
+    keys = ("l_loc", "l_scale", "l_draw", "s_loc", "s_scale", "s_draw", "y_loc", "y_scale", "y_draw")
+    out = {k: [] for k in keys}
+    for xs in grids:
+        for h in range(H):
+            mu_l, s2_l = prior_conditional(x, xs, tl_h[h].view(N, 1), mu_tilde_l, alpha_tilde_l, beta_tilde_l)
+            sc_l = torch.sqrt(_clip_neg(s2_l))
+            tl_star = torch.empty((), dtype=O.DTYPE).normal_().mul(sc_l).add(mu_l[0])
+            mu_s, s2_s = prior_conditional(x, xs, ts_h[h].view(N, 1), mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma)
+            sc_s = torch.sqrt(_clip_neg(s2_s))
+            ts_star = torch.empty((), dtype=O.DTYPE).normal_().mul(sc_s).add(mu_s[0])
+            mu_f, s2y = sep_predictive_moments(sus[h], x, xs, tl_star, ts_star, True)
+            sc_y = torch.sqrt(s2y)
+            yd = torch.empty(M, dtype=O.DTYPE).normal_().mul(sc_y).add(mu_f)
+            for k, v in zip(keys, (mu_l[0], sc_l, tl_star, mu_s[0], sc_s, ts_star)):
+                out[k].append(float(v))
+            for k, v in zip(keys[6:], (mu_f, sc_y, yd)):
+                out[k].append(v.numpy().copy())
+    return {k: np.asarray(v).reshape(G, H, *np.asarray(v).shape[1:]) for k, v in out.items()}
+
+
+def stationary_moments(tilde_l, tilde_sigma, uL_vec, tilde_sigma2_err, Y, x, grids):
+    """mu_f, sigma2_y [G,M] of the stationary model with the dense inverse of B_f (x) K_x + sigma2 I (prediction.py:1578-1596)."""
+    N, M = Y.shape
+    L = O.tril_vec_to_matrix(O.unconstrained_to_tril_vec(uL_vec, M), M)
+    B_f = L @ L.t()
+    l, sigma, s2e = torch.exp(tilde_l), torch.exp(tilde_sigma), torch.exp(tilde_sigma2_err)
+    K_x = O.rbf_cov(x, float(sigma), float(l))
+    invS = torch.inverse(torch.kron(B_f, K_x) + s2e * torch.eye(N * M, dtype=O.DTYPE))
+    y = Y.t().reshape(-1)
+    mus, s2s = [], []
+    for xs in grids:
+        k_x = rbf_cross(x, xs.view(1), float(sigma), float(l))
+        k_f = torch.kron(B_f, k_x).t()
+        mu_f = (k_f @ invS) @ y
+        s2y = sigma ** 2 * torch.diagonal(B_f) - torch.diagonal((k_f @ invS) @ k_f.t()) + s2e
+        s2y = s2y.clone()
+        s2y[s2y < 0] = PRECISION
+        mus.append(mu_f.numpy()); s2s.append(s2y.numpy())
+    return np.stack(mus), np.stack(s2s)

@@ -20,7 +20,7 @@ def pytest_configure(config):
 def golden_cases():
     """log-posterior + gradient fixtures (tests/golden/make_golden.py)"""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("predict_"))
+                  if not os.path.basename(p).startswith("predict"))
 
 
 def predict_cases():
@@ -28,12 +28,24 @@ def predict_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "predict_*.npz")))
 
 
+def predictsep_cases():
+    """separable-model prediction fixtures (tests/golden/make_golden_predict_sep.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "predictsep_*.npz")))
+
+
+def predictstat_cases():
+    """stationary-model prediction fixtures (tests/golden/make_golden_predict_sep.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "predictstat_*.npz")))
+
+
 def load_predict_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
     d = {k: z[k] for k in z.files}
-    d["hyper"] = json.loads(str(d["hyper"]))
+    if "hyper" in d:
+        d["hyper"] = json.loads(str(d["hyper"]))
     for k in ("N", "M", "n_sample", "seed"):
-        d[k] = int(d[k])
+        if k in d:
+            d[k] = int(d[k])
     return d
 
 

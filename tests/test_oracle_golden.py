@@ -3,7 +3,8 @@ reference (tests/golden/make_golden.py).  CPU-only."""
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden, load_predict_golden, max_rel, predict_cases, rel_err
+from conftest import (golden_cases, load_golden, load_predict_golden, max_rel, predict_cases, predictsep_cases,
+                      predictstat_cases, rel_err)
 from oracle import nmgp_oracle as O
 
 # The oracle restates the reference's algorithm op-for-op, so agreement is at rounding level for the
@@ -64,3 +65,52 @@ def test_predict_oracle_matches_reference_golden(name):
     for k in ("l_loc", "l_scale", "l_draw", "u_loc", "u_scale", "u_draw", "y_loc", "y_scale"):
         assert max_rel(r[k], g["hist_" + k]) < VAL_TOL, (name, "hist_" + k, max_rel(r[k], g["hist_" + k]))
     assert max_rel(r["y_draw"], g["hist_y"]) < VAL_TOL
+
+
+@pytest.mark.parametrize("name", predictsep_cases())
+def test_separable_predict_oracle_matches_reference_golden(name):
+    """Separable-model predictors (Utility/prediction.py:34-459) restated in oracle/nmgp_predict_oracle.py."""
+    import torch
+    from oracle import nmgp_predict_oracle as PO
+    g = load_predict_golden(name)
+    N, M = g["N"], g["M"]
+    T = M * (M + 1) // 2
+    p = torch.from_numpy(g["pars"])
+    Y, x, grids = torch.from_numpy(g["Y"]), torch.from_numpy(g["x"]), torch.from_numpy(g["grids"])
+    args = (p[:N], p[N:2 * N], p[2 * N:2 * N + T], p[-1], Y, x, grids)
+    assert max_rel(PO.sep_pointwise_plugin(*args, **g["hyper"]), g["map_percentiles"]) < VAL_TOL
+    torch.manual_seed(1000 + g["seed"])
+    r = PO.sep_pointwise_predict(g["n_sample"], *args, **g["hyper"])
+    for k in r:
+        assert max_rel(r[k], g[k]) < VAL_TOL, (name, k, max_rel(r[k], g[k]))
+    hp = torch.from_numpy(g["hist_pars"])
+    torch.manual_seed(5000 + g["seed"])
+    r = PO.sep_pointwise_history(hp[:, :N], hp[:, N:2 * N], hp[:, 2 * N:2 * N + T], hp[:, -1], Y, x,
+                                 torch.from_numpy(g["hist_grids"]), N_sample=int(g["hist_n_sample"]), **g["hyper"])
+    for k in ("l_loc", "l_scale", "l_draw", "s_loc", "s_scale", "s_draw", "y_loc", "y_scale"):
+        assert max_rel(r[k], g["hist_" + k]) < VAL_TOL, (name, "hist_" + k, max_rel(r[k], g["hist_" + k]))
+    assert max_rel(r["y_draw"], g["hist_y"]) < VAL_TOL
+
+
+@pytest.mark.parametrize("name", predictstat_cases())
+def test_stationary_predict_oracle_matches_reference_golden(name):
+    """Stationary-model predictors (Utility/prediction.py:1566-1692)."""
+    import torch
+    from oracle import nmgp_predict_oracle as PO
+    g = load_predict_golden(name)
+    M = g["M"]
+    T = M * (M + 1) // 2
+    p = torch.from_numpy(g["pars"])
+    Y, x = torch.from_numpy(g["Y"]), torch.from_numpy(g["x"])
+    mu, s2 = PO.stationary_moments(p[0], p[1], p[2:2 + T], p[-1], Y, x, torch.from_numpy(g["grids"]))
+    sd = np.sqrt(s2)
+    assert max_rel(np.stack([mu - 1.96 * sd, mu, mu + 1.96 * sd], axis=1), g["map_percentiles"]) < VAL_TOL
+    mu, s2 = PO.stationary_moments(p[0], p[1], p[2:2 + T], p[-1], Y, x, x[:6])
+    assert max_rel(mu, g["test_mean"]) < VAL_TOL and max_rel(np.sqrt(s2), g["test_std"]) < VAL_TOL
+    np.random.seed(7000 + g["seed"])
+    hp = torch.from_numpy(g["hist_pars"])
+    ys = []
+    for h in range(hp.shape[0]):
+        mu, s2 = PO.stationary_moments(hp[h, 0], hp[h, 1], hp[h, 2:2 + T], hp[h, -1], Y, x, torch.from_numpy(g["grids"]))
+        ys.append(np.stack([mu[i] + np.random.randn() * np.sqrt(s2[i]) for i in range(mu.shape[0])]))
+    assert max_rel(np.stack(ys), g["hist_y"]) < VAL_TOL
