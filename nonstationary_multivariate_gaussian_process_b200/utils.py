@@ -71,3 +71,63 @@ def lowtriangle2vec(L, N=None):
         return L[idx[0], idx[1]]
     r, c = np.tril_indices(N)
     return L[r, c]
+
+
+# ------------------------------------------------------------------------------------------------ driver-side helpers
+# Data splitting and scores the drivers call around the hot path (Utility/utils.py:91-196).  Host-side numpy; the random
+# splits go through the same third-party routine as the reference (sklearn's train_test_split), so a given random_state
+# yields the same partition.
+def data_split(x, Y, test_size=0.25, random_state=22, shuffle=True):
+    """Random train / test split of (x [N], Y [N,M]), each part re-sorted by x (utils.py:138-156)."""
+    from sklearn.model_selection import train_test_split
+    x_tr, x_te, Y_tr, Y_te = train_test_split(x, Y, test_size=test_size, random_state=random_state, shuffle=shuffle)
+    o_tr, o_te = np.argsort(x_tr), np.argsort(x_te)
+    return x_tr[o_tr], x_te[o_te], Y_tr[o_tr], Y_te[o_te]
+
+
+def data_split_extrapolation(x, Y, size=5):
+    """Hold out the last `size` time points (utils.py:159-164)."""
+    return x[:-size], x[-size:], Y[:-size], Y[-size:]
+
+
+def data_split_non(x, indx, y, test_size=0.25, random_state=22, shuffle=True):
+    """Random split of irregularly sampled data (x, output index, y) (utils.py:91-103)."""
+    from sklearn.model_selection import train_test_split
+    return tuple(train_test_split(x, indx, y, test_size=test_size, random_state=random_state, shuffle=shuffle))
+
+
+def data_split_non_chunk(x, indx, y, chunk_size=0.2, random_state=22, fix=False):
+    """Per output m, hold out one contiguous chunk of int(chunk_size * n_m) samples; its start is drawn with
+    np.random.choice after np.random.seed(random_state), or spread evenly over the outputs when fix=True (utils.py:106-135)."""
+    M = len(np.unique(indx))
+    parts = [[] for _ in range(6)]
+    np.random.seed(random_state)
+    for m in range(M):
+        sel = indx == m
+        xm, ym = x[sel], y[sel]
+        n_m = xm.shape[0]
+        n_te = int(chunk_size * n_m)
+        n_tr = n_m - n_te
+        start = int(np.floor(m * n_tr / (M - 1))) if fix else np.random.choice(n_tr)
+        te = np.arange(start, start + n_te)
+        tr = np.concatenate([np.arange(0, start), np.arange(start + n_te, n_m)])
+        for lst, v in zip(parts, (xm[tr], xm[te], m * np.ones(n_tr), m * np.ones(n_te), ym[tr], ym[te])):
+            lst.append(v)
+    return tuple(np.concatenate(p) for p in parts)
+
+
+def MSE(x, y, axis=None):
+    """Mean squared error (utils.py:167-174)."""
+    return np.mean((x - y) ** 2, axis=axis)
+
+
+def RMSE(x, y, axis=None):
+    """Root mean squared error (utils.py:177-184)."""
+    return np.sqrt(np.mean((x - y) ** 2, axis=axis))
+
+
+def LPD(mean_array, std_array, y_array):
+    """Mean log predictive density of y under N(mean, std^2), element-wise (utils.py:187-199)."""
+    mu, sd, yv = (np.asarray(a, dtype=np.float64).reshape(-1) for a in (mean_array, std_array, y_array))
+    z = (yv - mu) / sd
+    return float(np.mean(-0.5 * z * z - np.log(sd) - 0.5 * np.log(2.0 * np.pi)))

@@ -91,3 +91,26 @@ def test_synthetic_covariance_matches_oracle_up_to_the_ordering_permutation():
     assert np.all(np.diff(x) > 0) and x.min() > 0 and x.max() < 1
     xs, Y, pars = synth.sample_subject(N, M, 3)
     assert Y.shape == (N, M) and pars.shape == (O.n_params("nonseparable", N, M),)
+
+
+def test_driver_side_helpers():
+    """Splits and scores the drivers call around the hot path (Utility/utils.py:91-199), numpy only."""
+    import numpy as np
+    from scipy.stats import norm
+    from nonstationary_multivariate_gaussian_process_b200 import utils
+    rng = np.random.RandomState(3)
+    x, Y = np.sort(rng.rand(40)), rng.randn(40, 3)
+    x_tr, x_te, Y_tr, Y_te = utils.data_split(x, Y)
+    assert x_tr.shape == (30,) and x_te.shape == (10,) and np.all(np.diff(x_tr) > 0) and np.all(np.diff(x_te) > 0)
+    assert all(np.array_equal(Y[np.searchsorted(x, v)], row) for v, row in zip(x_te, Y_te))
+    a, b, c, d = utils.data_split_extrapolation(x, Y, size=7)
+    assert a.shape == (33,) and np.array_equal(b, x[-7:]) and np.array_equal(d, Y[-7:])
+    indx, y = np.repeat(np.arange(4), 10).astype(float), rng.randn(40)
+    xt, xs, it, is_, yt, ys = utils.data_split_non_chunk(x, indx, y, chunk_size=0.2, fix=True)
+    assert xt.shape == (32,) and xs.shape == (8,) and np.array_equal(np.unique(is_), np.arange(4.0))
+    for m in range(4):      # the held-out samples of an output are contiguous in its own ordering
+        pos = np.searchsorted(x[indx == m], xs[is_ == m])
+        assert np.array_equal(pos, np.arange(pos[0], pos[0] + 2))
+    m_, s_, y_ = rng.randn(5, 3), rng.rand(5, 3) + 0.1, rng.randn(5, 3)
+    assert abs(utils.LPD(m_, s_, y_) - norm.logpdf(y_, loc=m_, scale=s_).mean()) < 1e-14
+    assert np.allclose(utils.RMSE(m_, y_, axis=0) ** 2, utils.MSE(m_, y_, axis=0))

@@ -11,6 +11,10 @@ cat gpurun_out/pytest_$TAG.txt
   python tools/run_config.py separable 200 5 1 20
   python tools/run_config.py stationary 50 2 1 20
   python tools/run_config.py nonseparable 100 6 10000 3 ; } 2>&1 | tee gpurun_out/configs_$TAG.txt
+{ python tools/run_predict.py 100 6 1 201 100
+  python tools/run_predict.py 100 6 64 201 100
+  python tools/run_predict.py 500 10 1 201 100 ; } 2>&1 | grep "^{" | tee gpurun_out/predict_$TAG.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_err_$TAG.txt
 cat gpurun_out/bench_$TAG.json
 tail -5 gpurun_out/bench_err_$TAG.txt
