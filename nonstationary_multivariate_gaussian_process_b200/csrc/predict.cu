@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(128) pred_quad_kernel(const double* __restrict
   const int cc = blockIdx.z, pair = blockIdx.y, col0 = blockIdx.x * QT;
   const double* H = Hm + (long)cc * hm_stride + (long)pair * Ni64 * Npad;
   const double* KX = KXT + (long)cc * kx_stride;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // The quarter of the tile a warp owns is rotated per CTA: warps are pinned to SM sub-partitions (one DMMA pipe each), and
+  // the quarters do unequal work when the last row tile is mostly padding.
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = ((tid >> 5) + blockIdx.x + blockIdx.y) & 3;
   const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
   const int lr = lane >> 2, lk = lane & 3;
   const int nK = Npad / QK, total = (Ni64 / QT) * nK;
@@ -199,9 +202,14 @@ __global__ void __launch_bounds__(128) pred_quad_kernel(const double* __restrict
     const double* SA = &As[buf][(m0 + lr) * QLD + lk];
     const double* SB = &Bs[buf][(n0 + lr) * QLD + lk];
     // a warp whose 32 rows are all padding (N = 100: rows 96..127 of the second row tile) has nothing to add
-    if ((q / nK) * QT + m0 < N)
+    // 8-row groups of this warp that are all padding (N = 100: rows 104..127 of the second row tile) and k-steps of the last
+    // chunk that only meet zero padding are skipped
+    const int ksteps = min(QK / 4, (N - (q % nK) * QK + 3) / 4);
+    const int na = min(4, max(0, (N - ((q / nK) * QT + m0) + 7) / 8));
+    if (na > 0)
 #pragma unroll
     for (int ks = 0; ks < QK / 4; ++ks) {
+      if (ks >= ksteps) break;
       double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -210,8 +218,9 @@ __global__ void __launch_bounds__(128) pred_quad_kernel(const double* __restrict
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
+        if (i < na)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();   // this buffer is refilled by the load issued at the top of the next iteration
     if ((q + 1) % nK == 0) {

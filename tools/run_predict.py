@@ -27,15 +27,18 @@ ul = torch.from_numpy(0.3 * rng.standard_normal((S, G, NS, T))).cuda()
 
 
 def timed(fn):
-    for _ in range(2):
+    """median of per-call CUDA-event times after warm-up (the first call allocates the scratch and loads the kernels)"""
+    for _ in range(3):
         fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+    ts = []
+    for _ in range(max(reps, 5)):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         out = fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps, out
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), out
 
 
 ms_prior, _ = timed(lambda: plan.predict_prior_moments(p, grids))
