@@ -29,6 +29,9 @@ enum Mode : int {
   TRTRI_PANEL = 4,  // A(i,c)  <- A(i,c) * W_cc                        i > c
   LAUUM_UPD = 5,    // A(i,j) += A(r,i)^T * A(r,j)                     j <= i < r
   LAUUM_ROW = 6,    // A(r,j)  <- W_rr^T * A(r,j) (j<r);  A(r,r) <- W_rr^T W_rr
+  // POTRF_SYRK split for the look-ahead: the next block column alone, and everything to the right of it
+  POTRF_SYRK_COL = 7,   // A(i,k+1) -= A(i,k) * A(k+1,k)^T               i >= k+1
+  POTRF_SYRK_REST = 8,  // A(i,j)   -= A(i,k) * A(j,k)^T                 k+2 <= j <= i
 };
 
 struct EngineArgs {
@@ -102,6 +105,11 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
   } else if (MODE == POTRF_SYRK) {
     int a, b; tri_decode(t, a, b);
     i = s + 1 + a; j = s + 1 + b; ai = i; aj = s; bi = j; bj = s;
+  } else if (MODE == POTRF_SYRK_COL) {
+    i = s + 1 + t; j = s + 1; ai = i; aj = s; bi = j; bj = s;
+  } else if (MODE == POTRF_SYRK_REST) {
+    int a, b; tri_decode(t, a, b);
+    i = s + 2 + a; j = s + 2 + b; ai = i; aj = s; bi = j; bj = s;
   } else if (MODE == TRTRI_ROW) {
     i = s; j = t; ai = -1; aj = -1; bi = s; bj = j;
   } else if (MODE == TRTRI_UPD) {
@@ -116,11 +124,11 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
     i = s; j = t; ai = -1; aj = -1;
     if (j < s) { bi = s; bj = j; } else { bi = -1; bj = -1; }
   }
-  constexpr bool A_KM = (MODE == POTRF_PANEL || MODE == POTRF_SYRK || MODE == TRTRI_ROW || MODE == TRTRI_UPD ||
-                         MODE == TRTRI_PANEL);
-  constexpr bool B_KM = (MODE == POTRF_PANEL || MODE == POTRF_SYRK);
-  constexpr double alpha = (MODE == POTRF_SYRK || MODE == TRTRI_ROW) ? -1.0 : 1.0;
-  constexpr bool accumulate = (MODE == POTRF_SYRK || MODE == TRTRI_UPD || MODE == LAUUM_UPD);
+  constexpr bool SYRK = (MODE == POTRF_SYRK || MODE == POTRF_SYRK_COL || MODE == POTRF_SYRK_REST);
+  constexpr bool A_KM = (MODE == POTRF_PANEL || SYRK || MODE == TRTRI_ROW || MODE == TRTRI_UPD || MODE == TRTRI_PANEL);
+  constexpr bool B_KM = (MODE == POTRF_PANEL || SYRK);
+  constexpr double alpha = (SYRK || MODE == TRTRI_ROW) ? -1.0 : 1.0;
+  constexpr bool accumulate = (SYRK || MODE == TRTRI_UPD || MODE == LAUUM_UPD);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
@@ -244,30 +252,92 @@ EngineArgs make_args(const BlockBatch& b) {
 
 }  // namespace
 
+namespace {
+int launch_panel(const BlockBatch& b, const EngineArgs& g, int r, bool stable_panel, cudaStream_t st, long* launches) {
+  if (!stable_panel) return launch_tiles<POTRF_PANEL>(g, r, st, launches);
+  if (r <= 0) return 0;
+  dim3 pg(r, b.batch < 65535 ? b.batch : 65535);
+  constexpr size_t kTrsmSmem = 2ull * NB * (NB + 1) * sizeof(double);
+  static bool trsm_configured = false;
+  if (!trsm_configured) {
+    NMGP_CUDA_TRY(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    trsm_configured = true;
+  }
+  trsm_panel_kernel<<<pg, NB, kTrsmSmem, st>>>(g);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+// Right-looking potrf with a one-step look-ahead.  For a handful of matrices every block step is a chain of three dependent
+// kernels -- diagonal block (33 us for one matrix: 64 dependent pivots), panel, trailing update (memory-bound rank-64) -- and
+// the chain, not the arithmetic, sets the time (n = 5000: 79 steps x 74 us).  The trailing update is split: the next block
+// column alone (COL) and everything to the right of it (REST).  The chain diag -> panel -> COL runs on a HIGH-priority
+// helper stream, REST on the caller's stream, so that the next step's diagonal block and panel run beside REST and their few
+// CTAs are scheduled ahead of REST's thousands.  (The caller's stream usually has the lowest priority already, which is why
+// the chain, not REST, moves to the helper.)  Orderings: REST(k) after panel(k) [evP]; COL(k+1) after REST(k) [evR], because
+// both update the tiles of block column k+2; the caller's stream finally waits for the helper [evP of the last step].
+int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
+  EngineArgs g = make_args(b);
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  cudaStream_t crit = nullptr;
+  cudaEvent_t evP[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr}, ev0 = nullptr;
+  NMGP_CUDA_TRY(cudaStreamCreateWithPriority(&crit, cudaStreamNonBlocking, greatest));
+  bool ok = cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming) == cudaSuccess;
+  for (int e = 0; e < 2 && ok; ++e)
+    ok = cudaEventCreateWithFlags(&evP[e], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&evR[e], cudaEventDisableTiming) == cudaSuccess;
+  int rc = ok ? 0 : -2;
+  if (!ok) set_last_error("engine_potrf: creating the look-ahead events failed");
+  auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) { rc = -2; set_last_error(std::string("engine_potrf look-ahead: ") + cudaGetErrorString(e)); } return rc == 0; };
+  if (rc == 0) { cu(cudaEventRecord(ev0, st)); cu(cudaStreamWaitEvent(crit, ev0, 0)); }   // after whatever built the matrices
+  bool rest_pending = false;
+  int last_e = -1;
+  for (int k = 0; rc == 0 && k < b.Kt; ++k) {
+    g.step = k;
+    const int r = b.Kt - k - 1, e = k & 1;
+    if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
+    if ((rc = launch_panel(b, g, r, stable_panel, crit, launches))) break;
+    if (!cu(cudaEventRecord(evP[e], crit))) break;
+    last_e = e;
+    if (r <= 0) break;
+    if (rest_pending && !cu(cudaStreamWaitEvent(crit, evR[e ^ 1], 0))) break;      // REST(k-1) done
+    if ((rc = launch_tiles<POTRF_SYRK_COL>(g, r, crit, launches))) break;
+    rest_pending = false;
+    if (r > 1) {
+      if (!cu(cudaStreamWaitEvent(st, evP[e], 0))) break;
+      if ((rc = launch_tiles<POTRF_SYRK_REST>(g, (r - 1) * r / 2, st, launches))) break;
+      if (!cu(cudaEventRecord(evR[e], st))) break;
+      rest_pending = true;
+    }
+  }
+  // the caller's stream continues only after the helper's chain (also on errors, so that nothing is left racing)
+  if (last_e >= 0) {
+    if (b.Kt >= 2) cudaEventRecord(evP[last_e], crit);     // re-record behind the final COL / panel
+    cudaStreamWaitEvent(st, evP[last_e], 0);
+  }
+  cudaStreamDestroy(crit);                   // queued work still completes
+  cudaEventDestroy(ev0);
+  for (int e = 0; e < 2; ++e) {
+    if (evP[e]) cudaEventDestroy(evP[e]);
+    if (evR[e]) cudaEventDestroy(evR[e]);
+  }
+  return rc;
+}
+}  // namespace
+
 int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
   if (b.batch <= 0) return 0;
   if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine_potrf: bad block layout"); return -1; }
+  // look-ahead pays when a block step does not fill the GPU for long: few matrices, several block columns
+  if (b.Kt >= 8 && (long)b.batch * b.Kt < 1024) return potrf_lookahead(b, st, launches, stable_panel);
   EngineArgs g = make_args(b);
   for (int k = 0; k < b.Kt; ++k) {
     g.step = k;
     NMGP_TRY(engine_diag_step(b, k, st, launches, stable_panel));
     const int r = b.Kt - k - 1;
-    if (stable_panel) {
-      if (r > 0) {
-        dim3 pg(r, b.batch < 65535 ? b.batch : 65535);
-        constexpr size_t kTrsmSmem = 2ull * NB * (NB + 1) * sizeof(double);
-        static bool trsm_configured = false;
-        if (!trsm_configured) {
-          NMGP_CUDA_TRY(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
-          trsm_configured = true;
-        }
-        trsm_panel_kernel<<<pg, NB, kTrsmSmem, st>>>(g);
-        NMGP_CUDA_TRY(cudaGetLastError());
-        if (launches) ++*launches;
-      }
-    } else {
-      NMGP_TRY(launch_tiles<POTRF_PANEL>(g, r, st, launches));
-    }
+    NMGP_TRY(launch_panel(b, g, r, stable_panel, st, launches));
     NMGP_TRY(launch_tiles<POTRF_SYRK>(g, r * (r + 1) / 2, st, launches));
   }
   return 0;
