@@ -12,6 +12,8 @@
 // inside MultivariateNormal at logpos.py:274,279,358,365.
 #include "engine.cuh"
 
+#include <cstdlib>
+
 namespace nmgp {
 
 namespace {
@@ -194,6 +196,56 @@ __global__ void __launch_bounds__(256) symmetrize_kernel(EngineArgs g) {
   }
 }
 
+// Trailing update by a PANEL of nkb block columns at once:  A(i,j) -= sum_{kb} A(i,kb0+kb) A(j,kb0+kb)^T, accumulated in
+// registers over the panel, so the C tile is read and written once per panel instead of once per block column (the rank-64
+// update is memory-bound: 4 flop/B).  TRI: all tiles i >= j >= ja (tri_decode);  !TRI: the columns ja <= j < jb only.
+template <bool TRI>
+__global__ void __launch_bounds__(TILE_THREADS) syrk_wide_kernel(EngineArgs g, int ja, int jb, int kb0, int nkb) {
+  extern __shared__ __align__(16) double smem[];
+  double* SA = smem;
+  double* SB = smem + NB * LDS;
+  int i, j;
+  if (TRI) {
+    int a, b;
+    tri_decode(blockIdx.x, a, b);
+    i = ja + a; j = ja + b;
+  } else {
+    int t = blockIdx.x;
+    j = ja;
+    while (j < jb - 1 && t >= g.Kt - j) { t -= g.Kt - j; ++j; }
+    i = j + t;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
+  for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
+    double* Am = g.A + (long)mat * g.strideA;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      load_tile(SA, Am + ((long)i * NB) * g.ld + (long)(kb0 + kb) * NB, g.ld);
+      load_tile(SB, Am + ((long)j * NB) * g.ld + (long)(kb0 + kb) * NB, g.ld);
+      __syncthreads();
+      warp_mma<true, true>(SA, SB, m0, n0, acc);
+      __syncthreads();
+    }
+    double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
+    const int r = lane >> 2, c = 2 * (lane & 3);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double2* p = reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * g.ld + n0 + 8 * b + c);
+        double2 v = *p;
+        v.x -= acc[a][b][0];
+        v.y -= acc[a][b][1];
+        *p = v;
+      }
+  }
+}
+
 // Backward-stable panel solve  X L_kk^T = A(i,k)  by substitution (one thread per row), used instead of the
 // multiply-by-inverse POTRF_PANEL when the matrix is ill-conditioned (GP-prior covariances, cond ~ 1e10):
 // multiplying by an explicit inverse of the diagonal block inflates the backward error by cond(L_kk).
@@ -269,16 +321,41 @@ int launch_panel(const BlockBatch& b, const EngineArgs& g, int r, bool stable_pa
   return 0;
 }
 
-// Right-looking potrf with a one-step look-ahead.  For a handful of matrices every block step is a chain of three dependent
-// kernels -- diagonal block (33 us for one matrix: 64 dependent pivots), panel, trailing update (memory-bound rank-64) -- and
-// the chain, not the arithmetic, sets the time (n = 5000: 79 steps x 74 us).  The trailing update is split: the next block
-// column alone (COL) and everything to the right of it (REST).  The chain diag -> panel -> COL runs on a HIGH-priority
-// helper stream, REST on the caller's stream, so that the next step's diagonal block and panel run beside REST and their few
-// CTAs are scheduled ahead of REST's thousands.  (The caller's stream usually has the lowest priority already, which is why
-// the chain, not REST, moves to the helper.)  Orderings: REST(k) after panel(k) [evP]; COL(k+1) after REST(k) [evR], because
-// both update the tiles of block column k+2; the caller's stream finally waits for the helper [evP of the last step].
+template <bool TRI>
+int launch_syrk_wide(const EngineArgs& g, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches) {
+  int ntiles = 0;
+  if (TRI) { const int r = g.Kt - ja; ntiles = r * (r + 1) / 2; }
+  else for (int j = ja; j < jb; ++j) ntiles += g.Kt - j;
+  if (ntiles <= 0 || nkb <= 0 || g.batch <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    NMGP_CUDA_TRY(cudaFuncSetAttribute(syrk_wide_kernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    configured = true;
+  }
+  dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
+  syrk_wide_kernel<TRI><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g, ja, jb, kb0, nkb);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+// Right-looking potrf for a handful of large matrices: panels of W block columns with a look-ahead.
+//
+// Every block column is a chain of dependent kernels -- diagonal block (19 us for one matrix: 64 dependent pivots), panel,
+// update of what the next diagonal block needs -- and the chain, not the arithmetic, sets the time (n = 5000 started at
+// 79 steps x 74 us, profiles/r01_c3_chain.txt).  Two measures:
+//  * the trailing matrix is updated once per PANEL (rank 64 W, accumulated in registers) instead of once per block column:
+//    the rank-64 update is memory-bound (4 flop/B), the C tiles dominate its traffic;
+//  * look-ahead: the chain (diag -> panel -> in-panel update, then the update of the NEXT panel's columns) runs on a
+//    HIGH-priority helper stream, the rest of the trailing update (REST) on the caller's stream beside the next panel's
+//    chain.  (The caller's stream usually has the lowest priority already, which is why the chain, not REST, moves.)
+// Orderings: REST(P) after panel P is complete [evP]; NEXT(P+1) after REST(P) [evR], because both update the columns of
+// panel P+2; the caller's stream finally waits for the helper.
 int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool stable_panel) {
   EngineArgs g = make_args(b);
+  const int Kt = b.Kt;
+  int W = Kt >= 128 ? 8 : 2;   // measured (profiles/r01_potrf_panel_width.txt): n = 5000 is chain-bound for any W, n = 16 384 gains up to W = 8
+  if (const char* ev = getenv("NMGP_POTRF_W")) { const int w = atoi(ev); if (w >= 1 && w <= 16) W = w; }   // A/B timing
   int least = 0, greatest = 0;
   cudaDeviceGetStreamPriorityRange(&least, &greatest);
   cudaStream_t crit = nullptr;
@@ -290,31 +367,38 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
          cudaEventCreateWithFlags(&evR[e], cudaEventDisableTiming) == cudaSuccess;
   int rc = ok ? 0 : -2;
   if (!ok) set_last_error("engine_potrf: creating the look-ahead events failed");
-  auto cu = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) { rc = -2; set_last_error(std::string("engine_potrf look-ahead: ") + cudaGetErrorString(e)); } return rc == 0; };
+  auto cu = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == 0) { rc = -2; set_last_error(std::string("engine_potrf look-ahead: ") + cudaGetErrorString(e)); }
+    return rc == 0;
+  };
   if (rc == 0) { cu(cudaEventRecord(ev0, st)); cu(cudaStreamWaitEvent(crit, ev0, 0)); }   // after whatever built the matrices
   bool rest_pending = false;
-  int last_e = -1;
-  for (int k = 0; rc == 0 && k < b.Kt; ++k) {
-    g.step = k;
-    const int r = b.Kt - k - 1, e = k & 1;
-    if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
-    if ((rc = launch_panel(b, g, r, stable_panel, crit, launches))) break;
-    if (!cu(cudaEventRecord(evP[e], crit))) break;
+  int last_e = -1, panel = 0;
+  for (int p0 = 0; rc == 0 && p0 < Kt; p0 += W, ++panel) {
+    const int p1 = p0 + W < Kt ? p0 + W : Kt, e = panel & 1;
+    for (int k = p0; rc == 0 && k < p1; ++k) {
+      g.step = k;
+      if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
+      if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches))) break;
+      if (k + 1 < p1) rc = launch_syrk_wide<false>(g, k + 1, p1, k, 1, crit, launches);   // rest of this panel, rank 64
+    }
+    if (rc != 0 || !cu(cudaEventRecord(evP[e], crit))) break;
     last_e = e;
-    if (r <= 0) break;
-    if (rest_pending && !cu(cudaStreamWaitEvent(crit, evR[e ^ 1], 0))) break;      // REST(k-1) done
-    if ((rc = launch_tiles<POTRF_SYRK_COL>(g, r, crit, launches))) break;
+    if (p1 >= Kt) break;
+    if (rest_pending && !cu(cudaStreamWaitEvent(crit, evR[e ^ 1], 0))) break;              // REST(P-1) done
     rest_pending = false;
-    if (r > 1) {
+    const int n1 = p1 + W < Kt ? p1 + W : Kt;
+    if ((rc = launch_syrk_wide<false>(g, p1, n1, p0, p1 - p0, crit, launches))) break;     // NEXT: the next panel's columns
+    if (n1 < Kt) {
       if (!cu(cudaStreamWaitEvent(st, evP[e], 0))) break;
-      if ((rc = launch_tiles<POTRF_SYRK_REST>(g, (r - 1) * r / 2, st, launches))) break;
+      if ((rc = launch_syrk_wide<true>(g, n1, Kt, p0, p1 - p0, st, launches))) break;      // REST
       if (!cu(cudaEventRecord(evR[e], st))) break;
       rest_pending = true;
     }
   }
   // the caller's stream continues only after the helper's chain (also on errors, so that nothing is left racing)
   if (last_e >= 0) {
-    if (b.Kt >= 2) cudaEventRecord(evP[last_e], crit);     // re-record behind the final COL / panel
+    cudaEventRecord(evP[last_e], crit);
     cudaStreamWaitEvent(st, evP[last_e], 0);
   }
   cudaStreamDestroy(crit);                   // queued work still completes
