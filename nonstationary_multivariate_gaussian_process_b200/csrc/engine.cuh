@@ -58,11 +58,13 @@ int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launch
 // largest number of 64-blocks per side for which the Takahashi recursion of engine_potri_ll is used (see api.cu)
 constexpr int kTakahashiMaxBlocks = 16;
 
-// Heuristic: the left-looking path launches (Kt - k) * batch CTAs per block column, each a long K loop; it needs about
-// two waves of them (148 SMs x 3 resident CTAs) on average to keep the tensor pipes busy.  Measured on B200: n = 16 384
-// with batch 8 is 1.6x faster left-looking, batch 1 is 1.5x faster right-looking (profiles/r01_configs_h.txt).
+// Heuristic: the left-looking path launches (Kt - k) * batch CTAs per block column, each a long K loop; it needs a few
+// waves of them (148 SMs x 4 resident CTAs) to keep the tensor pipes busy.  Below that the right-looking path with panels and
+// look-ahead (engine.cu) is ahead.  Measured on B200, potrf only (profiles/r01_potrf_panel_width.txt): n = 16 384: batch 8
+// equal (404 ms), batch 4 right-looking 206 vs 236 ms, batch 1 54 ms; n = 4096 batch 16: 16.7 vs 17.2 ms; n = 2048 batch 64:
+// left-looking 7.9 vs 9.0 ms.
 inline bool prefer_left_looking(const BlockBatch& b) {
-  return b.Pbuf != nullptr && (b.batch >= 96 || (long)b.batch * b.Kt >= 1024);
+  return b.Pbuf != nullptr && (b.batch >= 96 || (long)b.batch * b.Kt >= 2048);
 }
 
 }  // namespace nmgp
