@@ -36,44 +36,56 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Conditional moments of one GP prior at G new inputs per subject (prediction.py:1060-1068 tilde_l, :1070-1081 uL):
 //   k = alpha^2 exp(-0.5 |(x - x*)/beta|^2),  w = L^-1 k (forward substitution with the plan's cached factor),
 //   mean_t = mu + w . z_t with z_t = L^-1 (v_t - mu) (already formed for the prior density),  sigma2 = (jitter + alpha^2) - w . w,
-//   negative sigma2 -> 1e-6.  One thread per (subject, new input); its w lives in scratch [N][G] (coalesced over g).
+//   negative sigma2 -> 1e-6.  One WARP per (subject, new input): w lives in shared memory, row i of L is read coalesced and
+//   the lanes split its dot product with w[0..i) (N dependent steps of a 5-shuffle reduction instead of N^2/2 serial FMAs).
 __global__ void __launch_bounds__(128) pred_prior_kernel(const double* __restrict__ x, const double* __restrict__ Lp,
                                                          const double* __restrict__ Z, int N, int nv,
                                                          const double* __restrict__ xstar, int G, double alpha2,
-                                                         double beta, double mu, double* __restrict__ Wscr,
-                                                         double* __restrict__ mean_out, double* __restrict__ s2_out) {
-  const int g = blockIdx.x * 128 + threadIdx.x;
+                                                         double beta, double mu, double* __restrict__ mean_out,
+                                                         double* __restrict__ s2_out) {
+  extern __shared__ __align__(16) double psm[];
+  const int wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * wpb + (threadIdx.x >> 5);
   const int c = blockIdx.y;
   if (g >= G) return;
+  double* w = psm + (size_t)(threadIdx.x >> 5) * N;
   const double* xs = x + (long)c * N;
   const double* L = Lp + (long)c * N * N;
-  double* W = Wscr + (long)c * N * G + g;
   const double b = xstar[(long)c * G + g] / beta;                       // kernels.py:38-39
+  for (int i = lane; i < N; i += 32) {
+    const double a = xs[i] / beta;
+    w[i] = __dmul_rn(exp(__dmul_rn(-0.5, ref_sqdist(a, b))), alpha2);
+  }
+  __syncwarp();
   double ww = 0.0;
   for (int i = 0; i < N; ++i) {
-    const double a = xs[i] / beta;
-    double s0 = __dmul_rn(exp(__dmul_rn(-0.5, ref_sqdist(a, b))), alpha2), s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const double* Li = L + (long)i * N;
-    int j = 0;
-    for (; j + 3 < i; j += 4) {
-      s0 -= Li[j] * W[(long)j * G];
-      s1 -= Li[j + 1] * W[(long)(j + 1) * G];
-      s2 -= Li[j + 2] * W[(long)(j + 2) * G];
-      s3 -= Li[j + 3] * W[(long)(j + 3) * G];
+    double s0 = 0.0, s1 = 0.0;
+    int j = lane;
+    for (; j + 32 < i; j += 64) {
+      s0 += Li[j] * w[j];
+      s1 += Li[j + 32] * w[j + 32];
     }
-    for (; j < i; ++j) s0 -= Li[j] * W[(long)j * G];
-    const double w = ((s0 + s1) + (s2 + s3)) / Li[i];
-    W[(long)i * G] = w;
-    ww += w * w;
+    if (j < i) s0 += Li[j] * w[j];
+    const double s = warp_sum(s0 + s1);
+    const double wi = (w[i] - s) / Li[i];
+    __syncwarp();
+    if (lane == 0) w[i] = wi;
+    __syncwarp();
+    ww += wi * wi;
   }
-  double s2v = __dadd_rn(kJitter, alpha2) - ww;                         // RBF_cov(x*)[0,0] - proj . k
-  if (s2v < 0.0) s2v = 1e-6;                                            // settings.precision, prediction.py:1066,1081
-  s2_out[(long)c * G + g] = s2v;
+  if (lane == 0) {
+    double s2v = __dadd_rn(kJitter, alpha2) - ww;                       // RBF_cov(x*)[0,0] - proj . k
+    if (s2v < 0.0) s2v = 1e-6;                                          // settings.precision, prediction.py:1066,1081
+    s2_out[(long)c * G + g] = s2v;
+  }
   const double* Zc = Z + (long)c * N * nv;
   for (int t = 0; t < nv; ++t) {
     double m = 0.0;
-    for (int i = 0; i < N; ++i) m += W[(long)i * G] * Zc[(long)i * nv + t];
-    mean_out[((long)c * G + g) * nv + t] = mu + m;
+    for (int i = lane; i < N; i += 32) m += w[i] * Zc[(long)i * nv + t];
+    m = warp_sum(m);
+    if (lane == 0) mean_out[((long)c * G + g) * nv + t] = mu + m;
   }
 }
 
@@ -370,14 +382,24 @@ __global__ void __launch_bounds__(128) pred_finish_sep_kernel(const double* __re
     if (launches) ++*launches;              \
   } while (0)
 
-size_t predict_prior_scratch_per_subject(int N, int G) { return (size_t)N * G; }
+size_t predict_prior_scratch_per_subject(int N, int G) { (void)N; (void)G; return 1; }   // w lives in shared memory
 
 int launch_predict_prior(const double* x, const double* Lp, const double* Z, int cs, int N, int nv, const double* xstar,
                          int G, double alpha, double beta, double mu, double* scratch, double* mean_out, double* s2_out,
                          cudaStream_t st, long* launches) {
+  (void)scratch;
   if (cs <= 0 || G <= 0) return 0;
-  dim3 grid((G + 127) / 128, cs);
-  pred_prior_kernel<<<grid, 128, 0, st>>>(x, Lp, Z, N, nv, xstar, G, alpha * alpha, beta, mu, scratch, mean_out, s2_out);
+  int wpb = 4;                                                 // warps per CTA, limited by their w vectors in shared memory
+  while (wpb > 1 && (size_t)wpb * N * sizeof(double) > 200u * 1024u) wpb >>= 1;
+  const size_t smem = (size_t)wpb * N * sizeof(double);
+  if (smem > 227u * 1024u) { set_last_error("predict: N too large for the prior-conditional kernel"); return -1; }
+  static size_t configured = 0;
+  if (smem > 48u * 1024u && smem > configured) {
+    NMGP_CUDA_TRY(cudaFuncSetAttribute(pred_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((G + wpb - 1) / wpb, cs);
+  pred_prior_kernel<<<grid, 32 * wpb, smem, st>>>(x, Lp, Z, N, nv, xstar, G, alpha * alpha, beta, mu, mean_out, s2_out);
   NMGP_LAUNCH_CHECK();
   return 0;
 }
