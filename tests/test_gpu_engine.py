@@ -84,3 +84,34 @@ def test_left_and_right_looking_engines_agree(N, M, S, cuda_device):
         dg = np.linalg.norm(res[mode][1] - res["right"][1], axis=1) / np.linalg.norm(res["right"][1], axis=1)
         assert dv.max() < 1e-12, (mode, dv)
         assert dg.max() < 1e-11, (mode, dg)
+
+
+@pytest.mark.parametrize("S", [3, 1200, 4500])
+def test_a_failed_subject_does_not_poison_later_evaluations(S, cuda_device):
+    """A non-finite parameter vector makes one subject's factorisation fail (info > 0, NaN outputs).  The workspace is
+    reused by every later call (and by other subjects of later chunks): the next evaluation with good parameters must be
+    exactly what a fresh plan returns.  n = 600 has a ragged last block, the case where stale tiles are multiplied by zeros."""
+    from nonstationary_multivariate_gaussian_process_b200 import synth
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    N, M = 100, 6
+    hyper = {"mu_tilde_l": 0.0, "alpha_tilde_l": 10.0, "beta_tilde_l": 1.0, "mu_L": 0.0, "alpha_L": 1.0, "beta_L": 1.0,
+             "a": 1e-2, "b": 1e-2}
+    base = [synth.sample_subject(N, M, 300 + s)[:2] + (synth.start_point("nonseparable", N, M, 300 + s, 0.05),)
+            for s in range(3)]
+    xs = np.stack([base[s % 3][0] for s in range(S)])
+    Ys = np.stack([base[s % 3][1] for s in range(S)])
+    ps = np.stack([base[s % 3][2] for s in range(S)])
+    good = torch.from_numpy(ps).cuda()
+    bad = good.clone()
+    bad[1, 5] = float("nan")
+    bad[S - 1, -1] = float("inf")
+    plan = LogPosteriorPlan("nonseparable", xs, Ys, hyper)
+    v0, g0, i0 = plan.value_and_grad(good)
+    vb, gb, ib = plan.value_and_grad(bad)
+    assert int(ib[1]) != 0 and int(ib[S - 1]) != 0 and int((ib != 0).sum()) == 2
+    ok = ib == 0
+    assert torch.isnan(vb[1, 0]) and torch.equal(vb[ok], v0[ok]) and torch.equal(gb[ok], g0[ok])   # S = 4500: two chunks share the workspace
+    v1, g1, i1 = plan.value_and_grad(good)
+    plan.close()
+    assert int(i1.abs().sum()) == 0
+    assert torch.equal(v1, v0) and torch.equal(g1, g0)
