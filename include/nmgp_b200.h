@@ -117,6 +117,22 @@ int nmgp_adam_step(double* pars_dev, const double* grad_dev, double* m_dev, doub
                    const unsigned char* frozen_dev, long S, long P, double lr, double beta1, double beta2, double eps,
                    long step, void* stream);
 
+/* Device-resident pieces of Hamiltonian Monte Carlo for all S subjects at once.  The drivers' HMC loops
+ * (Separable_model.py:209-210, Stationary_model_mpiKAISER.py:205-206, Nonseparable_model_mpiKAISER.py:267-270) hand
+ * `potential_func = logpos.nlogpos_obj*` to an external sampler (HMC_Sampler, not part of the reference repository); what a
+ * batched sampler needs from this library besides nmgp_logpost_grad is below, so that positions, momenta and gradients never
+ * leave the GPU (LogPosteriorPlan.hmc_sample composes them).  All pointers are device pointers, [S,P] unless noted.
+ *   nmgp_hmc_kick    p -= step * grad          for subjects with info[s] == 0 (info may be NULL)
+ *   nmgp_hmc_drift   q += eps * p
+ *   nmgp_hmc_accept  per subject: dH = (U[s] + |p0|^2/2) - (vals_prop[s,0] + |p1|^2/2); the proposal is accepted iff
+ *                    failed[s] == 0 (may be NULL), dH is finite and log_u[s] < dH; then q <- q_prop, grad <- grad_prop,
+ *                    U[s] <- vals_prop[s,0].  vals_prop is the [S,NMGP_NVALS] array of nmgp_logpost_grad; accepted [S] out. */
+int nmgp_hmc_kick(double* p_dev, const double* grad_dev, const int* info_dev, long S, long P, double step, void* stream);
+int nmgp_hmc_drift(double* q_dev, const double* p_dev, long S, long P, double eps, void* stream);
+int nmgp_hmc_accept(double* q_dev, const double* q_prop_dev, double* grad_dev, const double* grad_prop_dev, double* U_dev,
+                    const double* vals_prop_dev, const double* p0_dev, const double* p1_dev, const int* failed_dev,
+                    const double* log_u_dev, int* accepted_dev, long S, long P, void* stream);
+
 /* ---------------------------------------------------------------- posterior prediction (nonseparable model) ----
  * Stand-ins for the device work inside `point_/pointwise_/test_predmap_inhomogeneous_sampling`
  * (Utility/prediction.py:1038-1262; callers Nonseparable_Model/Nonseparable_model.py:377,387,399).  The reference draws,

@@ -103,6 +103,12 @@ def _declare(lib):
     lib.nmgp_adam_step.restype = c.c_int
     lib.nmgp_adam_step.argtypes = [dp, dp, dp, dp, ip, dp, c.c_long, c.c_long, c.c_double, c.c_double, c.c_double,
                                    c.c_double, c.c_long, vp]
+    lib.nmgp_hmc_kick.restype = c.c_int
+    lib.nmgp_hmc_kick.argtypes = [dp, dp, ip, c.c_long, c.c_long, c.c_double, vp]
+    lib.nmgp_hmc_drift.restype = c.c_int
+    lib.nmgp_hmc_drift.argtypes = [dp, dp, c.c_long, c.c_long, c.c_double, vp]
+    lib.nmgp_hmc_accept.restype = c.c_int
+    lib.nmgp_hmc_accept.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, ip, dp, ip, c.c_long, c.c_long, vp]
     lib.nmgp_predict_prior_moments.restype = c.c_int
     lib.nmgp_predict_prior_moments.argtypes = [c.c_void_p, dp, dp, c.c_int, dp, dp, dp, dp, vp]
     lib.nmgp_predict_moments.restype = c.c_int
@@ -124,7 +130,7 @@ def _declare(lib):
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
-           "nmgp_plan_block", "nmgp_adam_step", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
+           "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 
 

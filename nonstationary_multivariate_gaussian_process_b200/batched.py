@@ -211,6 +211,67 @@ class LogPosteriorPlan:
                 _lib.check(rc, "nmgp_adam_step")
         return p, (torch.stack(trace) if trace else torch.empty((0, self.S, _lib.NVALS), device=self.device)), info
 
+    # ------------------------------------------------------------------ device-resident HMC
+    def hmc_sample(self, pars0, sample_size: int, step_size: float, num_steps_in_leap: int, momenta=None, log_uniforms=None,
+                   seed: int | None = None, keep_every: int = 1):
+        """Hamiltonian Monte Carlo with potential `nlogpos_obj*` for all S subjects at once (independent chains), entirely on
+        the device -- what the drivers' `HMC_Sampler.HMC_sampler.sampler(sample_size, potential_func, init_position, step_size,
+        num_steps_in_leap, duplicate_samples=True, ...).main_hmc_loop()` does per subject (Separable_model.py:209-210,
+        Nonseparable_model_mpiKAISER.py:267-270): per sample a standard-normal momentum, `num_steps_in_leap` leapfrog steps of
+        size `step_size` (half kicks at both ends), Metropolis accept with a rejected proposal duplicating the current state.
+        One batched value+gradient evaluation per leapfrog step; positions, momenta and gradients never cross PCIe.
+        momenta [sample_size,S,P] / log_uniforms [sample_size,S] may be supplied (tests); else drawn on the device from `seed`.
+        Returns (samples [sample_size // keep_every, S, P] CUDA, accept_rate [S] CUDA, potential [S] CUDA)."""
+        torch = _lib.require_cuda()
+        f64 = torch.float64
+        q = torch.as_tensor(pars0, dtype=f64).to(self.device).reshape(self.S, self.P).clone().contiguous()
+        gen = None
+        if momenta is None or log_uniforms is None:
+            gen = torch.Generator(device=self.device)
+            gen.manual_seed(0 if seed is None else int(seed))
+        vals, grad, info = self.value_and_grad(q)
+        if int(info.abs().sum()) != 0:
+            raise _lib.NmgpError("hmc_sample: the initial position of some subject is not valid (info != 0)")
+        U = vals[:, 0].clone().contiguous()
+        grad = grad.clone().contiguous()
+        accepted = torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        n_acc = torch.zeros((self.S,), dtype=f64, device=self.device)
+        samples = []
+        eps, L = float(step_size), int(num_steps_in_leap)
+        if L < 1 or keep_every < 1:
+            raise ValueError("hmc_sample needs num_steps_in_leap >= 1 and keep_every >= 1")
+        lib, S, P = self.lib, self.S, self.P
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            for it in range(sample_size):
+                if momenta is not None:
+                    p0 = torch.as_tensor(momenta[it], dtype=f64).to(self.device).reshape(S, P).contiguous()
+                else:
+                    p0 = torch.randn((S, P), dtype=f64, device=self.device, generator=gen)
+                if log_uniforms is not None:
+                    lu = torch.as_tensor(log_uniforms[it], dtype=f64).to(self.device).reshape(S).contiguous()
+                else:
+                    lu = torch.log(torch.rand((S,), dtype=f64, device=self.device, generator=gen))
+                p = p0.clone()
+                qp = q.clone()
+                failed = torch.zeros((S,), dtype=torch.int32, device=self.device)
+                _lib.check(lib.nmgp_hmc_kick(p.data_ptr(), grad.data_ptr(), None, S, P, 0.5 * eps, stream), "nmgp_hmc_kick")
+                vp = gp = None
+                for l in range(L):
+                    _lib.check(lib.nmgp_hmc_drift(qp.data_ptr(), p.data_ptr(), S, P, eps, stream), "nmgp_hmc_drift")
+                    vp, gp, ip = self.value_and_grad(qp)
+                    failed |= (ip != 0).to(torch.int32)
+                    _lib.check(lib.nmgp_hmc_kick(p.data_ptr(), gp.data_ptr(), ip.data_ptr(), S, P,
+                                                 eps if l + 1 < L else 0.5 * eps, stream), "nmgp_hmc_kick")
+                _lib.check(lib.nmgp_hmc_accept(q.data_ptr(), qp.data_ptr(), grad.data_ptr(), gp.data_ptr(), U.data_ptr(),
+                                               vp.data_ptr(), p0.data_ptr(), p.data_ptr(), failed.data_ptr(), lu.data_ptr(),
+                                               accepted.data_ptr(), S, P, stream), "nmgp_hmc_accept")
+                n_acc += accepted.to(f64)
+                if (it + 1) % keep_every == 0:
+                    samples.append(q.clone())
+        out = torch.stack(samples) if samples else torch.empty((0, S, P), dtype=f64, device=self.device)
+        return out, n_acc / max(sample_size, 1), U
+
     # ------------------------------------------------------------------ posterior prediction (nonseparable model)
     def _xstar(self, xstar):
         torch = _lib.require_cuda()

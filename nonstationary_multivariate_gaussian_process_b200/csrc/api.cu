@@ -217,6 +217,58 @@ __global__ void __launch_bounds__(256) adam_kernel(double* __restrict__ pars, co
   }
 }
 
+// ---- Hamiltonian Monte Carlo pieces (the drivers' HMC loops call an external sampler with potential_func = nlogpos_obj*:
+// Separable_model.py:209-210, Nonseparable_model_mpiKAISER.py:267-270): leapfrog updates and the accept step for all subjects
+__global__ void __launch_bounds__(256) hmc_kick_kernel(double* __restrict__ p, const double* __restrict__ grad,
+                                                       const int* __restrict__ info, long S, long P, double step) {
+  const long total = S * P;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    if (info && info[idx / P] != 0) continue;
+    p[idx] -= step * grad[idx];
+  }
+}
+
+__global__ void __launch_bounds__(256) hmc_drift_kernel(double* __restrict__ q, const double* __restrict__ p, long total,
+                                                        double eps) {
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x)
+    q[idx] += eps * p[idx];
+}
+
+// one CTA per subject: dH = (U + |p0|^2/2) - (U' + |p1|^2/2); accept iff the proposal is valid and log u < dH
+__global__ void __launch_bounds__(256) hmc_accept_kernel(double* __restrict__ q, const double* __restrict__ q_prop,
+                                                         double* __restrict__ grad, const double* __restrict__ grad_prop,
+                                                         double* __restrict__ U, const double* __restrict__ vals_prop,
+                                                         const double* __restrict__ p0, const double* __restrict__ p1,
+                                                         const int* __restrict__ failed, const double* __restrict__ log_u,
+                                                         int* __restrict__ accepted, long P) {
+  __shared__ double scratch[40];
+  __shared__ int acc_s;
+  const long s = blockIdx.x;
+  double k0 = 0.0, k1 = 0.0;
+  for (long j = threadIdx.x; j < P; j += blockDim.x) {
+    const double a = p0[s * P + j], b = p1[s * P + j];
+    k0 += a * a;
+    k1 += b * b;
+  }
+  const double K0 = 0.5 * block_sum(k0, scratch);
+  const double K1 = 0.5 * block_sum(k1, scratch);
+  if (threadIdx.x == 0) {
+    const double Up = vals_prop[s * NMGP_NVALS];
+    const double dH = (U[s] + K0) - (Up + K1);
+    const bool ok = (!failed || failed[s] == 0) && Up == Up && dH == dH && log_u[s] < dH;
+    acc_s = ok ? 1 : 0;
+    accepted[s] = acc_s;
+    if (ok) U[s] = Up;
+  }
+  __syncthreads();
+  if (acc_s) {
+    for (long j = threadIdx.x; j < P; j += blockDim.x) {
+      q[s * P + j] = q_prop[s * P + j];
+      grad[s * P + j] = grad_prop[s * P + j];
+    }
+  }
+}
+
 __global__ void pack_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, long strideA, int ld) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = blockIdx.y;
@@ -719,6 +771,40 @@ int nmgp_predict_moments(nmgp_plan* pl, const double* pars, const double* xstar,
                                    mu_f + (size_t)s0 * C * M, s2_y + (size_t)s0 * C * M, st, &launches));
   }
   pl->last_launches = launches;
+  return 0;
+}
+
+int nmgp_hmc_kick(double* p, const double* grad, const int* info, long S, long P, double step, void* stream) {
+  if (!p || !grad || S < 0 || P <= 0) { set_last_error("nmgp_hmc_kick: bad arguments"); return NMGP_EINVAL; }
+  if (S == 0) return 0;
+  long blocks = (S * P + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  hmc_kick_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, grad, info, S, P, step);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int nmgp_hmc_drift(double* q, const double* p, long S, long P, double eps, void* stream) {
+  if (!q || !p || S < 0 || P <= 0) { set_last_error("nmgp_hmc_drift: bad arguments"); return NMGP_EINVAL; }
+  if (S == 0) return 0;
+  long blocks = (S * P + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  hmc_drift_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(q, p, S * P, eps);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int nmgp_hmc_accept(double* q, const double* q_prop, double* grad, const double* grad_prop, double* U, const double* vals_prop,
+                    const double* p0, const double* p1, const int* failed, const double* log_u, int* accepted, long S,
+                    long P, void* stream) {
+  if (!q || !q_prop || !grad || !grad_prop || !U || !vals_prop || !p0 || !p1 || !log_u || !accepted || S < 0 || P <= 0) {
+    set_last_error("nmgp_hmc_accept: bad arguments");
+    return NMGP_EINVAL;
+  }
+  if (S == 0) return 0;
+  hmc_accept_kernel<<<(unsigned)S, 256, 0, (cudaStream_t)stream>>>(q, q_prop, grad, grad_prop, U, vals_prop, p0, p1, failed,
+                                                                   log_u, accepted, P);
+  NMGP_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
