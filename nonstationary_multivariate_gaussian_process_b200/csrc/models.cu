@@ -76,7 +76,7 @@ __global__ void extract_factor_kernel(const double* __restrict__ A, long strideA
 // substitution -- the arithmetic MultivariateNormal.log_prob and its autograd backward do (logpos.py:274,279,358,365):
 //   TRANS=0:  L   X = rhs   (forward, blocks ascending)        TRANS=1:  L^T X = rhs   (backward, blocks descending)
 // Two kernels per block step, both batched over subjects, so a single large subject still spreads over the GPU:
-//   prior_diag_solve : X_k <- L_kk^-1 X_k  (or L_kk^-T)   one thread per right-hand side, L_kk in shared memory
+//   prior_diag_solve : X_k <- L_kk^-1 X_k  (or L_kk^-T)   one warp per right-hand side, L_kk in shared memory
 //   prior_update     : X_i <- X_i - L(i,k) X_k  for all i > k   (or  X_i - L(k,i)^T X_k, i < k)   one CTA per row block
 constexpr int PBS = 64;   // block rows
 constexpr int PVC = 24;   // right-hand sides per CTA (static shared memory stays under 48 KB)
@@ -101,19 +101,28 @@ __global__ void __launch_bounds__(128) prior_diag_solve_kernel(const double* __r
     Zb[r][v] = Xc[(long)(k0 + r) * nv + v0 + v];
   }
   __syncthreads();
-  if (threadIdx.x < vc) {
-    const int v = threadIdx.x;
-    if (TRANS) {
-      for (int r = rows - 1; r >= 0; --r) {
-        double sacc = Zb[r][v];
-        for (int cc = r + 1; cc < rows; ++cc) sacc -= Ld[cc][r] * Zb[cc][v];
-        Zb[r][v] = sacc / Ld[r][r];
-      }
-    } else {
-      for (int r = 0; r < rows; ++r) {
-        double sacc = Zb[r][v];
-        for (int cc = 0; cc < r; ++cc) sacc -= Ld[r][cc] * Zb[cc][v];
-        Zb[r][v] = sacc / Ld[r][r];
+  // one WARP per right-hand side (the four warps take them round-robin), lanes over the rows: 64 dependent steps of one
+  // shared-memory round trip each instead of one thread's 2048 dependent FMAs (23 us -> ~2 us for a single right-hand side,
+  // which is what the separable model's priors have)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < vc; v += 4) {
+      if (TRANS) {     // L^T x = z, descending: x_r final, then z_i -= L[r][i] x_r for i < r   (row r of L_kk)
+        for (int r = rows - 1; r >= 0; --r) {
+          const double xr = Zb[r][v] / Ld[r][r];
+          __syncwarp();
+          for (int i = lane; i < r; i += 32) Zb[i][v] -= Ld[r][i] * xr;
+          if (lane == 0) Zb[r][v] = xr;
+          __syncwarp();
+        }
+      } else {         // L x = z, ascending: x_r final, then z_i -= L[i][r] x_r for i > r   (column r of L_kk)
+        for (int r = 0; r < rows; ++r) {
+          const double xr = Zb[r][v] / Ld[r][r];
+          __syncwarp();
+          for (int i = r + 1 + lane; i < rows; i += 32) Zb[i][v] -= Ld[i][r] * xr;
+          if (lane == 0) Zb[r][v] = xr;
+          __syncwarp();
+        }
       }
     }
   }
@@ -639,7 +648,11 @@ __device__ void jacobi_eig_warp(double* Bm, double* V, int M, int lds) {
     }
     off = warp_sum(off);
     dg = warp_sum(dg);
-    if (off <= 1e-40 * dg || off == 0.0) break;
+    // Cyclic Jacobi converges quadratically, and rounding keeps sum(off^2) near 1e-31 sum(diag^2) forever: once it is below
+    // 1e-22 one more sweep takes it to that floor, so that sweep is the last.  (The old test, 1e-40, could never be met and
+    // cost all 30 sweeps: 230 us per call, the largest single item of a single-subject separable evaluation.)
+    if (off <= 1e-33 * dg || off == 0.0) break;
+    const bool final_sweep = off <= 1e-22 * dg;
     for (int p = 0; p < M - 1; ++p)
       for (int q = p + 1; q < M; ++q) {
         const double apq = Bm[p * lds + q];
@@ -668,6 +681,7 @@ __device__ void jacobi_eig_warp(double* Bm, double* V, int M, int lds) {
           __syncwarp();
         }
       }
+    if (final_sweep) break;
   }
   __syncwarp();
 }
