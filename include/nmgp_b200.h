@@ -39,6 +39,11 @@ extern "C" {
 #define NMGP_SEPARABLE 1    /* Utility/logpos.py:216-296  nlogpos_obj     */
 #define NMGP_NONSEPARABLE 2 /* Utility/logpos.py:299-380  nlogpos_obj_SVC */
 
+/* irregularly sampled data, one observation (x_n, indx_n, y_n) per row -- the "Hadamard" objectives */
+#define NMGP_HADAMARD 3     /* Utility/logpos.py:465-558  nlogpos_obj_hadamard     (separable)  */
+#define NMGP_HADAMARD_SVC 4 /* Utility/logpos.py:561-637  nlogpos_obj_hadamard_SVC (nonseparable) */
+#define NMGP_HADAMARD_S 5   /* Utility/logpos.py:640-716  nlogpos_obj_hadamard_S   (stationary) */
+
 #define NMGP_NVALS 6
 #define NMGP_NHYPER 9
 
@@ -68,6 +73,16 @@ int nmgp_n_params(int model, int N, int M);
  * memory); subjects are processed in chunks that fit. */
 int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const double* Y_dev,
                      const double* hyper, int prior_flag, size_t workspace_limit_bytes, void* stream);
+
+/* Plan for the Hadamard objectives (model = NMGP_HADAMARD / _SVC / _S): S subjects with N observations each,
+ * x [S,N] inputs, indx [S,N] (int32) the output index 0..M-1 of every observation, y [S,N] the observations, all device
+ * pointers.  Parameter vectors, hyper-parameters and value tuples follow the regularly sampled model of the same family
+ * (pars: logpos.py:479 / :60-72 / :657; the cross-output factor entries are RAW, no exp on the diagonal: logpos.py:518,
+ * 582-583, 682).  The plan is evaluated with nmgp_logpost_grad / _host like any other; the covariance is one dense
+ * N x N matrix per subject, K_x[n,n'] <r_n, r_n'> + sigma2_err I with r_n the row indx_n of the factor at observation n. */
+int nmgp_plan_create_hadamard(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const int* indx_dev,
+                              const double* y_dev, const double* hyper, int prior_flag, size_t workspace_limit_bytes,
+                              void* stream);
 
 int nmgp_plan_destroy(nmgp_plan* plan);
 

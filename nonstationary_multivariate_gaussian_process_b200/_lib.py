@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
-SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "api.cu"]
+SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "hadamard.cu", "api.cu"]
 HEADERS = ["common.cuh", "engine.cuh", "models.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -24,6 +24,7 @@ NHYPER = 9
 NPHASES = 5
 PHASE_NAMES = ("build", "potrf", "potri", "prior_solves", "contract")
 STATIONARY, SEPARABLE, NONSEPARABLE = 0, 1, 2
+HADAMARD, HADAMARD_SVC, HADAMARD_S = 3, 4, 5
 PRED_RAW_FACTOR = 1
 
 _lock = threading.Lock()
@@ -82,6 +83,9 @@ def _declare(lib):
     lib.nmgp_plan_create.restype = c.c_int
     lib.nmgp_plan_create.argtypes = [c.POINTER(c.c_void_p), c.c_int, c.c_int, c.c_int, c.c_int, dp, dp,
                                      c.POINTER(c.c_double), c.c_int, c.c_size_t, vp]
+    lib.nmgp_plan_create_hadamard.restype = c.c_int
+    lib.nmgp_plan_create_hadamard.argtypes = [c.POINTER(c.c_void_p), c.c_int, c.c_int, c.c_int, c.c_int, dp, ip, dp,
+                                              c.POINTER(c.c_double), c.c_int, c.c_size_t, vp]
     lib.nmgp_plan_destroy.restype = c.c_int
     lib.nmgp_plan_destroy.argtypes = [c.c_void_p]
     lib.nmgp_logpost_grad.restype = c.c_int
@@ -128,7 +132,7 @@ def _declare(lib):
     return lib
 
 
-EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_destroy", "nmgp_logpost_grad",
+EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_create_hadamard", "nmgp_plan_destroy", "nmgp_logpost_grad",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
            "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]

@@ -14,7 +14,9 @@ import numpy as np
 
 from . import _lib
 
-MODELS = {"stationary": _lib.STATIONARY, "separable": _lib.SEPARABLE, "nonseparable": _lib.NONSEPARABLE}
+MODELS = {"stationary": _lib.STATIONARY, "separable": _lib.SEPARABLE, "nonseparable": _lib.NONSEPARABLE,
+          "hadamard": _lib.HADAMARD, "hadamard_svc": _lib.HADAMARD_SVC, "hadamard_s": _lib.HADAMARD_S}
+HADAMARD_MODELS = ("hadamard", "hadamard_svc", "hadamard_s")
 
 # keyword order and defaults of the reference signatures (Utility/logpos.py:383, :216, :299)
 HYPER_SPEC = {
@@ -23,9 +25,15 @@ HYPER_SPEC = {
                   ("alpha_tilde_sigma", 1.0), ("beta_tilde_sigma", 1.0), ("a", 1), ("b", 1), ("c", 10)),
     "nonseparable": (("mu_tilde_l", 0.0), ("alpha_tilde_l", 5.0), ("beta_tilde_l", 1.0), ("mu_L", 0.0),
                      ("alpha_L", 5.0), ("beta_L", 1.0), ("a", 1), ("b", 1)),
+    # irregularly sampled variants (Utility/logpos.py:465, :561, :640): same keywords, their own defaults
+    "hadamard": (("mu_tilde_l", 0.0), ("alpha_tilde_l", 1.0), ("beta_tilde_l", 1.0), ("mu_tilde_sigma", 0.0),
+                 ("alpha_tilde_sigma", 1.0), ("beta_tilde_sigma", 1.0), ("a", 1), ("b", 1), ("c", 10)),
+    "hadamard_svc": (("mu_tilde_l", 0.0), ("alpha_tilde_l", 1.0), ("beta_tilde_l", 1.0), ("mu_L", 0.0),
+                     ("alpha_L", 1.0), ("beta_L", 1.0), ("a", 1), ("b", 1)),
+    "hadamard_s": (("mu_tilde_l", None), ("sigma_tilde_l", None), ("a", 1), ("b", 1), ("c", 10)),
 }
 # number of entries of the reference's verbose tuple (value + components)
-N_VERBOSE = {"stationary": 5, "separable": 6, "nonseparable": 5}
+N_VERBOSE = {"stationary": 5, "separable": 6, "nonseparable": 5, "hadamard": 6, "hadamard_svc": 5, "hadamard_s": 5}
 
 
 def hyper_vector(model: str, hyper: Mapping[str, float]) -> np.ndarray:
@@ -44,14 +52,18 @@ def hyper_vector(model: str, hyper: Mapping[str, float]) -> np.ndarray:
 
 def n_params(model: str, N: int, M: int) -> int:
     T = M * (M + 1) // 2
-    return {"stationary": T + 3, "separable": 2 * N + T + 1, "nonseparable": N + N * T + 1}[model]
+    return {"stationary": T + 3, "separable": 2 * N + T + 1, "nonseparable": N + N * T + 1,
+            "hadamard": 2 * N + T + 1, "hadamard_svc": N + N * T + 1, "hadamard_s": T + 3}[model]
 
 
 class LogPosteriorPlan:
     """Evaluation plan for S subjects of equal shape (N time points, M outputs) on one GPU."""
 
     def __init__(self, model: str, x, Y, hyper: Mapping[str, float] | None = None, prior: bool = True,
-                 device=None, workspace_limit_bytes: int = 0):
+                 device=None, workspace_limit_bytes: int = 0, indx=None, M: int | None = None):
+        """x [S,N] (or [N]); Y [S,N,M] (or [N,M]).  Hadamard models ('hadamard', 'hadamard_svc', 'hadamard_s': one
+        observation per row): Y is y [S,N] (or [N]), indx [S,N] the output index of every observation, M the number of
+        outputs (default: the number of distinct indices, as the reference counts it, logpos.py:478)."""
         torch = _lib.require_cuda()
         if model not in MODELS:
             raise ValueError(f"unknown model '{model}' (expected one of {sorted(MODELS)})")
@@ -60,11 +72,24 @@ class LogPosteriorPlan:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         x_t = torch.as_tensor(x, dtype=torch.float64)
         Y_t = torch.as_tensor(Y, dtype=torch.float64)
+        had = model in HADAMARD_MODELS
+        ix_t = None
         if x_t.dim() == 1:
             x_t, Y_t = x_t.unsqueeze(0), Y_t.unsqueeze(0)
-        if x_t.dim() != 2 or Y_t.dim() != 3 or Y_t.shape[:2] != x_t.shape:
-            raise ValueError(f"expected x [S,N] and Y [S,N,M]; got {tuple(x_t.shape)} and {tuple(Y_t.shape)}")
-        self.S, self.N, self.M = int(Y_t.shape[0]), int(Y_t.shape[1]), int(Y_t.shape[2])
+        if had:
+            if indx is None:
+                raise ValueError("the Hadamard models need indx (the output index of every observation)")
+            ix_t = torch.as_tensor(indx).to(torch.int64).reshape(x_t.shape)
+            if Y_t.shape != x_t.shape:
+                raise ValueError(f"expected x, indx, y of equal shape [S,N]; got {tuple(x_t.shape)} and {tuple(Y_t.shape)}")
+            n_out = int(M) if M is not None else int(torch.unique(ix_t).numel())
+            if int(ix_t.min()) < 0 or int(ix_t.max()) >= n_out:
+                raise ValueError("indx must hold output indices 0 .. M-1")
+            self.S, self.N, self.M = int(x_t.shape[0]), int(x_t.shape[1]), n_out
+        else:
+            if x_t.dim() != 2 or Y_t.dim() != 3 or Y_t.shape[:2] != x_t.shape:
+                raise ValueError(f"expected x [S,N] and Y [S,N,M]; got {tuple(x_t.shape)} and {tuple(Y_t.shape)}")
+            self.S, self.N, self.M = int(Y_t.shape[0]), int(Y_t.shape[1]), int(Y_t.shape[2])
         if self.N < 1 or self.M < 1 or self.M > 16:
             raise ValueError("need N >= 1 and 1 <= M <= 16")
         self.P = n_params(model, self.N, self.M)
@@ -76,11 +101,19 @@ class LogPosteriorPlan:
             xd = x_t.to(self.device).contiguous()
             Yd = Y_t.to(self.device).contiguous()
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            rc = self.lib.nmgp_plan_create(
-                ctypes.byref(self._handle), MODELS[model], self.S, self.N, self.M, xd.data_ptr(), Yd.data_ptr(),
-                hv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(self.prior), int(workspace_limit_bytes),
-                ctypes.c_void_p(stream))
-            _lib.check(rc, "nmgp_plan_create")
+            if had:
+                ixd = ix_t.to(torch.int32).to(self.device).contiguous()
+                rc = self.lib.nmgp_plan_create_hadamard(
+                    ctypes.byref(self._handle), MODELS[model], self.S, self.N, self.M, xd.data_ptr(), ixd.data_ptr(),
+                    Yd.data_ptr(), hv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(self.prior),
+                    int(workspace_limit_bytes), ctypes.c_void_p(stream))
+                _lib.check(rc, "nmgp_plan_create_hadamard")
+            else:
+                rc = self.lib.nmgp_plan_create(
+                    ctypes.byref(self._handle), MODELS[model], self.S, self.N, self.M, xd.data_ptr(), Yd.data_ptr(),
+                    hv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(self.prior), int(workspace_limit_bytes),
+                    ctypes.c_void_p(stream))
+                _lib.check(rc, "nmgp_plan_create")
         self._pinned = None
 
     # ------------------------------------------------------------------ properties

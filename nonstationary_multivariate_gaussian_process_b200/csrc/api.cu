@@ -34,6 +34,7 @@ struct nmgp_plan {
   long last_launches = 0;
   // persistent
   double *x = nullptr, *Y = nullptr;
+  int* indx = nullptr;                      // [S][N] output index of every observation (Hadamard objectives only)
   double *Wp0 = nullptr, *Wp1 = nullptr;    // [S][N][N] lower Cholesky factors of the prior covariances
   double *hld0 = nullptr, *hld1 = nullptr;  // [S] half log-determinants
   // chunk workspace
@@ -83,6 +84,7 @@ int dev_alloc(nmgp_plan* pl, Tp** out, size_t count) {
 
 HyperConst make_hyper_const(int model, const double* hy, int prior) {
   HyperConst h{};
+  if (model >= NMGP_HADAMARD) model = model == NMGP_HADAMARD ? NMGP_SEPARABLE : (model == NMGP_HADAMARD_SVC ? NMGP_NONSEPARABLE : NMGP_STATIONARY);
   h.prior = prior ? 1 : 0;
   h.half_log2pi = std::log(std::sqrt(2.0 * M_PI));
   double a = 1, b = 1, c = 10;
@@ -112,7 +114,9 @@ HyperConst make_hyper_const(int model, const double* hy, int prior) {
 size_t per_subject_bytes(const nmgp_plan* pl) {
   const size_t N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat, nP = pl->nP, Kt = pl->Kt;
   const size_t MT = pl->model == NMGP_NONSEPARABLE ? padded_M(pl->M) : 0;
-  size_t d = 0;
+  const bool had = pl->model >= NMGP_HADAMARD;
+  size_t d = had ? 5 * N * 16 : 0;     // row factors and the four gradient tables of the Hadamard objectives
+  if (had) d += 3 * N * (size_t)pl->nv1;
   d += 2 * nm * nP * nP;        // A, A2
   d += 3 * nm * Kt * kNB * kNB; // Dinv (W and W^T), Pbuf
   d += nm;                      // logdet
@@ -129,6 +133,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
 int alloc_workspace(nmgp_plan* pl) {
   const size_t cs = pl->chunk, N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat;
   const bool svc = pl->model == NMGP_NONSEPARABLE;
+  const bool had = pl->model >= NMGP_HADAMARD;
   const size_t MT = svc ? padded_M(pl->M) : 0;
   BlockBatch& b = pl->bb;
   b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
@@ -147,15 +152,15 @@ int alloc_workspace(nmgp_plan* pl) {
   NMGP_TRY(dev_alloc(pl, &w.ell, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.sig, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.s2, cs));
-  NMGP_TRY(dev_alloc(pl, &w.Lst, svc ? cs * n * MT : cs * M * M));
+  NMGP_TRY(dev_alloc(pl, &w.Lst, svc ? cs * n * MT : (had ? cs * N * 16 : cs * M * M)));
   NMGP_TRY(dev_alloc(pl, &w.Kx, cs * N * N));
   NMGP_TRY(dev_alloc(pl, &w.CK, cs * N * N));
   NMGP_TRY(dev_alloc(pl, &w.alpha, cs * nm * n));
-  NMGP_TRY(dev_alloc(pl, &w.yv, svc ? 1 : cs * nm * n));
-  NMGP_TRY(dev_alloc(pl, &w.Wout, svc ? cs * n * MT : cs * N * M));
-  NMGP_TRY(dev_alloc(pl, &w.Vout, svc ? cs * n * MT : cs * N * M));
-  NMGP_TRY(dev_alloc(pl, &w.Sa, svc ? cs * N * MT : 1));
-  NMGP_TRY(dev_alloc(pl, &w.Ca, svc ? cs * N * MT : 1));
+  NMGP_TRY(dev_alloc(pl, &w.yv, (svc || had) ? 1 : cs * nm * n));
+  NMGP_TRY(dev_alloc(pl, &w.Wout, svc ? cs * n * MT : (had ? cs * N * 16 : cs * N * M)));
+  NMGP_TRY(dev_alloc(pl, &w.Vout, svc ? cs * n * MT : (had ? cs * N * 16 : cs * N * M)));
+  NMGP_TRY(dev_alloc(pl, &w.Sa, svc ? cs * N * MT : (had ? cs * N * 16 : 1)));
+  NMGP_TRY(dev_alloc(pl, &w.Ca, svc ? cs * N * MT : (had ? cs * N * 16 : 1)));
   NMGP_TRY(dev_alloc(pl, &w.Ua, svc ? cs * N * MT : 1));
   NMGP_TRY(dev_alloc(pl, &w.gl, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.gs, cs * N));
@@ -340,6 +345,9 @@ int nmgp_n_params(int model, int N, int M) {
     case NMGP_STATIONARY: return T + 3;
     case NMGP_SEPARABLE: return 2 * N + T + 1;
     case NMGP_NONSEPARABLE: return N + N * T + 1;
+    case NMGP_HADAMARD: return 2 * N + T + 1;       // vec2pars(pars, N, M), logpos.py:479
+    case NMGP_HADAMARD_SVC: return N + N * T + 1;   // vec2pars_hadamard_SVC, logpos.py:60-72
+    case NMGP_HADAMARD_S: return T + 3;             // vec2pars_S, logpos.py:657
     default: return NMGP_EINVAL;
   }
 }
@@ -360,6 +368,10 @@ int nmgp_plan_destroy(nmgp_plan* pl) {
   return 0;
 }
 
+static int plan_create_impl(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const double* Y_dev,
+                            const int* indx_dev, const double* hyper, int prior_flag, size_t workspace_limit_bytes,
+                            void* stream);
+
 int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const double* Y_dev,
                      const double* hyper, int prior_flag, size_t workspace_limit_bytes, void* stream) {
   if (!out) return NMGP_EINVAL;
@@ -368,6 +380,25 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
     set_last_error("nmgp_plan_create: bad arguments (need 0<=model<=2, S>=0, N>=1, 1<=M<=16, non-null x/Y/hyper)");
     return NMGP_EINVAL;
   }
+  return plan_create_impl(out, model, S, N, M, x_dev, Y_dev, nullptr, hyper, prior_flag, workspace_limit_bytes, stream);
+}
+
+int nmgp_plan_create_hadamard(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const int* indx_dev,
+                              const double* y_dev, const double* hyper, int prior_flag, size_t workspace_limit_bytes,
+                              void* stream) {
+  if (!out) return NMGP_EINVAL;
+  *out = nullptr;
+  if (model < NMGP_HADAMARD || model > NMGP_HADAMARD_S || S < 0 || N <= 0 || M <= 0 || M > 16 || !hyper ||
+      (S > 0 && (!x_dev || !indx_dev || !y_dev))) {
+    set_last_error("nmgp_plan_create_hadamard: bad arguments (need 3<=model<=5, S>=0, N>=1, 1<=M<=16, non-null x/indx/y/hyper)");
+    return NMGP_EINVAL;
+  }
+  return plan_create_impl(out, model, S, N, M, x_dev, y_dev, indx_dev, hyper, prior_flag, workspace_limit_bytes, stream);
+}
+
+static int plan_create_impl(nmgp_plan** out, int model, int S, int N, int M, const double* x_dev, const double* Y_dev,
+                            const int* indx_dev, const double* hyper, int prior_flag, size_t workspace_limit_bytes,
+                            void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   nmgp_plan* pl = new (std::nothrow) nmgp_plan();
   if (!pl) return NMGP_ENOMEM;
@@ -377,12 +408,14 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
   std::memcpy(pl->hyper, hyper, sizeof(pl->hyper));
   pl->hc = make_hyper_const(model, hyper, prior_flag);
   const bool svc = model == NMGP_NONSEPARABLE;
-  pl->nmat = svc ? 1 : M;
+  const bool had = model >= NMGP_HADAMARD;          // one N x N matrix per subject, one observation per row
+  const int ycols = had ? 1 : M;
+  pl->nmat = (svc || had) ? 1 : M;
   pl->n = svc ? N * M : N;
   pl->nP = padded_dim(pl->n);
   pl->Kt = pl->nP / kNB;
-  pl->nprior = model == NMGP_STATIONARY ? 0 : 2;
-  pl->nv1 = svc ? pl->T : 1;
+  pl->nprior = (model == NMGP_STATIONARY || model == NMGP_HADAMARD_S) ? 0 : 2;
+  pl->nv1 = (svc || model == NMGP_HADAMARD_SVC) ? pl->T : 1;
   int rc = 0;
   do {
     if (S == 0) { pl->chunk = 0; break; }
@@ -391,10 +424,16 @@ int nmgp_plan_create(nmgp_plan** out, int model, int S, int N, int M, const doub
     // persistent state
     const size_t SN = (size_t)S * N;
     if ((rc = dev_alloc(pl, &pl->x, SN))) break;
-    if ((rc = dev_alloc(pl, &pl->Y, SN * M))) break;
+    if ((rc = dev_alloc(pl, &pl->Y, SN * ycols))) break;
     if (cudaMemcpyAsync(pl->x, x_dev, SN * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
-        cudaMemcpyAsync(pl->Y, Y_dev, SN * M * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        cudaMemcpyAsync(pl->Y, Y_dev, SN * ycols * sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
       set_last_error("nmgp_plan_create: copying x/Y failed"); rc = NMGP_ECUDA; break;
+    }
+    if (had) {
+      if ((rc = dev_alloc(pl, &pl->indx, SN))) break;
+      if (cudaMemcpyAsync(pl->indx, indx_dev, SN * sizeof(int), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_last_error("nmgp_plan_create_hadamard: copying indx failed"); rc = NMGP_ECUDA; break;
+      }
     }
     if (pl->nprior) {
       if ((rc = dev_alloc(pl, &pl->Wp0, SN * N))) break;
@@ -516,7 +555,9 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     BlockBatch b = pl->bb;
     b.batch = cs * pl->nmat;
     const double* xs = pl->x + (size_t)s0 * N;
-    const double* Ys = pl->Y + (size_t)s0 * N * M;
+    const bool had = pl->model >= NMGP_HADAMARD;
+    const double* Ys = pl->Y + (size_t)s0 * N * (had ? 1 : M);
+    const int* ixs = had ? pl->indx + (size_t)s0 * N : nullptr;
     const double* ps = pars + (size_t)s0 * P;
     double* vs = vals + (size_t)s0 * NMGP_NVALS;
     double* gs = grad ? grad + (size_t)s0 * P : nullptr;
@@ -524,7 +565,9 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     const int ci = s0 / pl->chunk;
     if (sync && sync->before) NMGP_CUDA_TRY(cudaStreamWaitEvent(st, sync->before[ci], 0));
     NMGP_MARK(0);
-    if (pl->model == NMGP_NONSEPARABLE) {
+    if (had) {
+      NMGP_TRY(had_forward(pl->model - NMGP_HADAMARD, cs, N, M, xs, ixs, ps, P, pl->hc, pl->w, b, st, &launches));
+    } else if (pl->model == NMGP_NONSEPARABLE) {
       NMGP_TRY(svc_forward(cs, N, M, xs, ps, P, pl->hc, pl->w, b, st, &launches));
     } else {
       NMGP_TRY(sep_forward(pl->model, cs, N, M, xs, Ys, ps, P, pl->hc, pl->w, b, st, &launches));
@@ -562,7 +605,10 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     NMGP_MARK(4);
     const double* h0 = pl->hld0 ? pl->hld0 + s0 : nullptr;
     const double* h1 = pl->hld1 ? pl->hld1 + s0 : nullptr;
-    if (pl->model == NMGP_NONSEPARABLE) {
+    if (had) {
+      NMGP_TRY(had_backward(pl->model - NMGP_HADAMARD, cs, N, M, Ys, ixs, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st,
+                            &launches));
+    } else if (pl->model == NMGP_NONSEPARABLE) {
       NMGP_TRY(svc_backward(cs, N, M, Ys, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
     } else {
       NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
@@ -666,7 +712,7 @@ static int ensure_pred_scratch(nmgp_plan* pl, size_t per_subject, int cs) {
 
 int nmgp_predict_prior_moments(nmgp_plan* pl, const double* pars, const double* xstar, int G, double* mu_l, double* s2_l,
                                double* mu_uL, double* s2_uL, void* stream) {
-  if (!pl || pl->nprior != 2 || G < 0 || (pl->S > 0 && G > 0 && (!pars || !xstar || !mu_l || !s2_l || !mu_uL || !s2_uL))) {
+  if (!pl || (pl->model != NMGP_SEPARABLE && pl->model != NMGP_NONSEPARABLE) || G < 0 || (pl->S > 0 && G > 0 && (!pars || !xstar || !mu_l || !s2_l || !mu_uL || !s2_uL))) {
     set_last_error("nmgp_predict_prior_moments: needs a separable or nonseparable plan and non-null buffers");
     return NMGP_EINVAL;
   }
@@ -711,7 +757,7 @@ int nmgp_predict_prior_moments(nmgp_plan* pl, const double* pars, const double* 
 int nmgp_predict_moments_sep(nmgp_plan* pl, const double* pars, const double* xstar, int G, int n_sample,
                              const double* tl_star, const double* ts_star, double* mu_f, double* quad, int* info,
                              void* stream) {
-  if (!pl || pl->model == NMGP_NONSEPARABLE || G < 0 || n_sample < 0 ||
+  if (!pl || (pl->model != NMGP_STATIONARY && pl->model != NMGP_SEPARABLE) || G < 0 || n_sample < 0 ||
       (pl->S > 0 && G > 0 && n_sample > 0 && (!pars || !xstar || !tl_star || !ts_star || !mu_f || !quad))) {
     set_last_error("nmgp_predict_moments_sep: needs a stationary or separable plan and non-null buffers");
     return NMGP_EINVAL;

@@ -1065,6 +1065,15 @@ int launch_reduce_info(const int* info_mat, int cs, int nmat, int* info_out, cud
   return 0;
 }
 
+int launch_kx(const double* x, const double* ell, const double* sig, int cs, int N, double* Kx, double* CK, cudaStream_t st,
+              long* launches) {
+  if (cs <= 0) return 0;
+  dim3 gk((N + 127) / 128, N, cs);
+  kx_kernel<<<gk, 128, 0, st>>>(x, ell, sig, N, Kx, CK);
+  NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_svc_prep(int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w, cudaStream_t st,
                     long* launches) {
   if (cs <= 0) return 0;

@@ -76,6 +76,9 @@ int launch_nonseparable_cov_reference_order(const double* x, const double* pars,
 // pieces of the nonseparable pass used on their own by the prediction path
 int launch_svc_prep(int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w, cudaStream_t st,
                     long* launches);   // pars -> ell, Lst, s2, prior residuals R0 / R1
+// Gibbs kernel (with jitter) and its tilde_l log-derivative for `cs` subjects: Kx, CK [cs][N][N]; sig may be NULL (= ones)
+int launch_kx(const double* x, const double* ell, const double* sig, int cs, int N, double* Kx, double* CK, cudaStream_t st,
+              long* launches);
 int launch_reduce_info(const int* info_mat, int cs, int nmat, int* info_out, cudaStream_t st, long* launches);
 int launch_symv(const BlockBatch& b, int n, const double* y, double* alpha, int batch, cudaStream_t st, long* launches);
 
@@ -108,5 +111,13 @@ int sep_forward(int model, int cs, int N, int M, const double* x, const double* 
 int sep_backward(int model, int cs, int N, int M, const double* pars, int P, const HyperConst& h, const Scratch& w,
                  const BlockBatch& b, const double* hld0, const double* hld1, double* vals, double* grad, int* info,
                  cudaStream_t st, long* launches);
+
+// ---- irregularly sampled ("Hadamard") objectives (Utility/logpos.py:465-716; hadamard.cu).  variant: 0 separable,
+// 1 SVC, 2 stationary.  One N x N matrix per subject; w.Lst holds the row factors [cs][N][16], w.Wout / Vout / Sa / Ca [cs][N][16].
+int had_forward(int variant, int cs, int N, int M, const double* x, const int* indx, const double* pars, int P,
+                const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches);
+int had_backward(int variant, int cs, int N, int M, const double* y, const int* indx, const double* pars, int P,
+                 const HyperConst& h, const Scratch& w, const BlockBatch& b, const double* hld0, const double* hld1,
+                 double* vals, double* grad, int* info, cudaStream_t st, long* launches);
 
 }  // namespace nmgp

@@ -63,15 +63,15 @@ def _fingerprint(t):
     return (a.shape, hash(a.tobytes()))
 
 
-def _get_plan(model, Y, x, hyper, prior):
+def _get_plan(model, Y, x, hyper, prior, indx=None):
     torch = _lib.require_cuda()
     Y = torch.as_tensor(Y, dtype=torch.float64)
     x = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
     key = (model, _fingerprint(Y), _fingerprint(x), tuple(sorted((k, float(v)) for k, v in hyper.items())), bool(prior),
-           torch.cuda.current_device())
+           torch.cuda.current_device(), None if indx is None else _fingerprint(torch.as_tensor(indx)))
     plan = _PLAN_CACHE.get(key)
     if plan is None:
-        plan = LogPosteriorPlan(model, x, Y, hyper, prior=prior)
+        plan = LogPosteriorPlan(model, x, Y, hyper, prior=prior, indx=indx)
         _PLAN_CACHE[key] = plan
         while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
             _, old = _PLAN_CACHE.popitem(last=False)
@@ -131,8 +131,8 @@ def _evaluate(plan, pars):
     return _FN.apply(p.reshape(plan.S, plan.P), plan)
 
 
-def _single(model, pars, Y, x, hyper, verbose, Prior):
-    plan = _get_plan(model, Y, x, hyper, Prior)
+def _single(model, pars, Y, x, hyper, verbose, Prior, indx=None):
+    plan = _get_plan(model, Y, x, hyper, Prior, indx)
     vals, _ = _evaluate(plan, pars)
     if not verbose:
         return vals[0, 0]
@@ -194,6 +194,87 @@ def logpos_SVC(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde
     pars = torch.cat([tilde_l.reshape(-1), uL_vecs.reshape(-1), tilde_sigma2_err.reshape(1)])
     return _positive(nlogpos_obj_SVC(pars, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b,
                                      verbose, Prior), verbose)
+
+
+# ------------------------------------------------------------------------------------- irregular sampling ("Hadamard")
+def vec2pars_hadamard_SVC(pars, N, M):
+    """(logpos.py:60-72)"""
+    T = M * (M + 1) // 2
+    return pars[:N], pars[N:N + N * T], pars[-1]
+
+
+def generate_vectorized_indexes(indx1, indx2):
+    """All (i, j) index pairs of two index vectors, row-major (logpos.py:75-86)."""
+    torch = _lib.require_cuda()
+    n1, n2 = indx1.shape[0], indx2.shape[0]
+    return (indx1.reshape(-1, 1).repeat(1, n2).reshape(-1).to(torch.int64), indx2.repeat(n1).to(torch.int64))
+
+
+def generate_K_index(B_f, indx):
+    """K_i[n,n'] = B_f[indx_n, indx_n'] (logpos.py:89-99)."""
+    torch = _lib.require_cuda()
+    ix = torch.as_tensor(indx).to(torch.int64)
+    return B_f[ix][:, ix]
+
+
+def generate_K_index_SVC_hadamard0(L_f_list, indexes):
+    """K_i[n,n'] = <L_n[indx_n,:], L_n'[indx_n',:]> (logpos.py:114-116)."""
+    torch = _lib.require_cuda()
+    L = torch.stack([L_f[int(i), :] for L_f, i in zip(L_f_list, indexes)])
+    return L @ L.t()
+
+
+generate_K_index_SVC_hadamard = generate_K_index_SVC_hadamard0   # same matrix, entry by entry (logpos.py:119-131)
+
+
+def nlogpos_obj_hadamard(pars, x, indx, y, mu_tilde_l=0., alpha_tilde_l=1., beta_tilde_l=1., mu_tilde_sigma=0.,
+                         alpha_tilde_sigma=1., beta_tilde_sigma=1., a=1, b=1, c=10, verbose=False, Prior=True):
+    """Separable model, irregular sampling: -log posterior [, loglik, lp_tilde_l, lp_tilde_sigma, lp_L, lp_sigma2]
+    (logpos.py:465-500)."""
+    hyper = dict(mu_tilde_l=mu_tilde_l, alpha_tilde_l=alpha_tilde_l, beta_tilde_l=beta_tilde_l,
+                 mu_tilde_sigma=mu_tilde_sigma, alpha_tilde_sigma=alpha_tilde_sigma, beta_tilde_sigma=beta_tilde_sigma,
+                 a=a, b=b, c=c)
+    return _single("hadamard", pars, y, x, hyper, verbose, Prior, indx)
+
+
+def nlogpos_obj_hadamard_SVC(pars, x, indx, y, mu_tilde_l=0., alpha_tilde_l=1., beta_tilde_l=1., mu_L=0., alpha_L=1.,
+                             beta_L=1., a=1, b=1, verbose=False, Prior=True):
+    """Nonseparable model, irregular sampling: -log posterior [, loglik, lp_tilde_l, lp_L, lp_sigma2] (logpos.py:561-579)."""
+    hyper = dict(mu_tilde_l=mu_tilde_l, alpha_tilde_l=alpha_tilde_l, beta_tilde_l=beta_tilde_l, mu_L=mu_L, alpha_L=alpha_L,
+                 beta_L=beta_L, a=a, b=b)
+    return _single("hadamard_svc", pars, y, x, hyper, verbose, Prior, indx)
+
+
+def nlogpos_obj_hadamard_S(pars, x, indx, y, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, verbose=False, Prior=True):
+    """Stationary model, irregular sampling: -log posterior [, loglik, lp_tilde_l, lp_L, lp_sigma2] (logpos.py:640-652)."""
+    hyper = dict(mu_tilde_l=mu_tilde_l, sigma_tilde_l=sigma_tilde_l, a=a, b=b, c=c)
+    return _single("hadamard_s", pars, y, x, hyper, verbose, Prior, indx)
+
+
+def logpos_hadamard(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l,
+                    mu_tilde_sigma, alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose=False, Prior=True):
+    """(logpos.py:503-558)"""
+    torch = _lib.require_cuda()
+    pars = torch.cat([tilde_l.reshape(-1), tilde_sigma.reshape(-1), L_vec.reshape(-1), tilde_sigma2_err.reshape(1)])
+    return _positive(nlogpos_obj_hadamard(pars, x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_tilde_sigma,
+                                          alpha_tilde_sigma, beta_tilde_sigma, a, b, c, verbose, Prior), verbose)
+
+
+def logpos_hadamard_SVC(tilde_l, L_vecs, tilde_sigma2_err, x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L,
+                        beta_L, a, b, verbose=False, Prior=True):
+    """(logpos.py:582-637)"""
+    torch = _lib.require_cuda()
+    pars = torch.cat([tilde_l.reshape(-1), L_vecs.reshape(-1), tilde_sigma2_err.reshape(1)])
+    return _positive(nlogpos_obj_hadamard_SVC(pars, x, indx, y, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L,
+                                              a, b, verbose, Prior), verbose)
+
+
+def logpos_hadamard_S(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, x, indx, y, mu_tilde_l, sigma_tilde_l, a, b, c,
+                      verbose=False, Prior=True):
+    """(logpos.py:655-716)"""
+    torch = _lib.require_cuda()
+    pars = torch.cat([tilde_l.reshape(1), tilde_sigma.reshape(1), L_vec.reshape(-1), tilde_sigma2_err.reshape(1)])
+    return _positive(nlogpos_obj_hadamard_S(pars, x, indx, y, mu_tilde_l, sigma_tilde_l, a, b, c, verbose, Prior), verbose)
 
 
 # ------------------------------------------------------------------------------------- batched entry points

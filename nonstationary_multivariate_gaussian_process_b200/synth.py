@@ -96,3 +96,27 @@ def start_point(model: str, N: int, M: int, seed: int, noise: float = 0.1):
     else:
         raise ValueError(model)
     return p + noise * rng.standard_normal(p.shape[0])
+
+
+def hadamard_case(model: str, N: int, M: int, seed: int, noise: float = 0.1):
+    """Irregularly sampled data for the Hadamard objectives (Utility/logpos.py:465-716): N observation times, each belonging
+    to ONE of the M outputs (every output present).  Returns x [N], indx [N] (int64), y [N] and a parameter vector in the
+    layout of `model` in {'hadamard', 'hadamard_svc', 'hadamard_s'} whose cross-output factor entries are RAW (these
+    objectives apply no exp to the diagonal, logpos.py:518, 582-583, 682)."""
+    x, Y, _ = sample_subject(N, M, seed)
+    rng = np.random.RandomState(4242 + seed)
+    indx = np.concatenate([np.arange(M), rng.randint(0, M, size=N - M)])
+    rng.shuffle(indx)
+    y = Y[np.arange(N), indx]
+    base = {"hadamard": "separable", "hadamard_svc": "nonseparable", "hadamard_s": "stationary"}[model]
+    p = start_point(base, N, M, seed, noise)
+    T = tril_size(M)
+    d = diag_slots(M)
+    if model == "hadamard_svc":
+        blk = p[N:N + N * T].reshape(N, T)
+        blk[:, d] = np.exp(blk[:, d])
+    else:
+        o = 2 * N if model == "hadamard" else 2
+        blk = p[o:o + T]
+        blk[d] = np.exp(blk[d])
+    return x, indx.astype(np.int64), y, p

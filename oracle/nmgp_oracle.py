@@ -221,6 +221,101 @@ def logpost_stationary(pars, Y, x, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, Pr
     return res, loglik, lp_l, lp_uL, lp_s2
 
 
+# ----------------------------------------------------------------------------- irregular sampling ("Hadamard")
+def inverse_gamma_logpdf_u(s2: torch.Tensor, a: float, b: float) -> torch.Tensor:
+    """(-a-1) log s2 - b/s2, WITHOUT the normaliser: what the Hadamard objectives use (Utility/distributions.py:116-124,
+    call sites logpos.py:555, 650, 708)."""
+    return (-a - 1.0) * torch.log(s2) - b / s2
+
+
+def _hadamard_loglik(y, Kx, Ki, s2):
+    """-0.5 logdet - 0.5 y^T inv(Kx o Ki + s2 I) y with explicit inverse + logdet (logpos.py:524-527, 590-593, 690-693)."""
+    Sigma = Kx * Ki + s2 * torch.eye(y.numel(), dtype=DTYPE)
+    return dense_loglik(y, Sigma)
+
+
+def logpost_hadamard(pars, y, x, indx, mu_tilde_l=0.0, alpha_tilde_l=1.0, beta_tilde_l=1.0, mu_tilde_sigma=0.0,
+                     alpha_tilde_sigma=1.0, beta_tilde_sigma=1.0, a=1, b=1, c=10, Prior=True):
+    """(logpost, loglik, lp_tilde_l, lp_tilde_sigma, lp_L, lp_sigma2) -- logpos.py:503-558.  pars = [tilde_l(N),
+    tilde_sigma(N), L_vec(T) RAW, tilde_sigma2_err]; one observation per row, indx its output."""
+    N = y.numel()
+    M = int(torch.unique(indx).numel())
+    T = tril_size(M)
+    tilde_l, tilde_sigma, L_vec, tilde_s2 = pars[:N], pars[N:2 * N], pars[2 * N:2 * N + T], pars[-1]
+    L = tril_vec_to_matrix(L_vec, M)                                   # vec2lowtriangle(L_vec, M): no exp, logpos.py:518
+    B = L @ L.t()
+    Kx = gibbs_cov(x, torch.exp(tilde_l), torch.exp(tilde_sigma))
+    s2 = torch.exp(tilde_s2)
+    loglik = _hadamard_loglik(y, Kx, B[indx][:, indx], s2)             # generate_K_index, logpos.py:89-99
+    lp_l = mvn_logpdf_full(tilde_l, mu_tilde_l, rbf_cov(x, alpha_tilde_l, beta_tilde_l))
+    lp_sig = mvn_logpdf_full(tilde_sigma, mu_tilde_sigma, rbf_cov(x, alpha_tilde_sigma, beta_tilde_sigma))
+    lp_L = normal_logpdf(L_vec, 0.0, c).sum()
+    lp_s2 = inverse_gamma_logpdf_u(s2, a, b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_sig + lp_L + lp_s2 + tilde_s2
+    return res, loglik, lp_l, lp_sig, lp_L, lp_s2
+
+
+def logpost_hadamard_svc(pars, y, x, indx, mu_tilde_l=0.0, alpha_tilde_l=1.0, beta_tilde_l=1.0, mu_L=0.0, alpha_L=1.0,
+                         beta_L=1.0, a=1, b=1, Prior=True):
+    """(logpost, loglik, lp_tilde_l, lp_L, lp_sigma2) -- logpos.py:582-637.  pars = [tilde_l(N), L_vecs(N*T) RAW,
+    tilde_sigma2_err] (logpos.py:60-72)."""
+    N = y.numel()
+    M = int(torch.unique(indx).numel())
+    T = tril_size(M)
+    tilde_l, L_vecs, tilde_s2 = pars[:N], pars[N:N + N * T], pars[-1]
+    Lm = tril_vec_to_matrix(L_vecs.view(N, T), M)                      # N,M,M, raw entries (logpos.py:582-583)
+    Rows = Lm[torch.arange(N), indx]                                   # row indx_n of L_n  (logpos.py:114-116)
+    Kx = gibbs_cov(x, torch.exp(tilde_l))
+    s2 = torch.exp(tilde_s2)
+    loglik = _hadamard_loglik(y, Kx, Rows @ Rows.t(), s2)
+    lp_l = mvn_logpdf_full(tilde_l, mu_tilde_l, rbf_cov(x, alpha_tilde_l, beta_tilde_l))
+    lp_L = mvn_logpdf_full(L_vecs.view(N, T).t(), mu_L, rbf_cov(x, alpha_L, beta_L)).sum()     # T columns, logpos.py:615-617
+    lp_s2 = inverse_gamma_logpdf_u(s2, a, b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_L + lp_s2 + tilde_s2
+    return res, loglik, lp_l, lp_L, lp_s2
+
+
+def logpost_hadamard_s(pars, y, x, indx, mu_tilde_l, sigma_tilde_l, a=1, b=1, c=10, Prior=True):
+    """(logpost, loglik, lp_tilde_l, lp_L, lp_sigma2) -- logpos.py:655-716.  pars = [tilde_l, tilde_sigma, L_vec(T) RAW,
+    tilde_sigma2_err]; K_x = RBF_cov(x, alpha=sigma, beta=l) (logpos.py:686)."""
+    M = int(torch.unique(indx).numel())
+    T = tril_size(M)
+    tilde_l, tilde_sigma, L_vec, tilde_s2 = pars[0], pars[1], pars[2:2 + T], pars[-1]
+    L = tril_vec_to_matrix(L_vec, M)
+    B = L @ L.t()
+    l, sigma = torch.exp(tilde_l), torch.exp(tilde_sigma)
+    xs = x / l
+    Kx = torch.eye(x.numel(), dtype=DTYPE) * JITTER + torch.exp(-0.5 * sq_dist(xs)) * sigma ** 2      # kernels.py:24-43
+    s2 = torch.exp(tilde_s2)
+    loglik = _hadamard_loglik(y, Kx, B[indx][:, indx], s2)
+    lp_l = normal_logpdf(tilde_l, mu_tilde_l, sigma_tilde_l)
+    lp_L = normal_logpdf(L_vec, 0.0, c).sum()
+    lp_s2 = inverse_gamma_logpdf_u(s2, a, b)
+    res = loglik
+    if Prior:
+        res = res + lp_l + lp_L + lp_s2 + tilde_s2
+    return res, loglik, lp_l, lp_L, lp_s2
+
+
+_HADAMARD = {"hadamard": logpost_hadamard, "hadamard_svc": logpost_hadamard_svc, "hadamard_s": logpost_hadamard_s}
+
+
+def value_and_grad_hadamard(model: str, pars, x, indx, y, **hyper):
+    """The Hadamard objectives the way a driver would call them (verbose=True, then `.backward()`):
+    (vals = [-logpost, loglik, priors...], grad)."""
+    p = torch.as_tensor(pars, dtype=DTYPE).detach().clone().requires_grad_(True)
+    out = _HADAMARD[model](p, torch.as_tensor(y, dtype=DTYPE), torch.as_tensor(x, dtype=DTYPE),
+                           torch.as_tensor(indx).to(torch.int64), **hyper)
+    neg = -out[0]
+    neg.backward()
+    vals = torch.stack([neg.detach()] + [torch.as_tensor(o).detach().reshape(()) for o in out[1:]])
+    return vals, p.grad.detach().clone()
+
+
 _MODELS = {
     "stationary": logpost_stationary,
     "separable": logpost_separable,

@@ -20,7 +20,22 @@ def pytest_configure(config):
 def golden_cases():
     """log-posterior + gradient fixtures (tests/golden/make_golden.py)"""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("predict"))
+                  if not os.path.basename(p).startswith(("predict", "hadamard")))
+
+
+def hadamard_cases():
+    """irregular-sampling ("Hadamard") objective fixtures (tests/golden/make_golden_hadamard.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "hadamard_*.npz")))
+
+
+def load_hadamard_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["model"] = str(d["model"])
+    d["hyper"] = json.loads(str(d["hyper"]))
+    d["prior"] = bool(d["prior"])
+    d["N"], d["M"] = int(d["N"]), int(d["M"])
+    return d
 
 
 def predict_cases():

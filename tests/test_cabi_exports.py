@@ -44,7 +44,9 @@ def test_n_params_needs_no_device(lib):
     assert lib.nmgp_n_params(0, 50, 2) == 3 + 3
     assert lib.nmgp_n_params(1, 200, 5) == 2 * 200 + 15 + 1
     assert lib.nmgp_n_params(2, 100, 6) == 100 + 100 * 21 + 1
-    assert lib.nmgp_n_params(3, 10, 2) < 0 and lib.nmgp_n_params(2, 0, 2) < 0
+    # Hadamard variants: vec2pars / vec2pars_hadamard_SVC / vec2pars_S on N observations (logpos.py:479, 60-72, 657)
+    assert lib.nmgp_n_params(3, 10, 2) == 24 and lib.nmgp_n_params(4, 10, 2) == 41 and lib.nmgp_n_params(5, 10, 2) == 6
+    assert lib.nmgp_n_params(6, 10, 2) < 0 and lib.nmgp_n_params(2, 0, 2) < 0
 
 
 def test_bad_arguments_return_codes_not_exceptions(lib):

@@ -3,7 +3,7 @@ reference (tests/golden/make_golden.py).  CPU-only."""
 import numpy as np
 import pytest
 
-from conftest import (golden_cases, load_golden, load_predict_golden, max_rel, predict_cases, predictsep_cases,
+from conftest import (golden_cases, hadamard_cases, load_golden, load_hadamard_golden, load_predict_golden, max_rel, predict_cases, predictsep_cases,
                       predictstat_cases, rel_err)
 from oracle import nmgp_oracle as O
 
@@ -114,3 +114,14 @@ def test_stationary_predict_oracle_matches_reference_golden(name):
         mu, s2 = PO.stationary_moments(hp[h, 0], hp[h, 1], hp[h, 2:2 + T], hp[h, -1], Y, x, torch.from_numpy(g["grids"]))
         ys.append(np.stack([mu[i] + np.random.randn() * np.sqrt(s2[i]) for i in range(mu.shape[0])]))
     assert max_rel(np.stack(ys), g["hist_y"]) < VAL_TOL
+
+
+@pytest.mark.parametrize("name", hadamard_cases())
+def test_hadamard_oracle_matches_reference_golden(name):
+    """Irregular-sampling objectives (Utility/logpos.py:465-716) restated in oracle/nmgp_oracle.py."""
+    g = load_hadamard_golden(name)
+    vals, grad = O.value_and_grad_hadamard(g["model"], g["pars"], g["x"], g["indx"], g["y"], Prior=g["prior"], **g["hyper"])
+    vals = vals.numpy()
+    for k in range(len(g["vals"])):
+        assert rel_err(vals[k], g["vals"][k]) < VAL_TOL, (name, k, vals[k], g["vals"][k])
+    assert rel_err(grad.numpy(), g["grad"]) < GRAD_TOL, name
