@@ -115,7 +115,7 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   const size_t N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat, nP = pl->nP, Kt = pl->Kt;
   const size_t MT = pl->model == NMGP_NONSEPARABLE ? padded_M(pl->M) : 0;
   const bool had = pl->model >= NMGP_HADAMARD;
-  size_t d = had ? 5 * N * 16 : 0;     // row factors and the four gradient tables of the Hadamard objectives
+  size_t d = had ? 6 * N * 16 : 0;     // row factors (both layouts) and the four gradient tables of the Hadamard objectives
   if (had) d += 3 * N * (size_t)pl->nv1;
   d += 2 * nm * nP * nP;        // A, A2
   d += 3 * nm * Kt * kNB * kNB; // Dinv (W and W^T), Pbuf
@@ -161,7 +161,7 @@ int alloc_workspace(nmgp_plan* pl) {
   NMGP_TRY(dev_alloc(pl, &w.Vout, svc ? cs * n * MT : (had ? cs * N * 16 : cs * N * M)));
   NMGP_TRY(dev_alloc(pl, &w.Sa, svc ? cs * N * MT : (had ? cs * N * 16 : 1)));
   NMGP_TRY(dev_alloc(pl, &w.Ca, svc ? cs * N * MT : (had ? cs * N * 16 : 1)));
-  NMGP_TRY(dev_alloc(pl, &w.Ua, svc ? cs * N * MT : 1));
+  NMGP_TRY(dev_alloc(pl, &w.Ua, svc ? cs * N * MT : (had ? cs * N * 16 : 1)));
   NMGP_TRY(dev_alloc(pl, &w.gl, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.gs, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.lam, cs * M));

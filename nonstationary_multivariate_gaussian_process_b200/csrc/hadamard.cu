@@ -33,7 +33,7 @@ __device__ __forceinline__ void tril_unrank(int t, int& m, int& k) {
 __global__ void had_prep_kernel(int variant, const double* __restrict__ pars, int P, int N, int M,
                                 const int* __restrict__ indx, double mu0, double mu1, double* __restrict__ ell,
                                 double* __restrict__ sig, double* __restrict__ s2, double* __restrict__ R,
-                                double* __restrict__ R0, double* __restrict__ R1) {
+                                double* __restrict__ Rt, double* __restrict__ R0, double* __restrict__ R1) {
   const int c = blockIdx.x;
   const int T = tril_size(M);
   const double* p = pars + (long)c * P;
@@ -47,25 +47,29 @@ __global__ void had_prep_kernel(int variant, const double* __restrict__ pars, in
     if (variant == 0) R1[(long)c * N + n] = ts - mu1;
     const double* Lv = variant == 0 ? p + 2 * N : (variant == 1 ? p + N + (long)n * T : p + 2);
     const int m = indx[(long)c * N + n];
-    for (int k = 0; k < RM; ++k) R[((long)c * N + n) * RM + k] = (k <= m && m < M) ? Lv[m * (m + 1) / 2 + k] : 0.0;
+    for (int k = 0; k < RM; ++k) {
+      const double r = (k <= m && m < M) ? Lv[m * (m + 1) / 2 + k] : 0.0;
+      R[((long)c * N + n) * RM + k] = r;                 // [n][k]: a row at a time (finish kernel)
+      Rt[((long)c * RM + k) * N + n] = r;                // [k][n]: coalesced over the observations (build, contraction)
+    }
   }
   if (variant == 1)
     for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) R1[(long)c * N * T + idx] = p[N + idx] - mu1;
 }
 
 // Sigma in the engine's padded layout (both triangles, identity padding)
-__global__ void had_build_kernel(const double* __restrict__ Kx, const double* __restrict__ R, const double* __restrict__ s2v,
-                                 int N, int M, double* __restrict__ A, long strideA, int ld) {
+__global__ void had_build_kernel(const double* __restrict__ Kx, const double* __restrict__ R, const double* __restrict__ Rt,
+                                 const double* __restrict__ s2v, int N, int M, double* __restrict__ A, long strideA, int ld) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = blockIdx.y;
   const int c = blockIdx.z;
   if (q >= ld) return;
   double v;
   if (p < N && q < N) {
-    const double* rp = R + ((long)c * N + p) * RM;
-    const double* rq = R + ((long)c * N + q) * RM;
+    const double* rp = R + ((long)c * N + p) * RM;          // uniform over the warp
+    const double* rq = Rt + (long)c * RM * N + q;             // coalesced
     double ki = 0.0;
-    for (int k = 0; k < M; ++k) ki += rp[k] * rq[k];
+    for (int k = 0; k < M; ++k) ki += rp[k] * rq[(long)k * N];
     v = Kx[((long)c * N + p) * N + q] * ki;
     if (p == q) v += s2v[c];
   } else {
@@ -79,7 +83,7 @@ __global__ void had_build_kernel(const double* __restrict__ Kx, const double* __
 template <int PASS>
 __global__ void __launch_bounds__(256) had_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N, int M,
                                                            const double* __restrict__ y, const double* __restrict__ Kx,
-                                                           const double* __restrict__ CK, const double* __restrict__ R,
+                                                           const double* __restrict__ CK, const double* __restrict__ Rt,
                                                            double* __restrict__ alpha, double* __restrict__ Wo,
                                                            double* __restrict__ Vo) {
   const int c = blockIdx.y;
@@ -89,23 +93,38 @@ __global__ void __launch_bounds__(256) had_contract_kernel(const double* __restr
   const double* zr = A + (long)c * strideA + (long)n * ld;
   const double* kr = Kx + ((long)c * N + n) * N;
   const double* cr = CK + ((long)c * N + n) * N;
-  const double* Rc = R + (long)c * N * RM;
+  const double* Rc = Rt + (long)c * RM * N;
   const double* al = alpha + (long)c * N;
   const double* yc = y + (long)c * N;
   double w[RM], v[RM], a = 0.0;
 #pragma unroll
   for (int k = 0; k < RM; ++k) w[k] = v[k] = 0.0;
-  for (int j = lane; j < N; j += 32) {
-    const double z = PASS == 0 ? zr[j] : al[j];
-    if (PASS == 0) a += z * yc[j];
-    const double zk = z * kr[j], zc = z * cr[j];
+  // the row is streamed once from HBM by this warp alone: four 32-wide slices are loaded before any arithmetic so that
+  // enough bytes are in flight (one slice per iteration ran at 1 TB/s)
+  for (int j0 = 0; j0 < N; j0 += 128) {
+    double z[4], zk[4], zc[4];
 #pragma unroll
-    for (int k = 0; k < RM; ++k)
-      if (k < M) {
-        const double r = Rc[(long)j * RM + k];
-        w[k] += zk * r;
-        v[k] += zc * r;
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      const bool ok = j < N;
+      z[u] = ok ? (PASS == 0 ? zr[j] : al[j]) : 0.0;
+      zk[u] = ok ? kr[j] : 0.0;
+      zc[u] = ok ? cr[j] : 0.0;
+      if (PASS == 0 && ok) a += z[u] * yc[j];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      if (j >= N) continue;
+      const double wk = z[u] * zk[u], wc = z[u] * zc[u];
+#pragma unroll
+      for (int k = 0; k < RM; ++k)
+        if (k < M) {
+          const double r = Rc[(long)k * N + j];
+          w[k] += wk * r;
+          v[k] += wc * r;
+        }
+    }
   }
   if (PASS == 0) {
     a = warp_sum(a);
@@ -257,11 +276,11 @@ __global__ void __launch_bounds__(256) had_finish_kernel(
 int had_forward(int variant, int cs, int N, int M, const double* x, const int* indx, const double* pars, int P,
                 const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
-  had_prep_kernel<<<cs, 256, 0, st>>>(variant, pars, P, N, M, indx, h.mu0, h.mu1, w.ell, w.sig, w.s2, w.Lst, w.R0, w.R1);
+  had_prep_kernel<<<cs, 256, 0, st>>>(variant, pars, P, N, M, indx, h.mu0, h.mu1, w.ell, w.sig, w.s2, w.Lst, w.Ua, w.R0, w.R1);
   NMGP_LAUNCH_CHECK();
   NMGP_TRY(launch_kx(x, w.ell, w.sig, cs, N, w.Kx, w.CK, st, launches));
   dim3 gb((b.nP + 127) / 128, b.nP, cs);
-  had_build_kernel<<<gb, 128, 0, st>>>(w.Kx, w.Lst, w.s2, N, M, b.A, b.strideA(), b.nP);
+  had_build_kernel<<<gb, 128, 0, st>>>(w.Kx, w.Lst, w.Ua, w.s2, N, M, b.A, b.strideA(), b.nP);
   NMGP_LAUNCH_CHECK();
   return 0;
 }
@@ -271,10 +290,10 @@ int had_backward(int variant, int cs, int N, int M, const double* y, const int* 
                  double* vals, double* grad, int* info, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   dim3 gc((N + 7) / 8, cs);
-  had_contract_kernel<0><<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, y, w.Kx, w.CK, w.Lst, w.alpha, w.Wout, w.Vout);
+  had_contract_kernel<0><<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, y, w.Kx, w.CK, w.Ua, w.alpha, w.Wout, w.Vout);
   NMGP_LAUNCH_CHECK();
   if (grad != nullptr) {
-    had_contract_kernel<1><<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, y, w.Kx, w.CK, w.Lst, w.alpha, w.Sa, w.Ca);
+    had_contract_kernel<1><<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, y, w.Kx, w.CK, w.Ua, w.alpha, w.Sa, w.Ca);
     NMGP_LAUNCH_CHECK();
   }
   had_finish_kernel<<<cs, 256, 0, st>>>(variant, N, M, P, pars, y, indx, h, b.A, b.strideA(), b.nP, b.logdet, b.info, w.alpha,

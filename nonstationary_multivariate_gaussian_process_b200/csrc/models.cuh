@@ -113,7 +113,8 @@ int sep_backward(int model, int cs, int N, int M, const double* pars, int P, con
                  cudaStream_t st, long* launches);
 
 // ---- irregularly sampled ("Hadamard") objectives (Utility/logpos.py:465-716; hadamard.cu).  variant: 0 separable,
-// 1 SVC, 2 stationary.  One N x N matrix per subject; w.Lst holds the row factors [cs][N][16], w.Wout / Vout / Sa / Ca [cs][N][16].
+// 1 SVC, 2 stationary.  One N x N matrix per subject; w.Lst holds the row factors [cs][N][16], w.Ua their transpose
+// [cs][16][N], w.Wout / Vout / Sa / Ca the gradient tables [cs][N][16].
 int had_forward(int variant, int cs, int N, int M, const double* x, const int* indx, const double* pars, int P,
                 const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches);
 int had_backward(int variant, int cs, int N, int M, const double* y, const int* indx, const double* pars, int P,
