@@ -356,17 +356,30 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
   const int Kt = b.Kt;
   int W = Kt >= 128 ? 8 : 2;   // measured (profiles/r01_potrf_panel_width.txt): n = 5000 is chain-bound for any W, n = 16 384 gains up to W = 8
   if (const char* ev = getenv("NMGP_POTRF_W")) { const int w = atoi(ev); if (w >= 1 && w <= 16) W = w; }   // A/B timing
-  int least = 0, greatest = 0;
-  cudaDeviceGetStreamPriorityRange(&least, &greatest);
-  cudaStream_t crit = nullptr;
-  cudaEvent_t evP[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr}, ev0 = nullptr;
-  NMGP_CUDA_TRY(cudaStreamCreateWithPriority(&crit, cudaStreamNonBlocking, greatest));
-  bool ok = cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming) == cudaSuccess;
-  for (int e = 0; e < 2 && ok; ++e)
-    ok = cudaEventCreateWithFlags(&evP[e], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&evR[e], cudaEventDisableTiming) == cudaSuccess;
-  int rc = ok ? 0 : -2;
-  if (!ok) set_last_error("engine_potrf: creating the look-ahead events failed");
+  // helper stream and events: created once per (host thread, device) and reused by every call
+  struct Helper {
+    int device = -1;
+    cudaStream_t crit = nullptr;
+    cudaEvent_t evP[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr}, ev0 = nullptr;
+  };
+  static thread_local Helper hp[16];
+  int dev = 0;
+  NMGP_CUDA_TRY(cudaGetDevice(&dev));
+  Helper& H = hp[dev & 15];
+  if (H.device != dev) {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    bool made = cudaStreamCreateWithPriority(&H.crit, cudaStreamNonBlocking, greatest) == cudaSuccess &&
+                cudaEventCreateWithFlags(&H.ev0, cudaEventDisableTiming) == cudaSuccess;
+    for (int e = 0; e < 2 && made; ++e)
+      made = cudaEventCreateWithFlags(&H.evP[e], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&H.evR[e], cudaEventDisableTiming) == cudaSuccess;
+    if (!made) { set_last_error("engine_potrf: creating the look-ahead stream / events failed"); return -2; }
+    H.device = dev;
+  }
+  cudaStream_t crit = H.crit;
+  cudaEvent_t *evP = H.evP, *evR = H.evR, ev0 = H.ev0;
+  int rc = 0;
   auto cu = [&](cudaError_t e) {
     if (e != cudaSuccess && rc == 0) { rc = -2; set_last_error(std::string("engine_potrf look-ahead: ") + cudaGetErrorString(e)); }
     return rc == 0;
@@ -400,12 +413,6 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
   if (last_e >= 0) {
     cudaEventRecord(evP[last_e], crit);
     cudaStreamWaitEvent(st, evP[last_e], 0);
-  }
-  cudaStreamDestroy(crit);                   // queued work still completes
-  cudaEventDestroy(ev0);
-  for (int e = 0; e < 2; ++e) {
-    if (evP[e]) cudaEventDestroy(evP[e]);
-    if (evR[e]) cudaEventDestroy(evR[e]);
   }
   return rc;
 }
