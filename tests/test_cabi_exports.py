@@ -78,3 +78,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_new_entry_points_validate_arguments_without_a_device(lib):
+    """Prediction, HMC and Hadamard entries: bad arguments give NMGP_EINVAL (-1) and a message, never a crash."""
+    out = ctypes.c_void_p()
+    hyper = (ctypes.c_double * 9)()
+    assert lib.nmgp_plan_create_hadamard(ctypes.byref(out), 2, 1, 4, 2, None, None, None, hyper, 1, 0, None) == -1
+    assert b"nmgp_plan_create_hadamard" in lib.nmgp_last_error() and not out.value
+    assert lib.nmgp_predict_prior_moments(None, None, None, 3, None, None, None, None, None) == -1
+    assert lib.nmgp_predict_moments(None, None, None, 3, 2, None, None, 0, None, None, None, None) == -1
+    assert lib.nmgp_predict_moments_sep(None, None, None, 3, 2, None, None, None, None, None, None) == -1
+    assert lib.nmgp_hmc_kick(None, None, None, 1, 4, 0.1, None) == -1
+    assert lib.nmgp_hmc_drift(None, None, 1, 4, 0.1, None) == -1
+    assert lib.nmgp_hmc_accept(None, None, None, None, None, None, None, None, None, None, None, 1, 4, None) == -1
+    assert lib.nmgp_hmc_kick(None, None, None, 0, 0, 0.1, None) == -1          # P must be positive
