@@ -240,10 +240,16 @@ def ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    hyper_names = plan.hyper_names()
+
     def step_device():
-        vals, grad, info = plan.value_and_grad(pars_d)
-        summ = sharding.local_summary(vals, info)
-        return sharding.all_reduce_summary(summ) if world > 1 else summ
+        # one sweep: value + gradient of every local subject and, in the same pass, the gradient with respect to the
+        # hyper-parameters shared by all subjects; the only collective is one all-reduce of 17 doubles
+        vals, grad, hgrad, info = plan.value_grad_and_hyper_grad(pars_d)
+        vec = sharding.local_sweep_vector(vals, info, hgrad)
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        return vec
 
     # ---- device-resident timing (value)
     for _ in range(a.warmup):
@@ -259,8 +265,9 @@ def ours(a):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
     launches = plan.last_launches * a.steps
-    if not isinstance(summary, dict):
-        summary = dict(zip(sharding.SUMMARY_FIELDS, summary.tolist()))
+    sv = summary.tolist()
+    summary = dict(zip(sharding.SUMMARY_FIELDS, sv[:8]))
+    shared_hyper_grad = dict(zip(hyper_names, sv[8:8 + len(hyper_names)]))
 
     # ---- end to end through the host-buffer C call (pinned host memory in, results out)
     e2e = None
@@ -312,6 +319,7 @@ def ours(a):
             "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
             "sweep_summary": {k: summary[k] for k in ("neg_logpost", "n_failed", "n_subjects")},
+            "shared_hyper_grad": shared_hyper_grad,
             "plan": {"chunk": plan.chunk, "device_bytes": plan.device_bytes, "subjects_this_rank": S},
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -93,6 +93,20 @@ int nmgp_plan_destroy(nmgp_plan* plan);
 int nmgp_logpost_grad(nmgp_plan* plan, const double* pars_dev, double* vals_dev, double* grad_dev, int* info_dev,
                       void* stream);
 
+/* Gradient of -log posterior of every subject with respect to the plan's hyper-parameters, hgrad_dev [S][NMGP_NHYPER] in
+ * the order documented above (unused slots 0).  In the reference every subject carries its own fixed hyper-parameter
+ * dictionary (Nonseparable_model_mpisim.py:311-312); this is the quantity a caller that TIES the hyper-priors across
+ * subjects needs: sum it over the local subjects and all-reduce it across ranks (sharding.py).  No reference
+ * implementation exists; validated against finite differences of the objective.  Uses the cached prior factors and
+ * needs no likelihood factorisation.  Zero when the plan was created with prior_flag = 0. */
+int nmgp_hyper_grad(nmgp_plan* plan, const double* pars_dev, double* hgrad_dev, void* stream);
+
+/* nmgp_logpost_grad and nmgp_hyper_grad in one pass: the hyper-parameter gradient reuses the evaluation's own prior solves
+ * (three extra small launches per chunk).  This is the sweep of a sharded run with tied hyper-priors: vals / hgrad are
+ * summed over the rank's subjects and all-reduced in one 17-double vector (sharding.py). */
+int nmgp_logpost_grad_hyper(nmgp_plan* plan, const double* pars_dev, double* vals_dev, double* grad_dev, double* hgrad_dev,
+                            int* info_dev, void* stream);
+
 /* Same call with HOST buffers (pageable or pinned): copies pars host->device, evaluates, copies
  * vals / grad / info back and synchronises the stream.  This is the call a reference maintainer binds
  *  and what bench.py times as `e2e`. */

@@ -155,6 +155,47 @@ class LogPosteriorPlan:
         _lib.check(rc, "nmgp_logpost_grad")
         return vals, grad, info
 
+    def hyper_grad(self, pars):
+        """d(-log posterior)/d(hyper-parameters) of every subject: pars [S,P] CUDA -> [S,9] CUDA float64 in the keyword order of
+        HYPER_SPEC[model] (unused slots 0).  The reference keeps the hyper-parameters fixed per subject
+        (Nonseparable_model_mpisim.py:311-312); a caller that ties them across subjects sums this over its subjects and
+        all-reduces it (sharding.all_reduce_hyper_grad)."""
+        torch = _lib.require_cuda()
+        if not (isinstance(pars, torch.Tensor) and pars.is_cuda):
+            raise TypeError("hyper_grad expects a CUDA tensor")
+        p = pars.detach().to(torch.float64).reshape(self.S, self.P).contiguous()
+        out = torch.zeros((self.S, _lib.NHYPER), dtype=torch.float64, device=self.device)
+        if self.S == 0:
+            return out
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_hyper_grad(self._handle, p.data_ptr(), out.data_ptr(), ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_hyper_grad")
+        return out
+
+    def value_grad_and_hyper_grad(self, pars, need_grad: bool = True):
+        """value_and_grad + hyper_grad in one pass (nmgp_logpost_grad_hyper): -> (vals, grad, hgrad [S,9], info)."""
+        torch = _lib.require_cuda()
+        if not (isinstance(pars, torch.Tensor) and pars.is_cuda):
+            raise TypeError("value_grad_and_hyper_grad expects a CUDA tensor")
+        p = pars.detach().to(torch.float64).reshape(self.S, self.P).contiguous()
+        vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
+        grad = torch.empty((self.S, self.P), dtype=torch.float64, device=self.device) if need_grad else None
+        hgrad = torch.zeros((self.S, _lib.NHYPER), dtype=torch.float64, device=self.device)
+        info = torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        if self.S == 0:
+            return vals, grad, hgrad, info
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_logpost_grad_hyper(self._handle, p.data_ptr(), vals.data_ptr(),
+                                                  grad.data_ptr() if need_grad else None, hgrad.data_ptr(),
+                                                  info.data_ptr(), ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_logpost_grad_hyper")
+        return vals, grad, hgrad, info
+
+    def hyper_names(self):
+        return tuple(k for k, _ in HYPER_SPEC[self.model])
+
     def profile(self, pars):
         """One evaluation with CUDA events between phases: returns ({phase: ms}, vals, grad, info) (device tensors)."""
         torch = _lib.require_cuda()

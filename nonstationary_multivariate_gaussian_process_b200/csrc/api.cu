@@ -43,6 +43,10 @@ struct nmgp_plan {
   // staging for the host-buffer call
   double *pars_d = nullptr, *vals_d = nullptr, *grad_d = nullptr;
   int* info_d = nullptr;
+  // nmgp_hyper_grad: traces of the prior precisions (depend on x and the hyper-parameters only; formed on the first call)
+  double *trI0 = nullptr, *trB0 = nullptr, *trI1 = nullptr, *trB1 = nullptr;  // [S]
+  double *hq0 = nullptr, *hq1 = nullptr;                                       // [chunk][4]
+  bool traces_ready = false;
   // lazily allocated scratch of the prediction entry points (not part of `allocs`)
   double* pred_scratch = nullptr;
   size_t pred_scratch_doubles = 0;
@@ -540,10 +544,85 @@ static int run_potri(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* 
   return engine_potri(b, st, launches);
 }
 
+// digamma(x), x > 0: recurrence up to x >= 6, then the asymptotic series (error < 1e-15 there)
+static double digamma_pos(double x) {
+  double r = 0.0;
+  while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + std::log(x) - 0.5 / x -
+         f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 - f * (691.0 / 32760 - f / 12))))));
+}
+
+static int ensure_prior_traces(nmgp_plan* pl, cudaStream_t st) {
+  if (pl->traces_ready || !pl->nprior || pl->S == 0) return 0;
+  const size_t S = pl->S, N = pl->N;
+  if (!pl->trI0) {
+    NMGP_TRY(dev_alloc(pl, &pl->trI0, S));
+    NMGP_TRY(dev_alloc(pl, &pl->trB0, S));
+    NMGP_TRY(dev_alloc(pl, &pl->trI1, S));
+    NMGP_TRY(dev_alloc(pl, &pl->trB1, S));
+  }
+  const size_t per = 3 * N * N + 2 * N;                    // doubles of scratch per subject (prior_traces)
+  size_t cap = ((size_t)512 << 20) / (per * sizeof(double));
+  if (cap < 1) cap = 1;
+  if (cap > S) cap = S;
+  if (cap > 65535) cap = 65535;
+  double* scratch = nullptr;
+  if (cudaMalloc(&scratch, cap * per * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("nmgp_hyper_grad: out of device memory for the trace scratch");
+    return NMGP_ENOMEM;
+  }
+  int rc = 0;
+  for (size_t s0 = 0; s0 < S && rc == 0; s0 += cap) {
+    const int cs = (int)(S - s0 < cap ? S - s0 : cap);
+    rc = prior_traces(pl->x + s0 * N, pl->Wp0 + s0 * N * N, cs, (int)N, pl->hyper[1], pl->hyper[2], scratch, pl->trI0 + s0,
+                      pl->trB0 + s0, st, nullptr);
+    if (rc == 0)
+      rc = prior_traces(pl->x + s0 * N, pl->Wp1 + s0 * N * N, cs, (int)N, pl->hyper[4], pl->hyper[5], scratch, pl->trI1 + s0,
+                        pl->trB1 + s0, st, nullptr);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) { set_last_error("nmgp_hyper_grad: trace kernels failed"); rc = NMGP_ECUDA; }
+  cudaFree(scratch);
+  if (rc == 0) pl->traces_ready = true;
+  return rc;
+}
+
+static int hyper_setup(nmgp_plan* pl, cudaStream_t st, HyperRaw* h) {
+  for (int k = 0; k < NMGP_NHYPER; ++k) h->hy[k] = pl->hyper[k];
+  h->a = pl->hc.ig_a;
+  h->b = pl->hc.ig_b;
+  h->digamma_a = digamma_pos(h->a);
+  h->prior = pl->hc.prior;
+  if (h->prior) NMGP_TRY(ensure_prior_traces(pl, st));
+  if (pl->nprior && !pl->hq0) {
+    NMGP_TRY(dev_alloc(pl, &pl->hq0, (size_t)pl->chunk * 4));
+    NMGP_TRY(dev_alloc(pl, &pl->hq1, (size_t)pl->chunk * 4));
+  }
+  return 0;
+}
+
+// the hyper-parameter gradient of chunk [s0, s0 + cs) once Z0/Z1/G0/G1 and s2 of that chunk are in the scratch
+static int hyper_chunk(nmgp_plan* pl, const HyperRaw& h, int s0, int cs, const double* ps, double* hgrad, cudaStream_t st,
+                       long* launches) {
+  const int N = pl->N;
+  const double* xs = pl->x + (size_t)s0 * N;
+  if (pl->nprior && h.prior) {
+    NMGP_TRY(launch_prior_quad(xs, pl->w.Z0, pl->w.G0, cs, N, 1, pl->hyper[1], pl->hyper[2], pl->hq0, st, launches));
+    NMGP_TRY(launch_prior_quad(xs, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, pl->hyper[4], pl->hyper[5], pl->hq1, st, launches));
+  }
+  return launch_hyper_finish(pl->model, cs, N, pl->M, pl->P, ps, h, pl->w.s2, pl->hq0, pl->hq1,
+                             pl->trI0 ? pl->trI0 + s0 : nullptr, pl->trB0 ? pl->trB0 + s0 : nullptr,
+                             pl->trI1 ? pl->trI1 + s0 : nullptr, pl->trB1 ? pl->trB1 + s0 : nullptr, pl->nv1,
+                             hgrad + (size_t)s0 * NMGP_NHYPER, st, launches);
+}
+
 static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st,
-                    float* phase_ms, const ChunkSync* sync = nullptr) {
+                    float* phase_ms, const ChunkSync* sync = nullptr, double* hgrad = nullptr) {
   long launches = 0;
   const int N = pl->N, M = pl->M, P = pl->P;
+  HyperRaw hraw{};
+  if (hgrad) NMGP_TRY(hyper_setup(pl, st, &hraw));
   cudaEvent_t ev[NMGP_NPHASES + 1];
   if (phase_ms) {
     for (int i = 0; i <= NMGP_NPHASES; ++i) NMGP_CUDA_TRY(cudaEventCreate(&ev[i]));
@@ -584,7 +663,7 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
       const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
       NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, ps_st, &launches));
       NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, ps_st, &launches));
-      if (grad) {
+      if (grad || hgrad) {
         NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, ps_st, &launches));
         NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, ps_st, &launches));
       }
@@ -613,6 +692,7 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     } else {
       NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
     }
+    if (hgrad) NMGP_TRY(hyper_chunk(pl, hraw, s0, cs, ps, hgrad, st, &launches));
     NMGP_MARK(5);
     if (sync && sync->after) NMGP_CUDA_TRY(cudaEventRecord(sync->after[ci], st));
     if (phase_ms) {
@@ -679,6 +759,41 @@ int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, 
   NMGP_CUDA_TRY(cudaStreamSynchronize(pl->copy_out));
   NMGP_CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
+}
+
+int nmgp_hyper_grad(nmgp_plan* pl, const double* pars, double* hgrad, void* stream) {
+  if (!pl || (pl->S > 0 && (!pars || !hgrad))) { set_last_error("nmgp_hyper_grad: null argument"); return NMGP_EINVAL; }
+  if (pl->model >= NMGP_HADAMARD) { set_last_error("nmgp_hyper_grad: not available for the Hadamard objectives"); return NMGP_EINVAL; }
+  if (pl->S == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl->N, M = pl->M, P = pl->P;
+  long launches = 0;
+  HyperRaw h{};
+  NMGP_TRY(hyper_setup(pl, st, &h));
+  for (int s0 = 0; s0 < pl->S; s0 += pl->chunk) {
+    const int cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk;
+    const double* ps = pars + (size_t)s0 * P;
+    if (pl->model == NMGP_NONSEPARABLE) NMGP_TRY(launch_svc_prep(cs, N, M, ps, P, pl->hc, pl->w, st, &launches));
+    else NMGP_TRY(launch_sep_prep(pl->model, cs, N, M, pl->Y + (size_t)s0 * N * M, ps, P, pl->hc, pl->w, st, &launches));
+    if (pl->nprior && h.prior) {
+      const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
+      const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
+      NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, st, &launches));
+      NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, st, &launches));
+      NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, st, &launches));
+      NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, st, &launches));
+    }
+    NMGP_TRY(hyper_chunk(pl, h, s0, cs, ps, hgrad, st, &launches));
+  }
+  pl->last_launches = launches;
+  return 0;
+}
+
+int nmgp_logpost_grad_hyper(nmgp_plan* pl, const double* pars, double* vals, double* grad, double* hgrad, int* info,
+                            void* stream) {
+  if (!pl || (pl->S > 0 && (!pars || !vals || !info || !hgrad))) { set_last_error("nmgp_logpost_grad_hyper: null argument"); return NMGP_EINVAL; }
+  if (pl->model >= NMGP_HADAMARD) { set_last_error("nmgp_logpost_grad_hyper: not available for the Hadamard objectives"); return NMGP_EINVAL; }
+  return evaluate(pl, pars, vals, grad, info, (cudaStream_t)stream, nullptr, nullptr, hgrad);
 }
 
 int nmgp_adam_step(double* pars, const double* grad, double* m, double* v, const int* info, const unsigned char* frozen,

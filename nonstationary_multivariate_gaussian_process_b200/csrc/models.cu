@@ -1139,12 +1139,19 @@ int svc_backward(int cs, int N, int M, const double* Y, const double* pars, int 
   return 0;
 }
 
-int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,
-                const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches) {
+int launch_sep_prep(int model, int cs, int N, int M, const double* Y, const double* pars, int P, const HyperConst& h,
+                    const Scratch& w, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   sep_prep_kernel<<<cs, 256, 0, st>>>(model, pars, P, N, M, Y, h.mu0, h.mu1, w.ell, w.sig, w.s2, w.Lst, w.lam, w.Vec, w.yv,
                                       w.R0, w.R1);
   NMGP_LAUNCH_CHECK();
+  return 0;
+}
+
+int sep_forward(int model, int cs, int N, int M, const double* x, const double* Y, const double* pars, int P,
+                const HyperConst& h, const Scratch& w, const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (cs <= 0) return 0;
+  NMGP_TRY(launch_sep_prep(model, cs, N, M, Y, pars, P, h, w, st, launches));
   dim3 gk((N + 127) / 128, N, cs);
   kx_kernel<<<gk, 128, 0, st>>>(x, w.ell, w.sig, N, w.Kx, w.CK);
   NMGP_LAUNCH_CHECK();

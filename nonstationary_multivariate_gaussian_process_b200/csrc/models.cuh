@@ -121,4 +121,21 @@ int had_backward(int variant, int cs, int N, int M, const double* y, const int* 
                  const HyperConst& h, const Scratch& w, const BlockBatch& b, const double* hld0, const double* hld1,
                  double* vals, double* grad, int* info, cudaStream_t st, long* launches);
 
+// ---- gradient with respect to the hyper-parameters of the priors (hyper.cu; the north star's tied-hyper-prior extension,
+// no reference implementation: SURVEY 8e)
+struct HyperRaw {
+  double hy[9];            // the plan's hyper-parameter vector (include/nmgp_b200.h order), unrounded
+  double a, b, digamma_a;  // inverse gamma on sigma2_err
+  int prior;
+};
+int launch_sep_prep(int model, int cs, int N, int M, const double* Y, const double* pars, int P, const HyperConst& h,
+                    const Scratch& w, cudaStream_t st, long* launches);
+int prior_traces(const double* x, const double* Lp, int cs, int N, double alpha, double beta, double* scratch, double* trI,
+                 double* trB, cudaStream_t st, long* launches);
+int launch_prior_quad(const double* x, const double* Z, const double* G, int cs, int N, int nv, double alpha, double beta,
+                      double* out, cudaStream_t st, long* launches);
+int launch_hyper_finish(int model, int cs, int N, int M, int P, const double* pars, const HyperRaw& h, const double* s2v,
+                        const double* q0, const double* q1, const double* trI0, const double* trB0, const double* trI1,
+                        const double* trB1, int nv1, double* hgrad, cudaStream_t st, long* launches);
+
 }  // namespace nmgp

@@ -6,6 +6,11 @@ nothing is exchanged between subjects.  Here rank r owns subjects [lo, hi) of th
 `grad` of a subject never leave its GPU.  The only collective is an all-reduce(sum) of a short float64 vector of
 sweep totals (sum of -log posterior, of each component, failure count, subject count) -- NCCL over NVLink on the
 GPU box, gloo in the CPU tests.
+
+BASELINE.json's north star additionally ties the hyper-priors across the subjects of a sharded run: the gradient of the
+summed -log posterior with respect to the shared hyper-parameters is the sum over subjects of the per-subject gradients
+(`LogPosteriorPlan.hyper_grad`, C entry point nmgp_hyper_grad), so it rides in the same all-reduce: `local_sweep_vector`
+packs [summary (8) | hyper-gradient (9)] into one 17-double vector, `all_reduce_sweep` sums it across ranks.
 """
 from __future__ import annotations
 
@@ -41,3 +46,29 @@ def all_reduce_summary(summary, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(summary, op=dist.ReduceOp.SUM, group=group)
     return dict(zip(SUMMARY_FIELDS, summary.tolist()))
+
+
+def local_hyper_grad(hgrad, info):
+    """hgrad [S_local,9] (per-subject d(-logpost)/d hyper), info [S_local] -> float64 [9]: the sum over this rank's
+    subjects whose evaluation succeeded (the same subjects local_summary sums)."""
+    import torch
+    ok = (info == 0).unsqueeze(1)
+    return torch.where(ok, hgrad, torch.zeros_like(hgrad)).sum(0)
+
+
+def local_sweep_vector(vals, info, hgrad=None):
+    """One rank's contribution to the sweep's single all-reduce: [summary (8) | shared-hyper-parameter gradient (9)]."""
+    import torch
+    s = local_summary(vals, info)
+    h = local_hyper_grad(hgrad, info) if hgrad is not None else torch.zeros(9, dtype=torch.float64, device=vals.device)
+    return torch.cat([s, h])
+
+
+def all_reduce_sweep(vec, hyper_names=(), group=None):
+    """Sum the [17] sweep vectors over all ranks (in place; one collective) -> (summary dict, hyper-gradient dict)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    v = vec.tolist()
+    n = len(SUMMARY_FIELDS)
+    return dict(zip(SUMMARY_FIELDS, v[:n])), dict(zip(hyper_names, v[n:n + len(hyper_names)]))

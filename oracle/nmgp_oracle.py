@@ -340,3 +340,52 @@ def value_and_grad(model: str, pars, Y, x, **hyper):
     neg.backward()
     vals = torch.stack([neg.detach()] + [torch.as_tensor(o).detach().reshape(()) for o in out[1:]])
     return vals, p.grad.detach().clone()
+
+
+# ----------------------------------------------------------------------------- hyper-parameter gradient
+def hyper_grad(model: str, pars, x, M: int, **hyper):
+    """d(-log posterior)/d(hyper-parameters), float64 numpy [9] in the keyword order of the reference signatures
+    (logpos.py:383 / :216 / :299), from the closed forms of the prior terms (logpos.py:271-292, 357-376, 444-458):
+    dense inverse of the prior covariance, no factor reuse -- an independent route to what csrc/hyper.cu computes.
+    Pinned to the unmodified reference's autograd through its keyword hyper-parameters
+    (tests/golden/make_golden_hyper.py -> tests/golden/hyper_*.npz)."""
+    import numpy as np
+    from scipy.special import digamma
+
+    p = np.asarray(pars, dtype=np.float64)
+    xv = np.asarray(x, dtype=np.float64)
+    N, T = xv.shape[0], tril_size(M)
+    s2 = math.exp(p[-1])
+    a, b = float(hyper["a"]), float(hyper["b"])
+    d_a = -math.log(s2) + math.log(b) - float(digamma(a))
+    d_b = -1.0 / s2 + a / b
+    out = np.zeros(9)
+    if model == "stationary":
+        mu, sd, c = float(hyper["mu_tilde_l"]), float(hyper["sigma_tilde_l"]), float(hyper["c"])
+        d, uL = p[0] - mu, p[2:2 + T]
+        out[:5] = [d / sd ** 2, d * d / sd ** 3 - 1.0 / sd, d_a, d_b, (uL ** 2).sum() / c ** 3 - T / c]
+        return -out
+    D = (xv[:, None] - xv[None, :]) ** 2
+
+    def gp(V, mu, alpha, beta):          # V [N, nv]: the nv vectors sharing the prior N(mu 1, alpha^2 E + jitter I)
+        E = np.exp(-0.5 * D / beta ** 2)
+        Si = np.linalg.inv(alpha ** 2 * E + JITTER * np.eye(N))
+        G = Si @ (V - mu)
+        dSa, dSb = 2.0 * alpha * E, alpha ** 2 / beta ** 3 * E * D
+        nv = V.shape[1]
+        quad = lambda dS: -0.5 * nv * np.sum(Si * dS) + 0.5 * np.einsum("it,ij,jt->", G, dS, G)
+        return G.sum(), quad(dSa), quad(dSb)
+
+    if model == "separable":
+        k1 = ("mu_tilde_sigma", "alpha_tilde_sigma", "beta_tilde_sigma")
+        V0, V1 = p[:N, None], p[N:2 * N, None]
+        c = float(hyper["c"])
+        uL = p[2 * N:2 * N + T]
+        out[8] = (uL ** 2).sum() / c ** 3 - T / c
+    else:
+        k1 = ("mu_L", "alpha_L", "beta_L")
+        V0, V1 = p[:N, None], p[N:N + N * T].reshape(N, T)
+    out[0:3] = gp(V0, float(hyper["mu_tilde_l"]), float(hyper["alpha_tilde_l"]), float(hyper["beta_tilde_l"]))
+    out[3:6] = gp(V1, *(float(hyper[k]) for k in k1))
+    out[6], out[7] = d_a, d_b
+    return -out

@@ -1,0 +1,94 @@
+"""GPU: nmgp_hyper_grad (csrc/hyper.cu) -- gradient of -log posterior with respect to the hyper-parameters of the priors,
+per subject -- against the golden vectors recorded from the unmodified reference's autograd through its keyword
+hyper-parameters (tests/golden/make_golden_hyper.py) and against the oracle's dense closed form."""
+import numpy as np
+import pytest
+
+from test_hyper_grad_oracle import CASES, load
+
+pytestmark = pytest.mark.gpu
+
+
+def _scaled_err(got, want):
+    return float((np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * np.abs(want).max())).max())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_hyper_grad_matches_reference_autograd(name, cuda_device):
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    from oracle import nmgp_oracle as O
+    d = load(name)
+    plan = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"])
+    pars = torch.from_numpy(d["pars"]).to(cuda_device)
+    hg = plan.hyper_grad(pars).cpu().numpy()
+    hg2 = plan.hyper_grad(pars).cpu().numpy()          # second call: cached traces
+    assert np.array_equal(hg, hg2)
+    for s in range(d["pars"].shape[0]):
+        orc = O.hyper_grad(d["model"], d["pars"][s], d["x"][s], d["M"], **d["hyper"])
+        # the prior covariances have condition numbers up to 1e10: every route carries ~1e-6 relative noise in the
+        # alpha / beta slots; the mu / a / b / c / sigma slots are tight
+        assert _scaled_err(hg[s], d["hgrad"][s]) < 2e-5, (name, s, hg[s], d["hgrad"][s])
+        assert _scaled_err(hg[s], orc) < 2e-5, (name, s, hg[s], orc)
+    # evaluation after the hyper-gradient call is unaffected (shared scratch)
+    vals, grad, info = plan.value_and_grad(pars)
+    assert int(info.abs().sum()) == 0
+    assert np.allclose(vals[:, 0].cpu().numpy(), d["vals"], rtol=1e-8)
+    # fused pass (nmgp_logpost_grad_hyper): same values, gradient and hyper-gradient, bit for bit
+    v2, g2, h2, i2 = plan.value_grad_and_hyper_grad(pars)
+    assert torch.equal(v2, vals) and torch.equal(g2, grad) and int(i2.abs().sum()) == 0
+    assert np.array_equal(h2.cpu().numpy(), hg)
+    v3, g3, h3, _ = plan.value_grad_and_hyper_grad(pars, need_grad=False)
+    assert g3 is None and torch.equal(v3, vals) and np.array_equal(h3.cpu().numpy(), hg)
+
+
+def test_hyper_grad_zero_without_prior(cuda_device):
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    d = load([c for c in CASES if "nonseparable" in c][0])
+    plan = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"], prior=False)
+    hg = plan.hyper_grad(torch.from_numpy(d["pars"]).to(cuda_device))
+    assert float(hg.abs().max()) == 0.0
+
+
+def test_hyper_grad_finite_difference_of_the_batched_objective(cuda_device):
+    """Central differences of the CUDA objective itself (sum over subjects, new plan per perturbed hyper-parameter) for the
+    float64 GP-prior slots: the quantity a tied-hyper-prior optimiser steps along."""
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    d = load("hyper_nonseparable_N20_M2_s0")
+    pars = torch.from_numpy(d["pars"]).to(cuda_device)
+    tot = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"]).hyper_grad(pars).sum(0).cpu().numpy()
+    names = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_L", "alpha_L", "beta_L")
+    for i, k in enumerate(names):
+        h = 1e-5 * max(abs(d["hyper"][k]), 1.0)
+        f = []
+        for sgn in (+1, -1):
+            hy = dict(d["hyper"])
+            hy[k] = hy[k] + sgn * h
+            v, _, info = LogPosteriorPlan(d["model"], d["x"], d["Y"], hy).value_and_grad(pars, need_grad=False)
+            assert int(info.abs().sum()) == 0
+            f.append(float(v[:, 0].sum()))
+        fd = (f[0] - f[1]) / (2 * h)
+        assert abs(fd - tot[i]) <= 1e-4 * max(abs(tot[i]), 1.0), (k, fd, tot[i])
+
+
+def test_sweep_vector_sums_successful_subjects(cuda_device):
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200 import sharding
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    d = load("hyper_nonseparable_N40_M3_s3")
+    plan = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"])
+    pars = torch.from_numpy(d["pars"]).to(cuda_device)
+    vals, _, info = plan.value_and_grad(pars, need_grad=False)
+    hg = plan.hyper_grad(pars)
+    info = info.clone()
+    info[1] = 3                                  # pretend subject 1 failed
+    vec = sharding.local_sweep_vector(vals, info, hg)
+    summ, hyp = sharding.all_reduce_sweep(vec, plan.hyper_names())
+    keep = [0, 2, 3]
+    assert summ["n_failed"] == 1 and summ["n_subjects"] == 4
+    assert abs(summ["neg_logpost"] - d["vals"][keep].sum()) < 1e-8 * abs(d["vals"][keep].sum())
+    want = d["hgrad"][keep].sum(0)
+    got = np.array([hyp[k] for k in plan.hyper_names()])
+    assert _scaled_err(got, want[:len(got)]) < 2e-5

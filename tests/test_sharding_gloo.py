@@ -36,7 +36,10 @@ def _worker(rank, world, port, S, out_dir):
     vals, info = _fake_sweep(S)
     lo, hi = sharding.shard_range(S, rank, world)
     summ = sharding.all_reduce_summary(sharding.local_summary(vals[lo:hi], info[lo:hi]))
-    torch.save({"summary": summ, "range": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
+    hg = torch.from_numpy(np.random.RandomState(1).standard_normal((S, 9)))
+    names = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_L", "alpha_L", "beta_L", "a", "b")
+    summ2, hyp = sharding.all_reduce_sweep(sharding.local_sweep_vector(vals[lo:hi], info[lo:hi], hg[lo:hi]), names)
+    torch.save({"summary": summ, "summary2": summ2, "hyper": hyp, "range": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,3 +56,11 @@ def test_two_rank_all_reduce_equals_single_process_sum(tmp_path):
         for k in sharding.SUMMARY_FIELDS:
             assert abs(g["summary"][k] - want[k]) < 1e-12, (k, g["summary"][k], want[k])
     assert want["n_failed"] > 0 and want["n_subjects"] == S
+    # the shared-hyper-parameter gradient rides in the same collective: sum over the successful subjects of all ranks
+    hg = torch.from_numpy(np.random.RandomState(1).standard_normal((S, 9)))
+    hwant = sharding.local_hyper_grad(hg, info).tolist()
+    for g in got:
+        assert g["summary2"] == g["summary"]
+        assert list(g["hyper"]) == ["mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_L", "alpha_L", "beta_L", "a", "b"]
+        for i, k in enumerate(g["hyper"]):
+            assert abs(g["hyper"][k] - hwant[i]) < 1e-12
