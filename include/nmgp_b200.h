@@ -107,6 +107,12 @@ int nmgp_hyper_grad(nmgp_plan* plan, const double* pars_dev, double* hgrad_dev, 
 int nmgp_logpost_grad_hyper(nmgp_plan* plan, const double* pars_dev, double* vals_dev, double* grad_dev, double* hgrad_dev,
                             int* info_dev, void* stream);
 
+/* Replace the plan's hyper-parameters (hyper[NMGP_NHYPER], host memory, same order as at creation) without rebuilding the
+ * plan: the step a tied-hyper-prior optimiser takes between sweeps.  The GP-prior covariances whose (alpha, beta) changed
+ * are factored again on `stream` (the reference re-factors them in every call, logpos.py:271-281 / :357-365); x, Y and the
+ * workspace stay.  Must not run concurrently with an evaluation of the same plan. */
+int nmgp_plan_set_hyper(nmgp_plan* plan, const double* hyper, void* stream);
+
 /* Same call with HOST buffers (pageable or pinned): copies pars host->device, evaluates, copies
  * vals / grad / info back and synchronises the stream.  This is the call a reference maintainer binds
  *  and what bench.py times as `e2e`. */

@@ -193,6 +193,20 @@ class LogPosteriorPlan:
         _lib.check(rc, "nmgp_logpost_grad_hyper")
         return vals, grad, hgrad, info
 
+    def set_hyper(self, hyper: Mapping[str, float]):
+        """Replace hyper-parameters in place (nmgp_plan_set_hyper): keywords not given keep their current value.  Only the
+        prior covariances whose (alpha, beta) changed are factored again."""
+        torch = _lib.require_cuda()
+        new = dict(self.hyper)
+        new.update(hyper)
+        hv = hyper_vector(self.model, new)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.nmgp_plan_set_hyper(self._handle, hv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                              ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_plan_set_hyper")
+        self.hyper = new
+
     def hyper_names(self):
         return tuple(k for k, _ in HYPER_SPEC[self.model])
 

@@ -789,6 +789,23 @@ int nmgp_hyper_grad(nmgp_plan* pl, const double* pars, double* hgrad, void* stre
   return 0;
 }
 
+int nmgp_plan_set_hyper(nmgp_plan* pl, const double* hyper, void* stream) {
+  if (!pl || !hyper) { set_last_error("nmgp_plan_set_hyper: null argument"); return NMGP_EINVAL; }
+  for (int k = 0; k < NMGP_NHYPER; ++k)
+    if (!(hyper[k] == hyper[k])) { set_last_error("nmgp_plan_set_hyper: NaN hyper-parameter"); return NMGP_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool refactor0 = pl->nprior && (hyper[1] != pl->hyper[1] || hyper[2] != pl->hyper[2]);
+  const bool refactor1 = pl->nprior && (hyper[4] != pl->hyper[4] || hyper[5] != pl->hyper[5]);
+  std::memcpy(pl->hyper, hyper, sizeof(pl->hyper));
+  pl->hc = make_hyper_const(pl->model, hyper, pl->hc.prior);
+  if (pl->S == 0) return 0;
+  // only the covariances whose (alpha, beta) moved are factored again; the means enter through the residuals
+  if (refactor0) NMGP_TRY(factor_prior(pl, hyper[1], hyper[2], pl->Wp0, pl->hld0, st));
+  if (refactor1) NMGP_TRY(factor_prior(pl, hyper[4], hyper[5], pl->Wp1, pl->hld1, st));
+  if (refactor0 || refactor1) pl->traces_ready = false;
+  return 0;
+}
+
 int nmgp_logpost_grad_hyper(nmgp_plan* pl, const double* pars, double* vals, double* grad, double* hgrad, int* info,
                             void* stream) {
   if (!pl || (pl->S > 0 && (!pars || !vals || !info || !hgrad))) { set_last_error("nmgp_logpost_grad_hyper: null argument"); return NMGP_EINVAL; }

@@ -61,7 +61,7 @@ def test_hyper_grad_finite_difference_of_the_batched_objective(cuda_device):
     tot = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"]).hyper_grad(pars).sum(0).cpu().numpy()
     names = ("mu_tilde_l", "alpha_tilde_l", "beta_tilde_l", "mu_L", "alpha_L", "beta_L")
     for i, k in enumerate(names):
-        h = 1e-5 * max(abs(d["hyper"][k]), 1.0)
+        h = 1e-3 * max(abs(d["hyper"][k]), 1.0)   # the objective carries ~1e-9 relative noise (prior cond. ~1e9): wide step
         f = []
         for sgn in (+1, -1):
             hy = dict(d["hyper"])
@@ -70,7 +70,7 @@ def test_hyper_grad_finite_difference_of_the_batched_objective(cuda_device):
             assert int(info.abs().sum()) == 0
             f.append(float(v[:, 0].sum()))
         fd = (f[0] - f[1]) / (2 * h)
-        assert abs(fd - tot[i]) <= 1e-4 * max(abs(tot[i]), 1.0), (k, fd, tot[i])
+        assert abs(fd - tot[i]) <= 2e-3 * max(abs(tot[i]), 1.0), (k, fd, tot[i])
 
 
 def test_sweep_vector_sums_successful_subjects(cuda_device):
@@ -92,3 +92,48 @@ def test_sweep_vector_sums_successful_subjects(cuda_device):
     want = d["hgrad"][keep].sum(0)
     got = np.array([hyp[k] for k in plan.hyper_names()])
     assert _scaled_err(got, want[:len(got)]) < 2e-5
+
+
+def test_set_hyper_equals_new_plan(cuda_device):
+    """nmgp_plan_set_hyper: values, gradients and hyper-gradients after an in-place change are those of a plan created with
+    the new hyper-parameters, bit for bit; changing them back restores the original results."""
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    for name in ("hyper_nonseparable_N40_M3_s3", "hyper_separable_N24_M2_s0", "hyper_stationary_N30_M3_s0"):
+        d = load(name)
+        pars = torch.from_numpy(d["pars"]).to(cuda_device)
+        plan = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"])
+        v0, g0, h0, _ = plan.value_grad_and_hyper_grad(pars)
+        new = {k: (v * 1.25 + 0.1) for k, v in d["hyper"].items()}
+        plan.set_hyper(new)
+        v1, g1, h1, i1 = plan.value_grad_and_hyper_grad(pars)
+        fresh = LogPosteriorPlan(d["model"], d["x"], d["Y"], new)
+        v2, g2, h2, i2 = fresh.value_grad_and_hyper_grad(pars)
+        assert int(i1.abs().sum()) == 0 and int(i2.abs().sum()) == 0
+        assert torch.equal(v1, v2) and torch.equal(g1, g2) and torch.equal(h1, h2)
+        assert not torch.equal(v0, v1)
+        plan.set_hyper(d["hyper"])
+        v3, g3, h3, _ = plan.value_grad_and_hyper_grad(pars)
+        assert torch.equal(v3, v0) and torch.equal(g3, g0) and torch.equal(h3, h0)
+
+
+def test_tied_hyper_descent_lowers_the_summed_objective(cuda_device):
+    """The loop the north star describes for subjects sharing hyper-priors: sweep -> summed hyper-gradient -> step on the
+    shared prior means -> nmgp_plan_set_hyper.  A few small gradient steps on (mu_tilde_l, mu_L) must lower the sum of
+    -log posterior over the subjects."""
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200 import sharding
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    d = load("hyper_nonseparable_N40_M3_s3")
+    pars = torch.from_numpy(d["pars"]).to(cuda_device)
+    plan = LogPosteriorPlan(d["model"], d["x"], d["Y"], d["hyper"])
+    hy = dict(d["hyper"])
+    totals = []
+    for _ in range(4):
+        vals, _, hg, info = plan.value_grad_and_hyper_grad(pars, need_grad=False)
+        summ, shared = sharding.all_reduce_sweep(sharding.local_sweep_vector(vals, info, hg), plan.hyper_names())
+        totals.append(summ["neg_logpost"])
+        for k in ("mu_tilde_l", "mu_L"):
+            hy[k] -= 1e-3 * shared[k]      # curvature of the sum in mu_L is ~46: a stable step
+        plan.set_hyper(hy)
+    assert totals[-1] < totals[0] and all(b <= a for a, b in zip(totals, totals[1:])), totals
