@@ -45,7 +45,7 @@ struct nmgp_plan {
   int* info_d = nullptr;
   // nmgp_hyper_grad: traces of the prior precisions (depend on x and the hyper-parameters only; formed on the first call)
   double *trI0 = nullptr, *trB0 = nullptr, *trI1 = nullptr, *trB1 = nullptr;  // [S]
-  double *hq0 = nullptr, *hq1 = nullptr;                                       // [chunk][4]
+  double *hq0 = nullptr, *hq1 = nullptr;                                       // [chunk][prior_quad_blocks(N)][4]
   bool traces_ready = false;
   // lazily allocated scratch of the prediction entry points (not part of `allocs`)
   double* pred_scratch = nullptr;
@@ -596,8 +596,8 @@ static int hyper_setup(nmgp_plan* pl, cudaStream_t st, HyperRaw* h) {
   h->prior = pl->hc.prior;
   if (h->prior) NMGP_TRY(ensure_prior_traces(pl, st));
   if (pl->nprior && !pl->hq0) {
-    NMGP_TRY(dev_alloc(pl, &pl->hq0, (size_t)pl->chunk * 4));
-    NMGP_TRY(dev_alloc(pl, &pl->hq1, (size_t)pl->chunk * 4));
+    NMGP_TRY(dev_alloc(pl, &pl->hq0, (size_t)pl->chunk * prior_quad_blocks(pl->N) * 4));
+    NMGP_TRY(dev_alloc(pl, &pl->hq1, (size_t)pl->chunk * prior_quad_blocks(pl->N) * 4));
   }
   return 0;
 }

@@ -74,38 +74,65 @@ __global__ void __launch_bounds__(256) sum_rows_kernel(const double* __restrict_
   if (threadIdx.x == 0) { trI[c] = ta; trB[c] = tb; }
 }
 
-// per subject and prior: sg = sum_{i,t} g_it,  gg = sum g_it^2,  rg = sum z_it^2 (= r^T g),  gBg = sum_ij dS_b,ij sum_t g_it g_jt
-__global__ void __launch_bounds__(256) prior_quad_kernel(const double* __restrict__ x, const double* __restrict__ Z,
+// per subject and prior, partial sums over a block of QRB rows i (one CTA each; summed in block order by hyper_finish_kernel,
+// so the result does not depend on scheduling):
+//   sg = sum_{i,t} g_it,  gg = sum g_it^2,  rg = sum z_it^2 (= r^T g),  gBg = sum_i sum_j dS_b,ij sum_t g_it g_jt
+// The QRB rows of G sit in shared memory; every thread walks columns j and reads G_j once for all QRB rows.
+constexpr int QRB = 8;
+__global__ void __launch_bounds__(128) prior_quad_kernel(const double* __restrict__ x, const double* __restrict__ Z,
                                                          const double* __restrict__ G, int N, int nv, double alpha2,
-                                                         double beta, double* __restrict__ out /*[cs][4]*/) {
+                                                         double beta, double* __restrict__ part /*[cs][nblk][4]*/) {
+  extern __shared__ double gi[];   // [QRB][nv]
   __shared__ double scratch[40];
-  const int c = blockIdx.x;
+  __shared__ double xi[QRB];
+  const int c = blockIdx.y, i0 = blockIdx.x * QRB;
+  const int nr = min(QRB, N - i0);
   const double* Gc = G + (long)c * N * nv;
   const double* Zc = Z + (long)c * N * nv;
   const double* xs = x + (long)c * N;
   double sg = 0.0, gg = 0.0, rg = 0.0, gbg = 0.0;
-  for (long idx = threadIdx.x; idx < (long)N * nv; idx += blockDim.x) {
-    const double g = Gc[idx], z = Zc[idx];
-    sg += g; gg += g * g; rg += z * z;
+  for (int idx = threadIdx.x; idx < QRB * nv; idx += blockDim.x) {
+    double g = 0.0;
+    if (idx < nr * nv) {
+      g = Gc[(long)i0 * nv + idx];
+      const double z = Zc[(long)i0 * nv + idx];
+      sg += g; gg += g * g; rg += z * z;
+    }
+    gi[idx] = g;                                          // rows past N: zero, their weights drop out
   }
-  const double cb = alpha2 / (beta * beta * beta);
-  for (long idx = threadIdx.x; idx < (long)N * N; idx += blockDim.x) {
-    const int i = (int)(idx / N), j = (int)(idx % N);
-    if (j >= i) continue;                                 // D_ii = 0; symmetric: count (i,j), j < i, twice
-    const double d = xs[i] - xs[j], d2 = d * d;
-    double dot = 0.0;
-    for (int t = 0; t < nv; ++t) dot += Gc[(long)i * nv + t] * Gc[(long)j * nv + t];
-    gbg += 2.0 * cb * exp(-0.5 * d2 / (beta * beta)) * d2 * dot;
+  if (threadIdx.x < QRB) xi[threadIdx.x] = threadIdx.x < nr ? xs[i0 + threadIdx.x] : 0.0;
+  __syncthreads();
+  const double ib2 = 1.0 / (beta * beta);
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    double dot[QRB];
+#pragma unroll
+    for (int r = 0; r < QRB; ++r) dot[r] = 0.0;
+    const double* gj = Gc + (long)j * nv;
+    for (int t = 0; t < nv; ++t) {
+      const double gjt = gj[t];
+#pragma unroll
+      for (int r = 0; r < QRB; ++r) dot[r] += gi[r * nv + t] * gjt;
+    }
+    const double xj = xs[j];
+#pragma unroll
+    for (int r = 0; r < QRB; ++r) {
+      const double d = xi[r] - xj, d2 = d * d;            // D_ii = 0: the diagonal drops out by itself
+      gbg += exp(-0.5 * d2 * ib2) * d2 * dot[r];
+    }
   }
+  gbg *= alpha2 / (beta * beta * beta);
   const double a = block_sum(sg, scratch), b = block_sum(gg, scratch), r = block_sum(rg, scratch), q = block_sum(gbg, scratch);
-  if (threadIdx.x == 0) { out[c * 4 + 0] = a; out[c * 4 + 1] = b; out[c * 4 + 2] = r; out[c * 4 + 3] = q; }
+  if (threadIdx.x == 0) {
+    double* o = part + ((long)c * gridDim.x + blockIdx.x) * 4;
+    o[0] = a; o[1] = b; o[2] = r; o[3] = q;
+  }
 }
 
 // hgrad[c][k] = d(-logpost_c)/d hyper_k in the plan's hyper-parameter order (include/nmgp_b200.h)
 __global__ void hyper_finish_kernel(int model, int cs, int N, int M, int P, const double* __restrict__ pars, HyperRaw h,
                                     const double* __restrict__ s2v, const double* __restrict__ q0, const double* __restrict__ q1,
                                     const double* __restrict__ trI0, const double* __restrict__ trB0,
-                                    const double* __restrict__ trI1, const double* __restrict__ trB1, int nv1,
+                                    const double* __restrict__ trI1, const double* __restrict__ trB1, int nv1, int nblk,
                                     double* __restrict__ hgrad) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cs) return;
@@ -118,7 +145,8 @@ __global__ void hyper_finish_kernel(int model, int cs, int N, int M, int P, cons
   // inverse gamma on sigma2_err: (-a-1) log s2 - b/s2 + a log b - lgamma(a)
   const double d_a = -log(s2) + log(h.b) - h.digamma_a, d_b = -1.0 / s2 + h.a / h.b;
   auto gp = [&](const double* q, double trI, double trB, double alpha, int nv, double& d_mu, double& d_alpha, double& d_beta) {
-    const double sg = q[0], gg = q[1], rg = q[2], gbg = q[3];
+    double sg = 0.0, gg = 0.0, rg = 0.0, gbg = 0.0;
+    for (int bk = 0; bk < nblk; ++bk) { sg += q[bk * 4 + 0]; gg += q[bk * 4 + 1]; rg += q[bk * 4 + 2]; gbg += q[bk * 4 + 3]; }
     d_mu = sg;
     d_alpha = (1.0 / alpha) * (-(double)nv * ((double)N - kJitter * trI) + (rg - kJitter * gg));
     d_beta = -0.5 * (double)nv * trB + 0.5 * gbg;
@@ -134,8 +162,8 @@ __global__ void hyper_finish_kernel(int model, int cs, int N, int M, int P, cons
     return;
   }
   double m0, a0, b0, m1, a1, b1;
-  gp(q0 + c * 4, trI0[c], trB0[c], h.hy[1], 1, m0, a0, b0);
-  gp(q1 + c * 4, trI1[c], trB1[c], h.hy[4], nv1, m1, a1, b1);
+  gp(q0 + (long)c * nblk * 4, trI0[c], trB0[c], h.hy[1], 1, m0, a0, b0);
+  gp(q1 + (long)c * nblk * 4, trI1[c], trB1[c], h.hy[4], nv1, m1, a1, b1);
   o[0] = -m0; o[1] = -a0; o[2] = -b0; o[3] = -m1; o[4] = -a1; o[5] = -b1;
   o[6] = -d_a; o[7] = -d_b;
   if (model == 1) {          // separable: Normal(0, c) on uL
@@ -179,10 +207,13 @@ int prior_traces(const double* x, const double* Lp, int cs, int N, double alpha,
   return 0;
 }
 
+int prior_quad_blocks(int N) { return (N + QRB - 1) / QRB; }
+
 int launch_prior_quad(const double* x, const double* Z, const double* G, int cs, int N, int nv, double alpha, double beta,
                       double* out, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
-  prior_quad_kernel<<<cs, 256, 0, st>>>(x, Z, G, N, nv, alpha * alpha, beta, out);
+  dim3 grid(prior_quad_blocks(N), cs);
+  prior_quad_kernel<<<grid, 128, (size_t)QRB * nv * sizeof(double), st>>>(x, Z, G, N, nv, alpha * alpha, beta, out);
   NMGP_LAUNCH_CHECK();
   return 0;
 }
@@ -192,7 +223,7 @@ int launch_hyper_finish(int model, int cs, int N, int M, int P, const double* pa
                         const double* trB1, int nv1, double* hgrad, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   hyper_finish_kernel<<<(cs + 127) / 128, 128, 0, st>>>(model, cs, N, M, P, pars, h, s2v, q0, q1, trI0, trB0, trI1, trB1, nv1,
-                                                        hgrad);
+                                                        prior_quad_blocks(N), hgrad);
   NMGP_LAUNCH_CHECK();
   return 0;
 }

@@ -38,9 +38,12 @@ out = {"model": model, "N": N, "M": M, "S": S, "first_hyper_grad_ms": first,
        "hyper_grad_ms": timed(lambda: plan.hyper_grad(p)), "hyper_grad_launches": plan.last_launches,
        "eval_ms": timed(lambda: plan.value_and_grad(p)), "eval_launches": plan.last_launches,
        "fused_ms": timed(lambda: plan.value_grad_and_hyper_grad(p)), "fused_launches": plan.last_launches}
-h2 = dict(hyper); h2["beta_tilde_l"] = 0.9
+h2 = dict(hyper)
 if model != "stationary":
+    h2["beta_tilde_l"] = 0.9
     h2["beta_L" if model == "nonseparable" else "beta_tilde_sigma"] = 0.9
+else:
+    h2["sigma_tilde_l"] = 5.0
 flip = [h2, hyper]
 out["set_hyper_ms"] = timed(lambda: plan.set_hyper(flip[0]) or flip.reverse())
 print(json.dumps(out))
