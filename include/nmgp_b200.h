@@ -113,6 +113,14 @@ int nmgp_logpost_grad_hyper(nmgp_plan* plan, const double* pars_dev, double* val
  * workspace stay.  Must not run concurrently with an evaluation of the same plan. */
 int nmgp_plan_set_hyper(nmgp_plan* plan, const double* hyper, void* stream);
 
+/* CUDA-graph replay of launch-bound evaluations.  Single-chunk plans whose evaluation is a few hundred small kernels or
+ * fewer (the one-subject-per-process MAP / HMC loops of Stationary_model.py:106-131, Separable_model.py:149-231,
+ * Nonseparable_model_mpisim.py:163-207) capture the kernel sequence of nmgp_logpost_grad / nmgp_logpost_grad_host once per
+ * buffer tuple and replay it with one cudaGraphLaunch; same kernels, same results bit for bit.  mode 0 = automatic (default),
+ * 1 = never (A/B timing, debugging).  nmgp_plan_graph_replays counts the evaluations served by a replay. */
+int nmgp_plan_set_graph(nmgp_plan* plan, int mode);
+long nmgp_plan_graph_replays(const nmgp_plan* plan);
+
 /* Same call with HOST buffers (pageable or pinned): copies pars host->device, evaluates, copies
  * vals / grad / info back and synchronises the stream.  This is the call a reference maintainer binds
  *  and what bench.py times as `e2e`. */

@@ -102,6 +102,10 @@ def _declare(lib):
     lib.nmgp_logpost_grad_profile.argtypes = [c.c_void_p, dp, dp, dp, ip, c.POINTER(c.c_float), vp]
     lib.nmgp_plan_set_engine.restype = c.c_int
     lib.nmgp_plan_set_engine.argtypes = [c.c_void_p, c.c_int]
+    lib.nmgp_plan_set_graph.restype = c.c_int
+    lib.nmgp_plan_set_graph.argtypes = [c.c_void_p, c.c_int]
+    lib.nmgp_plan_graph_replays.restype = c.c_long
+    lib.nmgp_plan_graph_replays.argtypes = [c.c_void_p]
     lib.nmgp_plan_last_launches.restype = c.c_long
     lib.nmgp_plan_last_launches.argtypes = [c.c_void_p]
     lib.nmgp_plan_device_bytes.restype = c.c_size_t
@@ -139,7 +143,7 @@ def _declare(lib):
 
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_create_hadamard", "nmgp_plan_destroy", "nmgp_logpost_grad", "nmgp_hyper_grad", "nmgp_plan_set_hyper", "nmgp_logpost_grad_hyper",
-           "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
+           "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_set_graph", "nmgp_plan_graph_replays", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
            "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 

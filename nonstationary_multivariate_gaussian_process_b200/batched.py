@@ -129,22 +129,38 @@ class LogPosteriorPlan:
     def last_launches(self) -> int:
         return self.lib.nmgp_plan_last_launches(self._handle)
 
+    @property
+    def graph_replays(self) -> int:
+        """evaluations served by a CUDA-graph replay so far (launch-bound single-chunk plans)"""
+        return self.lib.nmgp_plan_graph_replays(self._handle)
+
+    def set_graph(self, enabled: bool):
+        """CUDA-graph replay of launch-bound evaluations: on (automatic, default) / off (A/B timing)."""
+        _lib.check(self.lib.nmgp_plan_set_graph(self._handle, 0 if enabled else 1), "nmgp_plan_set_graph")
+
     def set_engine(self, mode: str):
         """'auto' | 'right' (right-looking tile tasks) | 'left' (left-looking / Takahashi): tests and A/B timing."""
         _lib.check(self.lib.nmgp_plan_set_engine(self._handle, {"auto": 0, "right": 1, "left": 2, "left_stable": 3, "recursive": 4}[mode]),
                    "nmgp_plan_set_engine")
 
     # ------------------------------------------------------------------ evaluation
-    def value_and_grad(self, pars, need_grad: bool = True):
+    def value_and_grad(self, pars, need_grad: bool = True, out=None):
         """Device path: pars [S,P] CUDA float64 -> (vals [S,6], grad [S,P] or None, info [S] int32), all CUDA.
-        Stream-ordered on torch's current stream; no host synchronisation."""
+        Stream-ordered on torch's current stream; no host synchronisation.  `out` = (vals, grad, info) reuses the caller's
+        buffers: a loop that evaluates into the same buffers from the same `pars` storage is replayed as one CUDA graph when
+        the plan is launch-bound (nmgp_plan_set_graph)."""
         torch = _lib.require_cuda()
         if not (isinstance(pars, torch.Tensor) and pars.is_cuda):
             raise TypeError("value_and_grad expects a CUDA tensor; use value_and_grad_host for host buffers")
         p = pars.detach().to(torch.float64).reshape(self.S, self.P).contiguous()
-        vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
-        grad = torch.empty((self.S, self.P), dtype=torch.float64, device=self.device) if need_grad else None
-        info = torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        if out is not None:
+            vals, grad, info = out
+            if not need_grad:
+                grad = None
+        else:
+            vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
+            grad = torch.empty((self.S, self.P), dtype=torch.float64, device=self.device) if need_grad else None
+            info = torch.empty((self.S,), dtype=torch.int32, device=self.device)
         if self.S == 0:
             return vals, grad, info
         with torch.cuda.device(self.device):
@@ -286,13 +302,16 @@ class LogPosteriorPlan:
         if frozen is not None:
             fz = torch.as_tensor(frozen, dtype=torch.bool).reshape(self.P).to(self.device).to(torch.uint8).contiguous()
         trace = []
+        # fixed output buffers: with unchanged pointers a launch-bound plan replays each evaluation as one CUDA graph
+        buf = (torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device), torch.empty_like(p),
+               torch.empty((self.S,), dtype=torch.int32, device=self.device))
         info = None
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             for it in range(1, steps + 1):
-                vals, grad, info = self.value_and_grad(p)
+                vals, grad, info = self.value_and_grad(p, out=buf)
                 if (it - 1) % record_every == 0:
-                    trace.append(vals)
+                    trace.append(vals.clone())
                 rc = self.lib.nmgp_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), info.data_ptr(),
                                              fz.data_ptr() if fz is not None else None, self.S, self.P, float(lr),
                                              float(betas[0]), float(betas[1]), float(eps), it, ctypes.c_void_p(stream))
@@ -329,6 +348,11 @@ class LogPosteriorPlan:
         if L < 1 or keep_every < 1:
             raise ValueError("hmc_sample needs num_steps_in_leap >= 1 and keep_every >= 1")
         lib, S, P = self.lib, self.S, self.P
+        # fixed proposal / output buffers: with unchanged pointers a launch-bound plan replays every leapfrog evaluation as
+        # one CUDA graph (nmgp_plan_set_graph)
+        p, qp = torch.empty_like(q), torch.empty_like(q)
+        buf = (torch.empty((S, _lib.NVALS), dtype=f64, device=self.device), torch.empty_like(q),
+               torch.empty((S,), dtype=torch.int32, device=self.device))
         with torch.cuda.device(self.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             for it in range(sample_size):
@@ -340,14 +364,14 @@ class LogPosteriorPlan:
                     lu = torch.as_tensor(log_uniforms[it], dtype=f64).to(self.device).reshape(S).contiguous()
                 else:
                     lu = torch.log(torch.rand((S,), dtype=f64, device=self.device, generator=gen))
-                p = p0.clone()
-                qp = q.clone()
+                p.copy_(p0)
+                qp.copy_(q)
                 failed = torch.zeros((S,), dtype=torch.int32, device=self.device)
                 _lib.check(lib.nmgp_hmc_kick(p.data_ptr(), grad.data_ptr(), None, S, P, 0.5 * eps, stream), "nmgp_hmc_kick")
                 vp = gp = None
                 for l in range(L):
                     _lib.check(lib.nmgp_hmc_drift(qp.data_ptr(), p.data_ptr(), S, P, eps, stream), "nmgp_hmc_drift")
-                    vp, gp, ip = self.value_and_grad(qp)
+                    vp, gp, ip = self.value_and_grad(qp, out=buf)
                     failed |= (ip != 0).to(torch.int32)
                     _lib.check(lib.nmgp_hmc_kick(p.data_ptr(), gp.data_ptr(), ip.data_ptr(), S, P,
                                                  eps if l + 1 < L else 0.5 * eps, stream), "nmgp_hmc_kick")

@@ -47,6 +47,20 @@ struct nmgp_plan {
   double *trI0 = nullptr, *trB0 = nullptr, *trI1 = nullptr, *trB1 = nullptr;  // [S]
   double *hq0 = nullptr, *hq1 = nullptr;                                       // [chunk][prior_quad_blocks(N)][4]
   bool traces_ready = false;
+  // CUDA-graph replay of launch-bound evaluations (single-chunk plans with few launches; see evaluate_replay)
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    const double* pars = nullptr;
+    double *vals = nullptr, *grad = nullptr;
+    int* info = nullptr;
+    long launches = 0;
+    int warm = 0;        // evaluations of this variant launched directly so far (lazy module loads, helper streams)
+    int captures = 0;    // re-captures after a pointer change; capped, then the variant launches directly for good
+  };
+  GraphSlot gslot[2];    // [grad requested]
+  cudaStream_t gcap = nullptr;   // capture stream (torch's current stream is usually the legacy stream, which cannot capture)
+  int graph_mode = 0;    // 0 auto, 1 never
+  long graph_replays = 0;
   // lazily allocated scratch of the prediction entry points (not part of `allocs`)
   double* pred_scratch = nullptr;
   size_t pred_scratch_doubles = 0;
@@ -360,6 +374,9 @@ int nmgp_plan_destroy(nmgp_plan* pl) {
   if (!pl) return 0;
   for (void* p : pl->allocs) cudaFree(p);
   if (pl->pred_scratch) cudaFree(pl->pred_scratch);
+  for (auto& g : pl->gslot)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (pl->gcap) cudaStreamDestroy(pl->gcap);
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_join) cudaEventDestroy(pl->ev_join);
   if (pl->side) cudaStreamDestroy(pl->side);
@@ -711,9 +728,70 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
   return 0;
 }
 
+static void drop_graphs(nmgp_plan* pl) {
+  for (auto& g : pl->gslot) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    g.warm = 0;
+    g.captures = 0;
+  }
+}
+
+// Launch-bound plans (one chunk, a few dozen to a few hundred small kernels: the drivers' one-subject-per-process MAP / HMC
+// loops, C1 / C2 of BASELINE.json) replay the evaluation as ONE CUDA graph: the kernel sequence of evaluate() -- including the
+// fork to the side stream and the look-ahead helper stream -- is captured once per (pars, vals, grad, info) pointer tuple on
+// the plan's own capture stream and launched with cudaGraphLaunch on the caller's stream.  The first evaluation of each
+// variant always launches directly (lazy module loading and the helper streams are not capturable); a failed capture or a
+// caller whose buffers keep moving falls back to direct launches of the same kernels -- never to anything else.
+constexpr long kGraphMaxLaunches = 512;
+constexpr int kGraphMaxCaptures = 4;
+static int evaluate_replay(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st) {
+  nmgp_plan::GraphSlot& g = pl->gslot[grad ? 1 : 0];
+  const bool eligible = pl->graph_mode == 0 && pl->S > 0 && pl->S <= pl->chunk && g.captures <= kGraphMaxCaptures &&
+                        (g.warm == 0 || g.launches <= kGraphMaxLaunches);
+  if (!eligible || g.warm == 0) {
+    const int rc = evaluate(pl, pars, vals, grad, info, st, nullptr);
+    if (rc == 0) { g.warm++; g.launches = pl->last_launches; }
+    return rc;
+  }
+  if (g.exec && (g.pars != pars || g.vals != vals || g.grad != grad || g.info != info)) {
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  if (!g.exec) {
+    if (++g.captures > kGraphMaxCaptures) return evaluate(pl, pars, vals, grad, info, st, nullptr);
+    if (!pl->gcap && cudaStreamCreateWithFlags(&pl->gcap, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      pl->graph_mode = 1;
+      return evaluate(pl, pars, vals, grad, info, st, nullptr);
+    }
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(pl->gcap, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int rc = evaluate(pl, pars, vals, grad, info, pl->gcap, nullptr);
+      const cudaError_t ec = cudaStreamEndCapture(pl->gcap, &graph);
+      ok = rc == 0 && ec == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      g.exec = nullptr;
+      pl->graph_mode = 1;   // this plan launches directly from now on
+      return evaluate(pl, pars, vals, grad, info, st, nullptr);
+    }
+    g.pars = pars; g.vals = vals; g.grad = grad; g.info = info;
+    g.launches = pl->last_launches;
+  }
+  NMGP_CUDA_TRY(cudaGraphLaunch(g.exec, st));
+  pl->last_launches = g.launches;
+  pl->graph_replays++;
+  return 0;
+}
+
 int nmgp_logpost_grad(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, void* stream) {
   if (!pl || (pl->S > 0 && (!pars || !vals || !info))) { set_last_error("nmgp_logpost_grad: null argument"); return NMGP_EINVAL; }
-  return evaluate(pl, pars, vals, grad, info, (cudaStream_t)stream, nullptr);
+  return evaluate_replay(pl, pars, vals, grad, info, (cudaStream_t)stream);
 }
 
 int nmgp_logpost_grad_profile(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, float* phase_ms,
@@ -729,6 +807,17 @@ int nmgp_logpost_grad_host(nmgp_plan* pl, const double* pars_h, double* vals_h, 
   cudaStream_t st = (cudaStream_t)stream;
   const int P = pl->P;
   const int nch = (pl->S + pl->chunk - 1) / pl->chunk;
+  if (nch == 1 && pl->graph_mode == 0) {
+    // one chunk: nothing to pipeline -- copy in, evaluate (graph replay when launch-bound), copy out, all on `st`
+    const size_t S = pl->S;
+    NMGP_CUDA_TRY(cudaMemcpyAsync(pl->pars_d, pars_h, S * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    NMGP_TRY(evaluate_replay(pl, pl->pars_d, pl->vals_d, grad_h ? pl->grad_d : nullptr, pl->info_d, st));
+    NMGP_CUDA_TRY(cudaMemcpyAsync(vals_h, pl->vals_d, S * NMGP_NVALS * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (grad_h) NMGP_CUDA_TRY(cudaMemcpyAsync(grad_h, pl->grad_d, S * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (info_h) NMGP_CUDA_TRY(cudaMemcpyAsync(info_h, pl->info_d, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NMGP_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+  }
   // fork the copy streams off `st`, so the call stays ordered after whatever the caller queued there
   NMGP_CUDA_TRY(cudaEventRecord(pl->ev_start, st));
   NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->copy_in, pl->ev_start, 0));
@@ -798,6 +887,7 @@ int nmgp_plan_set_hyper(nmgp_plan* pl, const double* hyper, void* stream) {
   const bool refactor1 = pl->nprior && (hyper[4] != pl->hyper[4] || hyper[5] != pl->hyper[5]);
   std::memcpy(pl->hyper, hyper, sizeof(pl->hyper));
   pl->hc = make_hyper_const(pl->model, hyper, pl->hc.prior);
+  drop_graphs(pl);   // the hyper-parameter constants are kernel arguments baked into the captured graphs
   if (pl->S == 0) return 0;
   // only the covariances whose (alpha, beta) moved are factored again; the means enter through the residuals
   if (refactor0) NMGP_TRY(factor_prior(pl, hyper[1], hyper[2], pl->Wp0, pl->hld0, st));
@@ -988,11 +1078,18 @@ int nmgp_hmc_accept(double* q, const double* q_prop, double* grad, const double*
 
 int nmgp_plan_set_engine(nmgp_plan* pl, int mode) {
   if (!pl || mode < 0 || mode > 4) return NMGP_EINVAL;
+  drop_graphs(pl);                          // the captured kernel sequence belongs to the old engine choice
   pl->engine_mode = mode == 3 ? 2 : mode;   // 4: automatic potrf, level-synchronous recursive inverse
   pl->stable_inverse = mode == 3;
   return 0;
 }
 
+int nmgp_plan_set_graph(nmgp_plan* pl, int mode) {
+  if (!pl || mode < 0 || mode > 1) { set_last_error("nmgp_plan_set_graph: mode must be 0 (auto) or 1 (never)"); return NMGP_EINVAL; }
+  pl->graph_mode = mode;
+  return 0;
+}
+long nmgp_plan_graph_replays(const nmgp_plan* pl) { return pl ? pl->graph_replays : 0; }
 long nmgp_plan_last_launches(const nmgp_plan* pl) { return pl ? pl->last_launches : 0; }
 size_t nmgp_plan_device_bytes(const nmgp_plan* pl) { return pl ? pl->dev_bytes : 0; }
 int nmgp_plan_chunk(const nmgp_plan* pl) { return pl ? pl->chunk : 0; }
