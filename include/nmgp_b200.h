@@ -107,6 +107,13 @@ int nmgp_hyper_grad(nmgp_plan* plan, const double* pars_dev, double* hgrad_dev, 
 int nmgp_logpost_grad_hyper(nmgp_plan* plan, const double* pars_dev, double* vals_dev, double* grad_dev, double* hgrad_dev,
                             int* info_dev, void* stream);
 
+/* One rank's contribution to the sweep's single all-reduce, in one launch with a fixed summation order:
+ * out17[0..5] = sum over the successful subjects (info == 0) of vals[s][0..5], out17[6] = number of failed subjects,
+ * out17[7] = S, out17[8..16] = sum over the successful subjects of hgrad[s][0..8] (zeros if hgrad_dev == NULL).
+ * Device pointers.  The reference has no counterpart (its MPI ranks exchange nothing, Nonseparable_model_mpisim.py:39-43). */
+int nmgp_sweep_reduce(const double* vals_dev, const double* hgrad_dev, const int* info_dev, long S, double* out17_dev,
+                      void* stream);
+
 /* Replace the plan's hyper-parameters (hyper[NMGP_NHYPER], host memory, same order as at creation) without rebuilding the
  * plan: the step a tied-hyper-prior optimiser takes between sweeps.  The GP-prior covariances whose (alpha, beta) changed
  * are factored again on `stream` (the reference re-factors them in every call, logpos.py:271-281 / :357-365); x, Y and the

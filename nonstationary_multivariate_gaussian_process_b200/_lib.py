@@ -94,6 +94,8 @@ def _declare(lib):
     lib.nmgp_hyper_grad.argtypes = [c.c_void_p, dp, dp, vp]
     lib.nmgp_logpost_grad_hyper.restype = c.c_int
     lib.nmgp_logpost_grad_hyper.argtypes = [c.c_void_p, dp, dp, dp, dp, ip, vp]
+    lib.nmgp_sweep_reduce.restype = c.c_int
+    lib.nmgp_sweep_reduce.argtypes = [dp, dp, ip, c.c_long, dp, vp]
     lib.nmgp_plan_set_hyper.restype = c.c_int
     lib.nmgp_plan_set_hyper.argtypes = [c.c_void_p, c.POINTER(c.c_double), vp]
     lib.nmgp_logpost_grad_host.restype = c.c_int
@@ -142,7 +144,7 @@ def _declare(lib):
     return lib
 
 
-EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_create_hadamard", "nmgp_plan_destroy", "nmgp_logpost_grad", "nmgp_hyper_grad", "nmgp_plan_set_hyper", "nmgp_logpost_grad_hyper",
+EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_create_hadamard", "nmgp_plan_destroy", "nmgp_logpost_grad", "nmgp_hyper_grad", "nmgp_plan_set_hyper", "nmgp_sweep_reduce", "nmgp_logpost_grad_hyper",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_set_graph", "nmgp_plan_graph_replays", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
            "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]

@@ -157,6 +157,12 @@ class LogPosteriorPlan:
             vals, grad, info = out
             if not need_grad:
                 grad = None
+            for t, shape, dt in ((vals, (self.S, _lib.NVALS), torch.float64), (grad, (self.S, self.P), torch.float64),
+                                 (info, (self.S,), torch.int32)):
+                if t is not None and not (isinstance(t, torch.Tensor) and t.device == self.device and t.dtype == dt
+                                          and tuple(t.shape) == shape and t.is_contiguous()):
+                    raise ValueError(f"out buffers must be contiguous {dt} CUDA tensors on {self.device} of shapes "
+                                     f"[S,{_lib.NVALS}], [S,P], [S]")
         else:
             vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
             grad = torch.empty((self.S, self.P), dtype=torch.float64, device=self.device) if need_grad else None

@@ -878,6 +878,11 @@ int nmgp_hyper_grad(nmgp_plan* pl, const double* pars, double* hgrad, void* stre
   return 0;
 }
 
+int nmgp_sweep_reduce(const double* vals, const double* hgrad, const int* info, long S, double* out17, void* stream) {
+  if (S < 0 || !out17 || (S > 0 && (!vals || !info))) { set_last_error("nmgp_sweep_reduce: bad arguments"); return NMGP_EINVAL; }
+  return launch_sweep_reduce(vals, hgrad, info, S, out17, (cudaStream_t)stream);
+}
+
 int nmgp_plan_set_hyper(nmgp_plan* pl, const double* hyper, void* stream) {
   if (!pl || !hyper) { set_last_error("nmgp_plan_set_hyper: null argument"); return NMGP_EINVAL; }
   for (int k = 0; k < NMGP_NHYPER; ++k)

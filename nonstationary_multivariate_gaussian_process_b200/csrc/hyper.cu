@@ -174,7 +174,39 @@ __global__ void hyper_finish_kernel(int model, int cs, int N, int M, int P, cons
   }
 }
 
+// One rank's contribution to the sweep's all-reduce, in one launch and in a fixed summation order:
+// out[0..5] = sum over the successful subjects (info == 0) of vals[s][0..5], out[6] = #failed, out[7] = #subjects,
+// out[8..16] = sum over the successful subjects of hgrad[s][0..8] (zeros when hgrad == NULL).
+__global__ void __launch_bounds__(1024) sweep_reduce_kernel(const double* __restrict__ vals, const double* __restrict__ hgrad,
+                                                            const int* __restrict__ info, long S, double* __restrict__ out) {
+  __shared__ double scratch[40];
+  double acc[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) acc[k] = 0.0;
+  for (long s = threadIdx.x; s < S; s += blockDim.x) {
+    if (info[s] != 0) { acc[6] += 1.0; continue; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] += vals[s * 6 + k];
+    if (hgrad) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[8 + k] += hgrad[s * 9 + k];
+    }
+  }
+  acc[7] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    const double t = block_sum(acc[k], scratch);
+    if (threadIdx.x == 0) out[k] = (k == 7) ? (double)S : t;
+  }
+}
+
 }  // namespace
+
+int launch_sweep_reduce(const double* vals, const double* hgrad, const int* info, long S, double* out, cudaStream_t st) {
+  sweep_reduce_kernel<<<1, 1024, 0, st>>>(vals, hgrad, info, S, out);
+  NMGP_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 
 #define NMGP_LAUNCH_CHECK()                 \
   do {                                      \

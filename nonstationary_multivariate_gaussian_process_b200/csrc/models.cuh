@@ -132,6 +132,7 @@ int launch_sep_prep(int model, int cs, int N, int M, const double* Y, const doub
                     const Scratch& w, cudaStream_t st, long* launches);
 int prior_traces(const double* x, const double* Lp, int cs, int N, double alpha, double beta, double* scratch, double* trI,
                  double* trB, cudaStream_t st, long* launches);
+int launch_sweep_reduce(const double* vals, const double* hgrad, const int* info, long S, double* out, cudaStream_t st);
 int prior_quad_blocks(int N);   // partial sums per subject written by launch_prior_quad: out is [cs][blocks][4]
 int launch_prior_quad(const double* x, const double* Z, const double* G, int cs, int N, int nv, double alpha, double beta,
                       double* out, cudaStream_t st, long* launches);

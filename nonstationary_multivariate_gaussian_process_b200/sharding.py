@@ -57,8 +57,24 @@ def local_hyper_grad(hgrad, info):
 
 
 def local_sweep_vector(vals, info, hgrad=None):
-    """One rank's contribution to the sweep's single all-reduce: [summary (8) | shared-hyper-parameter gradient (9)]."""
+    """One rank's contribution to the sweep's single all-reduce: [summary (8) | shared-hyper-parameter gradient (9)].
+    CUDA tensors: one launch of the library's own reduction (nmgp_sweep_reduce, fixed summation order); host tensors (the
+    gloo tests): the same sums with torch."""
     import torch
+    if vals.is_cuda:
+        import ctypes
+
+        from . import _lib
+        v = vals.detach().to(torch.float64).contiguous()
+        i = info.to(torch.int32).contiguous()
+        h = hgrad.detach().to(torch.float64).contiguous() if hgrad is not None else None
+        out = torch.empty(len(SUMMARY_FIELDS) + 9, dtype=torch.float64, device=vals.device)
+        with torch.cuda.device(vals.device):
+            stream = torch.cuda.current_stream(vals.device).cuda_stream
+            rc = _lib.load_library().nmgp_sweep_reduce(v.data_ptr(), h.data_ptr() if h is not None else None, i.data_ptr(),
+                                                       int(v.shape[0]), out.data_ptr(), ctypes.c_void_p(stream))
+        _lib.check(rc, "nmgp_sweep_reduce")
+        return out
     s = local_summary(vals, info)
     h = local_hyper_grad(hgrad, info) if hgrad is not None else torch.zeros(9, dtype=torch.float64, device=vals.device)
     return torch.cat([s, h])

@@ -137,3 +137,22 @@ def test_tied_hyper_descent_lowers_the_summed_objective(cuda_device):
             hy[k] -= 1e-3 * shared[k]      # curvature of the sum in mu_L is ~46: a stable step
         plan.set_hyper(hy)
     assert totals[-1] < totals[0] and all(b <= a for a, b in zip(totals, totals[1:])), totals
+
+
+def test_sweep_reduce_kernel_equals_the_torch_sums(cuda_device):
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200 import sharding
+    rng = np.random.RandomState(3)
+    for S in (1, 7, 1000, 10000):
+        vals = torch.from_numpy(rng.standard_normal((S, 6)))
+        hg = torch.from_numpy(rng.standard_normal((S, 9)))
+        info = torch.from_numpy((rng.rand(S) < 0.1).astype(np.int32) * 4)
+        vals[info != 0] = float("nan")
+        hg[info != 0] = float("nan")
+        want = sharding.local_sweep_vector(vals, info, hg)                       # host tensors: torch sums
+        got = sharding.local_sweep_vector(vals.to(cuda_device), info.to(cuda_device), hg.to(cuda_device))
+        got2 = sharding.local_sweep_vector(vals.to(cuda_device), info.to(cuda_device), hg.to(cuda_device))
+        assert torch.equal(got, got2)
+        assert torch.allclose(got.cpu(), want, rtol=1e-12, atol=1e-10), (S, got, want)
+        none = sharding.local_sweep_vector(vals.to(cuda_device), info.to(cuda_device), None).cpu()
+        assert torch.equal(none[:8], got.cpu()[:8]) and float(none[8:].abs().max()) == 0.0
