@@ -20,7 +20,7 @@ def pytest_configure(config):
 def golden_cases():
     """log-posterior + gradient fixtures (tests/golden/make_golden.py)"""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("predict", "hadamard", "empirical", "hyper")))
+                  if not os.path.basename(p).startswith(("predict", "hadamard", "empirical", "hyper", "map_")))
 
 
 def hadamard_cases():
