@@ -481,3 +481,98 @@ class LogPosteriorPlan:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------- subjects of unequal shape
+def group_by_shape(shapes):
+    """[(N_0, M_0), (N_1, M_1), ...] -> {(N, M): [subject indices in input order]} (insertion-ordered by first occurrence)."""
+    groups: dict = {}
+    for i, sh in enumerate(shapes):
+        groups.setdefault((int(sh[0]), int(sh[1])), []).append(i)
+    return groups
+
+
+class RaggedPlans:
+    """Subjects with their OWN numbers of time points (and outputs): the personalized / real-data drivers fit one patient per
+    process, every patient with a different N (Nonseparable_model_personalized.py, Nonseparable_model_mpiKAISER.py:39-60,
+    Separable_model_personalized.py:26-27).  A `LogPosteriorPlan` batches subjects of one shape; this groups the subjects by
+    (N, M), keeps one plan per shape and presents them in the caller's subject order.  Parameter vectors have different
+    lengths, so they travel as a list of 1-D tensors (host or device) or, for device-resident loops, as the packed
+    per-shape matrices of `pack`."""
+
+    def __init__(self, model: str, xs, Ys, hyper: Mapping[str, float] | None = None, prior: bool = True, device=None,
+                 workspace_limit_bytes: int = 0):
+        torch = _lib.require_cuda()
+        if model in HADAMARD_MODELS:
+            raise ValueError("RaggedPlans covers the regularly sampled models")
+        if len(xs) != len(Ys):
+            raise ValueError(f"got {len(xs)} time-stamp vectors and {len(Ys)} observation matrices")
+        self.model, self.S = model, len(xs)
+        x_t = [torch.as_tensor(x, dtype=torch.float64).reshape(-1) for x in xs]
+        Y_t = [torch.as_tensor(Y, dtype=torch.float64) for Y in Ys]
+        for i, (x, Y) in enumerate(zip(x_t, Y_t)):
+            if Y.dim() != 2 or Y.shape[0] != x.shape[0]:
+                raise ValueError(f"subject {i}: expected x [N] and Y [N,M]; got {tuple(x.shape)} and {tuple(Y.shape)}")
+        self.shapes = [(int(Y.shape[0]), int(Y.shape[1])) for Y in Y_t]
+        self.groups = group_by_shape(self.shapes)
+        self.plans = {}
+        for sh, idx in self.groups.items():
+            self.plans[sh] = LogPosteriorPlan(model, torch.stack([x_t[i] for i in idx]), torch.stack([Y_t[i] for i in idx]),
+                                              hyper, prior=prior, device=device, workspace_limit_bytes=workspace_limit_bytes)
+        self.device = next(iter(self.plans.values())).device if self.plans else torch.device(
+            device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.P = [n_params(model, N, M) for N, M in self.shapes]
+
+    def pack(self, pars_list):
+        """list of S parameter vectors (subject order) -> {shape: [S_shape, P_shape] CUDA float64}."""
+        torch = _lib.require_cuda()
+        if len(pars_list) != self.S:
+            raise ValueError(f"expected {self.S} parameter vectors, got {len(pars_list)}")
+        out = {}
+        for sh, idx in self.groups.items():
+            rows = [torch.as_tensor(pars_list[i], dtype=torch.float64).detach().reshape(-1) for i in idx]
+            for i, r in zip(idx, rows):
+                if r.numel() != self.P[i]:
+                    raise ValueError(f"subject {i}: expected {self.P[i]} parameters for shape {sh}, got {r.numel()}")
+            out[sh] = torch.stack([r.to(self.device) for r in rows]).contiguous()
+        return out
+
+    def unpack(self, packed):
+        """{shape: [S_shape, ...]} -> list of S rows in subject order."""
+        rows = [None] * self.S
+        for sh, idx in self.groups.items():
+            for k, i in enumerate(idx):
+                rows[i] = packed[sh][k]
+        return rows
+
+    def value_and_grad_packed(self, packed, need_grad: bool = True):
+        """{shape: pars} -> {shape: (vals, grad, info)}: one batched evaluation per shape, all stream-ordered, no host sync."""
+        return {sh: self.plans[sh].value_and_grad(packed[sh], need_grad=need_grad) for sh in self.groups}
+
+    def value_and_grad(self, pars_list, need_grad: bool = True):
+        """list of S parameter vectors -> (vals [S,6] CUDA, list of S gradient vectors (CUDA) or None, info [S] CUDA),
+        all in subject order."""
+        torch = _lib.require_cuda()
+        res = self.value_and_grad_packed(self.pack(pars_list), need_grad=need_grad)
+        vals = torch.empty((self.S, _lib.NVALS), dtype=torch.float64, device=self.device)
+        info = torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        for sh, idx in self.groups.items():
+            ix = torch.as_tensor(idx, device=self.device)
+            vals[ix] = res[sh][0]
+            info[ix] = res[sh][2]
+        grads = self.unpack({sh: r[1] for sh, r in res.items()}) if need_grad else None
+        return vals, grads, info
+
+    def map_fit(self, pars_list, steps: int, lr: float, **kw):
+        """`LogPosteriorPlan.map_fit` per shape -> (list of S fitted vectors, info [S]) in subject order."""
+        torch = _lib.require_cuda()
+        packed = self.pack(pars_list)
+        fitted, info = {}, torch.empty((self.S,), dtype=torch.int32, device=self.device)
+        for sh, idx in self.groups.items():
+            fitted[sh], _, inf = self.plans[sh].map_fit(packed[sh], steps, lr, **kw)
+            info[torch.as_tensor(idx, device=self.device)] = inf
+        return self.unpack(fitted), info
+
+    def close(self):
+        for p in self.plans.values():
+            p.close()

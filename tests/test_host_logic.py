@@ -140,3 +140,11 @@ def test_empirical_initialisation_matches_the_reference():
         assert out[7] == int(g["est_tilde_sigma2_err"]) == -4
         S, L_vec = ee.global_estimation(x, Y)
         assert np.allclose(S, g["global_S"], rtol=1e-14) and np.allclose(np.asarray(L_vec), g["global_L_vec"], rtol=1e-13)
+
+
+def test_group_by_shape_keeps_subject_order():
+    from nonstationary_multivariate_gaussian_process_b200.batched import group_by_shape
+    g = group_by_shape([(30, 3), (45, 2), (30, 3), (64, 4), (45, 2), (30, 3)])
+    assert list(g) == [(30, 3), (45, 2), (64, 4)]
+    assert g[(30, 3)] == [0, 2, 5] and g[(45, 2)] == [1, 4] and g[(64, 4)] == [3]
+    assert group_by_shape([]) == {}
