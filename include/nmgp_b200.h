@@ -120,8 +120,7 @@ int nmgp_sweep_reduce(const double* vals_dev, const double* hgrad_dev, const int
  * workspace stay.  Must not run concurrently with an evaluation of the same plan. */
 int nmgp_plan_set_hyper(nmgp_plan* plan, const double* hyper, void* stream);
 
-/* CUDA-graph replay of launch-bound evaluations.  Single-chunk plans whose evaluation is a few hundred small kernels or
- * fewer (the one-subject-per-process MAP / HMC loops of Stationary_model.py:106-131, Separable_model.py:149-231,
+/* CUDA-graph replay of launch-bound evaluations.  Single-chunk plans whose evaluation is at most 256 small kernels (the one-subject-per-process MAP / HMC loops of Stationary_model.py:106-131, Separable_model.py:149-231,
  * Nonseparable_model_mpisim.py:163-207) capture the kernel sequence of nmgp_logpost_grad / nmgp_logpost_grad_host once per
  * buffer tuple and replay it with one cudaGraphLaunch; same kernels, same results bit for bit.  mode 0 = automatic (default),
  * 1 = never (A/B timing, debugging).  nmgp_plan_graph_replays counts the evaluations served by a replay. */

@@ -743,12 +743,18 @@ static void drop_graphs(nmgp_plan* pl) {
 // the plan's own capture stream and launched with cudaGraphLaunch on the caller's stream.  The first evaluation of each
 // variant always launches directly (lazy module loading and the helper streams are not capturable); a failed capture or a
 // caller whose buffers keep moving falls back to direct launches of the same kernels -- never to anything else.
-constexpr long kGraphMaxLaunches = 512;
+// Cap of 256 kernels: measured (profiles/r01_latency_graph.txt) the replay gains 15-25 % up to ~60 kernels and nothing on the
+// chain-bound large-matrix evaluations (n = 5000: 355 kernels, 8.34 vs 8.39 ms; n = 16 384: 1072 kernels, 144 vs 148 ms),
+// whose look-ahead relies on stream priorities.
+static long graph_max_launches() {
+  static const long v = getenv("NMGP_GRAPH_MAX_LAUNCHES") ? atol(getenv("NMGP_GRAPH_MAX_LAUNCHES")) : 256;   // A/B timing
+  return v;
+}
 constexpr int kGraphMaxCaptures = 4;
 static int evaluate_replay(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st) {
   nmgp_plan::GraphSlot& g = pl->gslot[grad ? 1 : 0];
   const bool eligible = pl->graph_mode == 0 && pl->S > 0 && pl->S <= pl->chunk && g.captures <= kGraphMaxCaptures &&
-                        (g.warm == 0 || g.launches <= kGraphMaxLaunches);
+                        (g.warm == 0 || g.launches <= graph_max_launches());
   if (!eligible || g.warm == 0) {
     const int rc = evaluate(pl, pars, vals, grad, info, st, nullptr);
     if (rc == 0) { g.warm++; g.launches = pl->last_launches; }
