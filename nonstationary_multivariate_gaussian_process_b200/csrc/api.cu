@@ -675,7 +675,9 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     const bool overlap = pl->nprior && !phase_ms && pl->side;
     cudaStream_t ps_st = overlap ? pl->side : st;
     auto prior_solves = [&]() -> int {
-      if (!pl->nprior) return 0;
+      // the hyper-parameter gradient needs only the prep outputs and these solves: it rides on the same (side) stream,
+      // beside the factorisation
+      if (!pl->nprior) return hgrad ? hyper_chunk(pl, hraw, s0, cs, ps, hgrad, ps_st, &launches) : 0;
       const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
       const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
       NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, ps_st, &launches));
@@ -684,6 +686,7 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
         NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, ps_st, &launches));
         NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, ps_st, &launches));
       }
+      if (hgrad) NMGP_TRY(hyper_chunk(pl, hraw, s0, cs, ps, hgrad, ps_st, &launches));
       return 0;
     };
     if (overlap) {
@@ -709,7 +712,6 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     } else {
       NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, pl->w, b, h0, h1, vs, gs, is, st, &launches));
     }
-    if (hgrad) NMGP_TRY(hyper_chunk(pl, hraw, s0, cs, ps, hgrad, st, &launches));
     NMGP_MARK(5);
     if (sync && sync->after) NMGP_CUDA_TRY(cudaEventRecord(sync->after[ci], st));
     if (phase_ms) {

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) sum_rows_kernel(const double* __restrict_
 //   sg = sum_{i,t} g_it,  gg = sum g_it^2,  rg = sum z_it^2 (= r^T g),  gBg = sum_i sum_j dS_b,ij sum_t g_it g_jt
 // The QRB rows of G sit in shared memory; every thread walks columns j and reads G_j once for all QRB rows.
 constexpr int QRB = 8;
-__global__ void __launch_bounds__(128) prior_quad_kernel(const double* __restrict__ x, const double* __restrict__ Z,
+__global__ void __launch_bounds__(128, 6) prior_quad_kernel(const double* __restrict__ x, const double* __restrict__ Z,
                                                          const double* __restrict__ G, int N, int nv, double alpha2,
                                                          double beta, double* __restrict__ part /*[cs][nblk][4]*/) {
   extern __shared__ double gi[];   // [QRB][nv]
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(128) prior_quad_kernel(const double* __restric
 #pragma unroll
     for (int r = 0; r < QRB; ++r) dot[r] = 0.0;
     const double* gj = Gc + (long)j * nv;
-    for (int t = 0; t < nv; ++t) {
+#pragma unroll 4
+    for (int t = 0; t < nv; ++t) {           // several loads of the G_j row in flight: the kernel is load-latency bound
       const double gjt = gj[t];
 #pragma unroll
       for (int r = 0; r < QRB; ++r) dot[r] += gi[r * nv + t] * gjt;
