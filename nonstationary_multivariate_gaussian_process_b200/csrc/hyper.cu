@@ -79,46 +79,54 @@ __global__ void __launch_bounds__(256) sum_rows_kernel(const double* __restrict_
 //   sg = sum_{i,t} g_it,  gg = sum g_it^2,  rg = sum z_it^2 (= r^T g),  gBg = sum_i sum_j dS_b,ij sum_t g_it g_jt
 // The QRB rows of G sit in shared memory; every thread walks columns j and reads G_j once for all QRB rows.
 constexpr int QRB = 8;
+// A CTA walks `rbpc` consecutive row blocks (many subjects: one CTA per subject, one reduction at the end; a single large
+// subject: one row block per CTA, so that it still spreads over the GPU).
 __global__ void __launch_bounds__(128, 6) prior_quad_kernel(const double* __restrict__ x, const double* __restrict__ Z,
-                                                         const double* __restrict__ G, int N, int nv, double alpha2,
-                                                         double beta, double* __restrict__ part /*[cs][nblk][4]*/) {
+                                                            const double* __restrict__ G, int N, int nv, double alpha2,
+                                                            double beta, int rbpc, double* __restrict__ part /*[cs][parts][4]*/) {
   extern __shared__ double gi[];   // [QRB][nv]
   __shared__ double scratch[40];
   __shared__ double xi[QRB];
-  const int c = blockIdx.y, i0 = blockIdx.x * QRB;
-  const int nr = min(QRB, N - i0);
+  const int c = blockIdx.y;
+  const int nblk = (N + QRB - 1) / QRB;
+  const int rb0 = blockIdx.x * rbpc, rb1 = min(nblk, rb0 + rbpc);
   const double* Gc = G + (long)c * N * nv;
   const double* Zc = Z + (long)c * N * nv;
   const double* xs = x + (long)c * N;
-  double sg = 0.0, gg = 0.0, rg = 0.0, gbg = 0.0;
-  for (int idx = threadIdx.x; idx < QRB * nv; idx += blockDim.x) {
-    double g = 0.0;
-    if (idx < nr * nv) {
-      g = Gc[(long)i0 * nv + idx];
-      const double z = Zc[(long)i0 * nv + idx];
-      sg += g; gg += g * g; rg += z * z;
-    }
-    gi[idx] = g;                                          // rows past N: zero, their weights drop out
-  }
-  if (threadIdx.x < QRB) xi[threadIdx.x] = threadIdx.x < nr ? xs[i0 + threadIdx.x] : 0.0;
-  __syncthreads();
   const double ib2 = 1.0 / (beta * beta);
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    double dot[QRB];
-#pragma unroll
-    for (int r = 0; r < QRB; ++r) dot[r] = 0.0;
-    const double* gj = Gc + (long)j * nv;
-#pragma unroll 4
-    for (int t = 0; t < nv; ++t) {           // several loads of the G_j row in flight: the kernel is load-latency bound
-      const double gjt = gj[t];
-#pragma unroll
-      for (int r = 0; r < QRB; ++r) dot[r] += gi[r * nv + t] * gjt;
+  double sg = 0.0, gg = 0.0, rg = 0.0, gbg = 0.0;
+  for (int rb = rb0; rb < rb1; ++rb) {
+    const int i0 = rb * QRB;
+    const int nr = min(QRB, N - i0);
+    __syncthreads();                                        // the previous row block's gi / xi are no longer read
+    for (int idx = threadIdx.x; idx < QRB * nv; idx += blockDim.x) {
+      double g = 0.0;
+      if (idx < nr * nv) {
+        g = Gc[(long)i0 * nv + idx];
+        const double z = Zc[(long)i0 * nv + idx];
+        sg += g; gg += g * g; rg += z * z;
+      }
+      gi[idx] = g;                                          // rows past N: zero, their weights drop out
     }
-    const double xj = xs[j];
+    if (threadIdx.x < QRB) xi[threadIdx.x] = threadIdx.x < nr ? xs[i0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      double dot[QRB];
 #pragma unroll
-    for (int r = 0; r < QRB; ++r) {
-      const double d = xi[r] - xj, d2 = d * d;            // D_ii = 0: the diagonal drops out by itself
-      gbg += exp(-0.5 * d2 * ib2) * d2 * dot[r];
+      for (int r = 0; r < QRB; ++r) dot[r] = 0.0;
+      const double* gj = Gc + (long)j * nv;
+#pragma unroll 4
+      for (int t = 0; t < nv; ++t) {           // several loads of the G_j row in flight: the kernel is load-latency bound
+        const double gjt = gj[t];
+#pragma unroll
+        for (int r = 0; r < QRB; ++r) dot[r] += gi[r * nv + t] * gjt;
+      }
+      const double xj = xs[j];
+#pragma unroll
+      for (int r = 0; r < QRB; ++r) {
+        const double d = xi[r] - xj, d2 = d * d;            // D_ii = 0: the diagonal drops out by itself
+        gbg += exp(-0.5 * d2 * ib2) * d2 * dot[r];
+      }
     }
   }
   gbg *= alpha2 / (beta * beta * beta);
@@ -242,11 +250,22 @@ int prior_traces(const double* x, const double* Lp, int cs, int N, double alpha,
 
 int prior_quad_blocks(int N) { return (N + QRB - 1) / QRB; }
 
+// row blocks per CTA and the resulting number of partial sums per subject for a launch over `cs` subjects
+static int quad_rbpc(int N, int cs) {
+  const int nblk = prior_quad_blocks(N);
+  long rbpc = (long)nblk * cs / 4096;
+  if (rbpc < 1) rbpc = 1;
+  if (rbpc > nblk) rbpc = nblk;
+  return (int)rbpc;
+}
+static int quad_parts(int N, int cs) { const int r = quad_rbpc(N, cs); return (prior_quad_blocks(N) + r - 1) / r; }
+
 int launch_prior_quad(const double* x, const double* Z, const double* G, int cs, int N, int nv, double alpha, double beta,
                       double* out, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
-  dim3 grid(prior_quad_blocks(N), cs);
-  prior_quad_kernel<<<grid, 128, (size_t)QRB * nv * sizeof(double), st>>>(x, Z, G, N, nv, alpha * alpha, beta, out);
+  dim3 grid(quad_parts(N, cs), cs);
+  prior_quad_kernel<<<grid, 128, (size_t)QRB * nv * sizeof(double), st>>>(x, Z, G, N, nv, alpha * alpha, beta, quad_rbpc(N, cs),
+                                                                          out);
   NMGP_LAUNCH_CHECK();
   return 0;
 }
@@ -256,7 +275,7 @@ int launch_hyper_finish(int model, int cs, int N, int M, int P, const double* pa
                         const double* trB1, int nv1, double* hgrad, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   hyper_finish_kernel<<<(cs + 127) / 128, 128, 0, st>>>(model, cs, N, M, P, pars, h, s2v, q0, q1, trI0, trB0, trI1, trB1, nv1,
-                                                        prior_quad_blocks(N), hgrad);
+                                                        quad_parts(N, cs), hgrad);
   NMGP_LAUNCH_CHECK();
   return 0;
 }
