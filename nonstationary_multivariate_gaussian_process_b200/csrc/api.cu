@@ -67,6 +67,10 @@ struct nmgp_plan {
   // side stream: the GP-prior triangular solves are independent of the factorisation and run beside it
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // second side stream: the two priors' solves are independent chains of small kernels (single-subject plans: the longest
+  // chain of the whole evaluation), so each prior gets its own stream
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ev_join2 = nullptr;
   // host-buffer call: copy streams and per-chunk events, so that the H2D of chunk c+1 and the D2H of chunk c-1 run
   // under the evaluation of chunk c
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -380,6 +384,8 @@ int nmgp_plan_destroy(nmgp_plan* pl) {
   if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
   if (pl->ev_join) cudaEventDestroy(pl->ev_join);
   if (pl->side) cudaStreamDestroy(pl->side);
+  if (pl->ev_join2) cudaEventDestroy(pl->ev_join2);
+  if (pl->side2) cudaStreamDestroy(pl->side2);
   if (pl->ev_start) cudaEventDestroy(pl->ev_start);
   for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : pl->ev_done) cudaEventDestroy(e);
@@ -512,6 +518,8 @@ static int plan_create_impl(nmgp_plan** out, int model, int S, int N, int M, con
     }
     if (pl->nprior) {
       if (cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&pl->side2, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&pl->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         set_last_error("nmgp_plan_create: creating the side stream failed"); rc = NMGP_ECUDA; break;
@@ -672,19 +680,23 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     // The prior solves only need the residuals written by the forward pass.  In the normal call they run on the plan's
     // side stream beside the factorisation (fork/join with events, so the call stays stream-ordered on `st`); the
     // profiling call keeps them on `st` so that every phase is timed alone.
-    const bool overlap = pl->nprior && !phase_ms && pl->side;
-    cudaStream_t ps_st = overlap ? pl->side : st;
+    const bool overlap = pl->nprior && !phase_ms && pl->side && pl->side2;
+    cudaStream_t ps_st = overlap ? pl->side : st;     // prior 0, then the hyper-parameter gradient
+    cudaStream_t ps_st1 = overlap ? pl->side2 : st;   // prior 1
     auto prior_solves = [&]() -> int {
-      // the hyper-parameter gradient needs only the prep outputs and these solves: it rides on the same (side) stream,
+      // the hyper-parameter gradient needs only the prep outputs and these solves: it rides on the side stream too,
       // beside the factorisation
       if (!pl->nprior) return hgrad ? hyper_chunk(pl, hraw, s0, cs, ps, hgrad, ps_st, &launches) : 0;
       const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
       const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
+      const bool back = grad || hgrad;
       NMGP_TRY(launch_prior_solve(L0, pl->w.R0, pl->w.Z0, cs, N, 1, 0, ps_st, &launches));
-      NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, ps_st, &launches));
-      if (grad || hgrad) {
-        NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, ps_st, &launches));
-        NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, ps_st, &launches));
+      if (back) NMGP_TRY(launch_prior_solve(L0, pl->w.Z0, pl->w.G0, cs, N, 1, 1, ps_st, &launches));
+      NMGP_TRY(launch_prior_solve(L1, pl->w.R1, pl->w.Z1, cs, N, pl->nv1, 0, ps_st1, &launches));
+      if (back) NMGP_TRY(launch_prior_solve(L1, pl->w.Z1, pl->w.G1, cs, N, pl->nv1, 1, ps_st1, &launches));
+      if (overlap) {
+        NMGP_CUDA_TRY(cudaEventRecord(pl->ev_join2, pl->side2));
+        NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_join2, 0));
       }
       if (hgrad) NMGP_TRY(hyper_chunk(pl, hraw, s0, cs, ps, hgrad, ps_st, &launches));
       return 0;
@@ -692,6 +704,7 @@ static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* gra
     if (overlap) {
       NMGP_CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
       NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fork, 0));
+      NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side2, pl->ev_fork, 0));
       NMGP_TRY(prior_solves());
       NMGP_CUDA_TRY(cudaEventRecord(pl->ev_join, pl->side));
     }
