@@ -88,3 +88,75 @@ def all_reduce_sweep(vec, hyper_names=(), group=None):
     v = vec.tolist()
     n = len(SUMMARY_FIELDS)
     return dict(zip(SUMMARY_FIELDS, v[:n])), dict(zip(hyper_names, v[n:n + len(hyper_names)]))
+
+
+# hyper-parameters that must stay positive are stepped in log space
+POSITIVE_HYPER = ("alpha_tilde_l", "beta_tilde_l", "alpha_tilde_sigma", "beta_tilde_sigma", "alpha_L", "beta_L", "sigma_tilde_l",
+                  "a", "b", "c")
+
+
+class HyperAdam:
+    """Adam on the tied hyper-parameters (host scalars).  Every rank feeds it the same all-reduced gradient, so every rank
+    takes the same step: the shared values never need a broadcast.  Positive hyper-parameters move in log space."""
+
+    def __init__(self, hyper, tied, lr, betas=(0.9, 0.999), eps=1e-8):
+        import math
+        self.tied = tuple(tied)
+        unknown = [k for k in self.tied if k not in hyper]
+        if unknown:
+            raise KeyError(f"tied hyper-parameters {unknown} are not hyper-parameters of this plan")
+        self.lr, self.b1, self.b2, self.eps, self.t = float(lr), float(betas[0]), float(betas[1]), float(eps), 0
+        self.m = {k: 0.0 for k in self.tied}
+        self.v = {k: 0.0 for k in self.tied}
+        self._log, self._exp = math.log, math.exp
+
+    def step(self, hyper, grad):
+        """hyper: current values; grad: d(sum of -log posterior)/d hyper -> new dict (untied keys unchanged)."""
+        self.t += 1
+        new = dict(hyper)
+        for k in self.tied:
+            pos = k in POSITIVE_HYPER
+            h = float(hyper[k])
+            g = float(grad[k]) * (h if pos else 1.0)              # chain rule for theta = log h
+            if g != g:                                            # a sweep without a valid subject: leave the value alone
+                continue
+            self.m[k] = self.b1 * self.m[k] + (1.0 - self.b1) * g
+            self.v[k] = self.b2 * self.v[k] + (1.0 - self.b2) * g * g
+            mhat = self.m[k] / (1.0 - self.b1 ** self.t)
+            vhat = self.v[k] / (1.0 - self.b2 ** self.t)
+            theta = (self._log(h) if pos else h) - self.lr * mhat / (vhat ** 0.5 + self.eps)
+            new[k] = self._exp(theta) if pos else theta
+        return new
+
+
+def tied_map_fit(plan, pars0, steps, lr, tied, hyper_lr, group=None, betas=(0.9, 0.999), eps=1e-8):
+    """MAP fit of a sharded population whose subjects SHARE the hyper-parameters in `tied` (BASELINE.json's north star; the
+    reference fixes one dictionary per subject, Nonseparable_model_mpisim.py:311-312): per iteration one fused sweep of this
+    rank's subjects (value, gradient, hyper-gradient), the device-resident Adam step on their parameters
+    (Nonseparable_model_mpisim.py:177-190), ONE all-reduce of 17 doubles, and the same Adam step on the shared
+    hyper-parameters on every rank (`nmgp_plan_set_hyper` re-factors only the prior covariances that moved).
+    Returns (pars [S_local,P] CUDA, hyper dict, trace: list of the all-reduced sweep summaries)."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+    p = torch.as_tensor(pars0, dtype=torch.float64).to(plan.device).reshape(plan.S, plan.P).clone().contiguous()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    from .batched import hyper_vector
+    hyper = dict(zip(plan.hyper_names(), (float(x) for x in hyper_vector(plan.model, plan.hyper))))
+    opt = HyperAdam(hyper, tied, hyper_lr, betas, eps)
+    names, trace = plan.hyper_names(), []
+    with torch.cuda.device(plan.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(plan.device).cuda_stream)
+        for it in range(1, int(steps) + 1):
+            vals, grad, hgrad, info = plan.value_grad_and_hyper_grad(p)
+            if plan.S > 0:
+                _lib.check(plan.lib.nmgp_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), info.data_ptr(), None,
+                                                   plan.S, plan.P, float(lr), float(betas[0]), float(betas[1]), float(eps), it,
+                                                   stream), "nmgp_adam_step")
+            totals, shared = all_reduce_sweep(local_sweep_vector(vals, info, hgrad), names, group=group)
+            trace.append(totals)
+            hyper = opt.step(hyper, shared)
+            plan.set_hyper(hyper)
+    return p, hyper, trace

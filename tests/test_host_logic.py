@@ -148,3 +148,29 @@ def test_group_by_shape_keeps_subject_order():
     assert list(g) == [(30, 3), (45, 2), (64, 4)]
     assert g[(30, 3)] == [0, 2, 5] and g[(45, 2)] == [1, 4] and g[(64, 4)] == [3]
     assert group_by_shape([]) == {}
+
+
+def test_hyper_adam_matches_torch_adam_and_keeps_positive_values_positive():
+    """HyperAdam on (mu, log alpha): the same trajectory as torch.optim.Adam on those coordinates; untied keys untouched."""
+    import math
+    from nonstationary_multivariate_gaussian_process_b200.sharding import HyperAdam
+    hyper = {"mu_L": 0.3, "alpha_L": 2.0, "beta_L": 1.0}
+    opt = HyperAdam(hyper, ("mu_L", "alpha_L"), lr=0.05)
+    mu = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    la = torch.tensor(math.log(2.0), dtype=torch.float64, requires_grad=True)
+    ref = torch.optim.Adam([mu, la], lr=0.05)
+    for _ in range(25):
+        # objective f = (mu - 1)^2 + (alpha - 0.5)^2 + alpha * mu
+        g = {"mu_L": 2 * (hyper["mu_L"] - 1) + hyper["alpha_L"], "alpha_L": 2 * (hyper["alpha_L"] - 0.5) + hyper["mu_L"],
+             "beta_L": 123.0}
+        hyper = opt.step(hyper, g)
+        ref.zero_grad()
+        f = (mu - 1) ** 2 + (torch.exp(la) - 0.5) ** 2 + torch.exp(la) * mu
+        f.backward()
+        ref.step()
+    assert abs(hyper["mu_L"] - float(mu)) < 1e-12 and abs(hyper["alpha_L"] - float(torch.exp(la))) < 1e-12
+    assert hyper["beta_L"] == 1.0 and hyper["alpha_L"] > 0
+    with pytest.raises(KeyError):
+        HyperAdam(hyper, ("nope",), lr=0.1)
+    nan = opt.step(hyper, {"mu_L": float("nan"), "alpha_L": float("nan")})
+    assert nan["mu_L"] == hyper["mu_L"] and nan["alpha_L"] == hyper["alpha_L"]
