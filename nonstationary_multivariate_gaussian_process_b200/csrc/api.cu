@@ -47,6 +47,8 @@ struct nmgp_plan {
   double *trI0 = nullptr, *trB0 = nullptr, *trI1 = nullptr, *trB1 = nullptr;  // [S]
   double *hq0 = nullptr, *hq1 = nullptr;                                       // [chunk][prior_quad_blocks(N)][4]
   bool traces_ready = false;
+  double* trace_scratch = nullptr;   // kept between calls: a tied-hyper-prior loop re-forms the traces every iteration
+  size_t trace_cap = 0;              // subjects per pass through trace_scratch
   // CUDA-graph replay of launch-bound evaluations (single-chunk plans with few launches; see evaluate_replay)
   struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
@@ -378,6 +380,7 @@ int nmgp_plan_destroy(nmgp_plan* pl) {
   if (!pl) return 0;
   for (void* p : pl->allocs) cudaFree(p);
   if (pl->pred_scratch) cudaFree(pl->pred_scratch);
+  if (pl->trace_scratch) cudaFree(pl->trace_scratch);
   for (auto& g : pl->gslot)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (pl->gcap) cudaStreamDestroy(pl->gcap);
@@ -588,29 +591,32 @@ static int ensure_prior_traces(nmgp_plan* pl, cudaStream_t st) {
     NMGP_TRY(dev_alloc(pl, &pl->trB1, S));
   }
   const size_t per = 3 * N * N + 2 * N;                    // doubles of scratch per subject (prior_traces)
-  size_t cap = ((size_t)512 << 20) / (per * sizeof(double));
-  if (cap < 1) cap = 1;
-  if (cap > S) cap = S;
-  if (cap > 65535) cap = 65535;
-  double* scratch = nullptr;
-  if (cudaMalloc(&scratch, cap * per * sizeof(double)) != cudaSuccess) {
-    cudaGetLastError();
-    set_last_error("nmgp_hyper_grad: out of device memory for the trace scratch");
-    return NMGP_ENOMEM;
+  if (!pl->trace_scratch) {
+    size_t cap = ((size_t)512 << 20) / (per * sizeof(double));
+    if (cap < 1) cap = 1;
+    if (cap > S) cap = S;
+    if (cap > 65535) cap = 65535;
+    if (cudaMalloc(&pl->trace_scratch, cap * per * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      pl->trace_scratch = nullptr;
+      set_last_error("nmgp_hyper_grad: out of device memory for the trace scratch");
+      return NMGP_ENOMEM;
+    }
+    pl->trace_cap = cap;
+    pl->dev_bytes += cap * per * sizeof(double);
   }
-  int rc = 0;
-  for (size_t s0 = 0; s0 < S && rc == 0; s0 += cap) {
+  const size_t cap = pl->trace_cap;
+  double* scratch = pl->trace_scratch;
+  // stream-ordered on `st`: no host synchronisation, the scratch stays with the plan
+  for (size_t s0 = 0; s0 < S; s0 += cap) {
     const int cs = (int)(S - s0 < cap ? S - s0 : cap);
-    rc = prior_traces(pl->x + s0 * N, pl->Wp0 + s0 * N * N, cs, (int)N, pl->hyper[1], pl->hyper[2], scratch, pl->trI0 + s0,
-                      pl->trB0 + s0, st, nullptr);
-    if (rc == 0)
-      rc = prior_traces(pl->x + s0 * N, pl->Wp1 + s0 * N * N, cs, (int)N, pl->hyper[4], pl->hyper[5], scratch, pl->trI1 + s0,
-                        pl->trB1 + s0, st, nullptr);
+    NMGP_TRY(prior_traces(pl->x + s0 * N, pl->Wp0 + s0 * N * N, cs, (int)N, pl->hyper[1], pl->hyper[2], scratch, pl->trI0 + s0,
+                          pl->trB0 + s0, st, nullptr));
+    NMGP_TRY(prior_traces(pl->x + s0 * N, pl->Wp1 + s0 * N * N, cs, (int)N, pl->hyper[4], pl->hyper[5], scratch, pl->trI1 + s0,
+                          pl->trB1 + s0, st, nullptr));
   }
-  if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) { set_last_error("nmgp_hyper_grad: trace kernels failed"); rc = NMGP_ECUDA; }
-  cudaFree(scratch);
-  if (rc == 0) pl->traces_ready = true;
-  return rc;
+  pl->traces_ready = true;
+  return 0;
 }
 
 static int hyper_setup(nmgp_plan* pl, cudaStream_t st, HyperRaw* h) {
