@@ -131,30 +131,38 @@ def make_inputs(a, lo, hi, device):
     T = M * (M + 1) // 2
     x = np.empty((S, N))
     pars = np.empty((S, {"stationary": T + 3, "separable": 2 * N + T + 1, "nonseparable": N + N * T + 1}[a.model]))
-    truth = np.empty((S, N + N * T + 1))
     for i, s in enumerate(range(lo, hi)):
-        xs, tl, uL, ts2 = synth.truth(N, M, s)
-        x[i] = xs
-        truth[i] = np.concatenate([tl, uL.reshape(-1), [ts2]])
+        x[i] = synth.truth(N, M, s)[0]
         pars[i] = synth.start_point(a.model, N, M, s)
     lib = _lib.load_library()
     n = N * M
     Y = torch.empty((S, N, M), dtype=torch.float64, device=device)
     gen = torch.Generator(device=device)
-    step = max(1, min(S, int((2 << 30) // (n * n * 8))))
     stream = torch.cuda.current_stream().cuda_stream
-    for s0 in range(0, S, step):
-        cs = min(step, S - s0)
-        xd = torch.from_numpy(x[s0:s0 + cs]).to(device)
-        td = torch.from_numpy(truth[s0:s0 + cs]).to(device)
+    # Observations are drawn in fixed GLOBAL blocks of subjects, one seed per block, whatever the sharding: every subject gets
+    # the same Y at 1, 2, 4 or 8 ranks, so `sweep_summary` of the runs is comparable (a rank generates the whole block it
+    # overlaps and keeps its part).
+    blk = max(1, min(250, int((2 << 30) // (n * n * 8))))
+    for g0 in range((lo // blk) * blk, hi, blk):
+        g1 = min(g0 + blk, a.subjects)
+        cs = g1 - g0
+        xb = np.empty((cs, N))
+        tb = np.empty((cs, N + N * T + 1))
+        for i, s in enumerate(range(g0, g1)):
+            xs, tl, uL, ts2 = synth.truth(N, M, s)
+            xb[i] = xs
+            tb[i] = np.concatenate([tl, uL.reshape(-1), [ts2]])
+        xd = torch.from_numpy(xb).to(device)
+        td = torch.from_numpy(tb).to(device)
         cov = torch.empty((cs, n, n), dtype=torch.float64, device=device)
         _lib.check(lib.nmgp_nonseparable_cov(xd.data_ptr(), td.data_ptr(), cs, N, M, cov.data_ptr(),
                                              ctypes.c_void_p(stream)), "nmgp_nonseparable_cov")
         Lc = torch.linalg.cholesky(cov)
-        gen.manual_seed(12345 + lo + s0)
+        gen.manual_seed(12345 + g0)
         z = torch.randn((cs, n, 1), dtype=torch.float64, device=device, generator=gen)
-        y = (Lc @ z).squeeze(-1)                                   # output-major (m*N+i), sim.py:263-264
-        Y[s0:s0 + cs] = y.view(cs, M, N).transpose(1, 2)
+        y = (Lc @ z).squeeze(-1).view(cs, M, N).transpose(1, 2)    # output-major (m*N+i), sim.py:263-264
+        a0, a1 = max(g0, lo), min(g1, hi)
+        Y[a0 - lo:a1 - lo] = y[a0 - g0:a1 - g0]
         del cov, Lc
     return torch.from_numpy(x), Y, torch.from_numpy(pars)
 
