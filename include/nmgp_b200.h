@@ -244,6 +244,33 @@ int nmgp_gibbs_cov(const double* x1, const double* sigma1, const double* ell1, i
  * (The plan itself builds the same matrix time-major and blocked; this entry exists for parity tests.) */
 int nmgp_nonseparable_cov(const double* x, const double* pars, int batch, int N, int M, double* out, void* stream);
 
+/* ---- stand-alone helpers behind the reference-signature mirrors (cold paths; all device pointers, FP64, row-major) ----
+ * nmgp_pairwise_sqdist: out[i,j] = (x1_i^2 + x2_j^2) - 2 x1_i x2_j for N x 1 inputs, x2 NULL = x1
+ *                       (Utility/kernels.py:5-21 `pairwise_distances`, same operation order).
+ * nmgp_kron:            out [h1 h2, w1 w2] = t1 [h1,w1] (x) t2 [h2,w2]
+ *                       (Utility/kronecker_operation.py:5-22 `kronecker_product`; :25-33 `kronecker_product_diag` is w1 = w2 = 1).
+ * nmgp_kron_mv:         out [M1 N1] = (B [M1,M2] (x) K [N1,N2]) y [M2 N2] as vec((K Y) B^T), y output-major; scratch [M2 N1]
+ *                       (Utility/kronecker_operation.py:72-85 `kron_mv`).
+ * nmgp_gram:            out [R,R] = L L^T for the stacked per-time-point factors L [R,M]
+ *                       (Utility/logpos.py:111-118 `generate_K_index_SVC`).
+ * nmgp_sym_eig:         eigenvalues (ascending) and eigenvectors (columns of V [M,M]) of a symmetric M x M matrix, M <= 16,
+ *                       one-warp cyclic Jacobi (what `torch.symeig(B, eigenvectors=True)` returns at
+ *                       Utility/kronecker_operation.py:45, distributions.py:37).
+ * nmgp_kron_eig_solve:  for Sigma = sigma2 I + B (x) K (B [M,M], K [N,N] symmetric, M <= 16): out2[0] = log det Sigma,
+ *                       out2[1] = r^T Sigma^-1 r (0 if r is NULL), inv_out (or NULL) = Sigma^-1 dense [MN,MN], info (or NULL) =
+ *                       0 or the first failing Cholesky pivot.  Block formulation: eig(B) + M Cholesky factorisations of
+ *                       lam_m K + sigma2 I on the batched engine -- no N x N eigensolver.  Stands in for
+ *                       `kron_inv` / `kron_logdet` (Utility/kronecker_operation.py:36-69) and
+ *                       `multivariate_normal_logpdf0/1/2` (Utility/distributions.py:26-113).  Synchronises `stream`. */
+int nmgp_pairwise_sqdist(const double* x1, int N1, const double* x2, int N2, double* out, void* stream);
+int nmgp_kron(const double* t1, int h1, int w1, const double* t2, int h2, int w2, double* out, void* stream);
+int nmgp_kron_mv(const double* B, int M1, int M2, const double* K, int N1, int N2, const double* y, double* out,
+                 double* scratch, void* stream);
+int nmgp_gram(const double* L, int R, int M, double* out, void* stream);
+int nmgp_sym_eig(const double* B, int M, double* lam, double* V, void* stream);
+int nmgp_kron_eig_solve(const double* B, int M, const double* K, int N, double sigma2, double* inv_out, const double* r,
+                        double* out2, int* info, void* stream);
+
 /* Batched blocked Cholesky engine on `batch` symmetric positive-definite matrices [batch, n, n] (row-major,
  * lower triangle referenced).  In place:
  *   potrf: lower triangle <- L (strict upper untouched), logdet[b] = log det A_b, info[b] as above.

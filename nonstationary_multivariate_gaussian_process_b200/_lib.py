@@ -14,8 +14,12 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
-SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "hadamard.cu", "hyper.cu", "api.cu"]
-HEADERS = ["common.cuh", "engine.cuh", "models.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
+# A/B timing of kernel variants (tools/build_variant.py): NMGP_B200_LIB points at another build of the SAME sources with
+# different -D switches.  Not a fallback: the file must exist, and it is this package's own CUDA library either way.
+if os.environ.get("NMGP_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["NMGP_B200_LIB"])
+SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "hadamard.cu", "hyper.cu", "kron.cu", "api.cu"]
+HEADERS = ["common.cuh", "engine.cuh", "models.cuh", "jacobi.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -43,20 +47,24 @@ def _stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu -> libnmgp_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str | None = None,
+                  csrc: str | None = None) -> str:
+    """Compile csrc/*.cu -> libnmgp_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+    `extra_flags` / `out_path` / `csrc` build a variant beside it (tools/build_variant.py)."""
+    lib_path = out_path or os.path.join(_HERE, "libnmgp_b200.so")
+    csrc = csrc or CSRC
+    if not force and not out_path and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    objdir = os.path.join(_HERE, "build")
+    objdir = os.path.join(_HERE, "build", os.path.basename(lib_path)[:-3] if out_path else "")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
-        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        res = subprocess.run(cmd, cwd=csrc, capture_output=True, text=True)
         if res.returncode != 0:
             raise NmgpError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
         return obj
@@ -64,13 +72,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:      # one nvcc per translation unit, in parallel
         objs = list(pool.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs
     if verbose:
         print(" ".join(cmd))
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    res = subprocess.run(cmd, cwd=csrc, capture_output=True, text=True)
     if res.returncode != 0:
         raise NmgpError("nvcc link failed:\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return lib_path
 
 
 def _declare(lib):
@@ -137,6 +145,18 @@ def _declare(lib):
     lib.nmgp_gibbs_cov.argtypes = [dp, dp, dp, c.c_int, dp, dp, dp, c.c_int, dp, vp]
     lib.nmgp_nonseparable_cov.restype = c.c_int
     lib.nmgp_nonseparable_cov.argtypes = [dp, dp, c.c_int, c.c_int, c.c_int, dp, vp]
+    lib.nmgp_pairwise_sqdist.restype = c.c_int
+    lib.nmgp_pairwise_sqdist.argtypes = [dp, c.c_int, dp, c.c_int, dp, vp]
+    lib.nmgp_kron.restype = c.c_int
+    lib.nmgp_kron.argtypes = [dp, c.c_int, c.c_int, dp, c.c_int, c.c_int, dp, vp]
+    lib.nmgp_kron_mv.restype = c.c_int
+    lib.nmgp_kron_mv.argtypes = [dp, c.c_int, c.c_int, dp, c.c_int, c.c_int, dp, dp, dp, vp]
+    lib.nmgp_gram.restype = c.c_int
+    lib.nmgp_gram.argtypes = [dp, c.c_int, c.c_int, dp, vp]
+    lib.nmgp_sym_eig.restype = c.c_int
+    lib.nmgp_sym_eig.argtypes = [dp, c.c_int, dp, dp, vp]
+    lib.nmgp_kron_eig_solve.restype = c.c_int
+    lib.nmgp_kron_eig_solve.argtypes = [dp, c.c_int, dp, c.c_int, c.c_double, dp, dp, dp, ip, vp]
     lib.nmgp_potrf_batched.restype = c.c_int
     lib.nmgp_potrf_batched.argtypes = [dp, c.c_int, c.c_int, dp, ip, vp]
     lib.nmgp_potrf_potri_batched.restype = c.c_int
@@ -146,7 +166,7 @@ def _declare(lib):
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_create_hadamard", "nmgp_plan_destroy", "nmgp_logpost_grad", "nmgp_hyper_grad", "nmgp_plan_set_hyper", "nmgp_sweep_reduce", "nmgp_logpost_grad_hyper",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_set_graph", "nmgp_plan_graph_replays", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
-           "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_potrf_batched",
+           "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_pairwise_sqdist", "nmgp_kron", "nmgp_kron_mv", "nmgp_gram", "nmgp_sym_eig", "nmgp_kron_eig_solve", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 
 

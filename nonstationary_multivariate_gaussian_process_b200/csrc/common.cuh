@@ -1,6 +1,7 @@
 // Shared helpers for the NMGP B200 kernels (sm_100a, FP64).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -25,6 +26,37 @@ void set_last_error(const std::string& msg);  // api.cu
     int _r = (expr);              \
     if (_r != 0) return _r;       \
   } while (0)
+
+// Function attributes (dynamic shared memory above 48 KB) belong to the (function, device) pair, not to the process: a
+// plan on cuda:1 after one on cuda:0 must set them again.  One flag per device and call site; a lost race only repeats
+// the (idempotent) call.  `kernel` may be a parenthesised template-id.
+constexpr int kMaxDevices = 64;
+#define NMGP_SMEM_ATTR_PER_DEVICE(kernel, bytes)                                                                  \
+  do {                                                                                                            \
+    static std::atomic<size_t> _nmgp_done[::nmgp::kMaxDevices];                                                   \
+    int _dev = 0;                                                                                                 \
+    NMGP_CUDA_TRY(cudaGetDevice(&_dev));                                                                          \
+    const bool _slot = _dev >= 0 && _dev < ::nmgp::kMaxDevices;                                                   \
+    if (!_slot || _nmgp_done[_dev].load(std::memory_order_acquire) < (size_t)(bytes)) {                           \
+      NMGP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      if (_slot) _nmgp_done[_dev].store((size_t)(bytes), std::memory_order_release);                              \
+    }                                                                                                             \
+  } while (0)
+
+// number of SMs of the current device (148 on B200; never hard-coded in grid sizing)
+inline int sm_count() {
+  static std::atomic<int> cached[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < kMaxDevices) {
+    const int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < kMaxDevices) cached[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
 
 constexpr double kJitter = 1e-6;  // Utility/settings.py:3
 

@@ -283,11 +283,7 @@ __global__ void __launch_bounds__(NB) trsm_panel_kernel(EngineArgs g) {
 template <int MODE>
 int launch_tiles(const EngineArgs& g, int ntiles, cudaStream_t st, long* launches) {
   if (ntiles <= 0 || g.batch <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    configured = true;
-  }
+  NMGP_SMEM_ATTR_PER_DEVICE(tile_kernel<MODE>, TILE_SMEM);
   dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
   tile_kernel<MODE><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g);
   NMGP_CUDA_TRY(cudaGetLastError());
@@ -310,11 +306,7 @@ int launch_panel(const BlockBatch& b, const EngineArgs& g, int r, bool stable_pa
   if (r <= 0) return 0;
   dim3 pg(r, b.batch < 65535 ? b.batch : 65535);
   constexpr size_t kTrsmSmem = 2ull * NB * (NB + 1) * sizeof(double);
-  static bool trsm_configured = false;
-  if (!trsm_configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
-    trsm_configured = true;
-  }
+  NMGP_SMEM_ATTR_PER_DEVICE(trsm_panel_kernel, kTrsmSmem);
   trsm_panel_kernel<<<pg, NB, kTrsmSmem, st>>>(g);
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
@@ -327,11 +319,7 @@ int launch_syrk_wide(const EngineArgs& g, int ja, int jb, int kb0, int nkb, cuda
   if (TRI) { const int r = g.Kt - ja; ntiles = r * (r + 1) / 2; }
   else for (int j = ja; j < jb; ++j) ntiles += g.Kt - j;
   if (ntiles <= 0 || nkb <= 0 || g.batch <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(syrk_wide_kernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    configured = true;
-  }
+  NMGP_SMEM_ATTR_PER_DEVICE(syrk_wide_kernel<TRI>, TILE_SMEM);
   dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
   syrk_wide_kernel<TRI><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g, ja, jb, kb0, nkb);
   NMGP_CUDA_TRY(cudaGetLastError());

@@ -17,6 +17,7 @@ struct BlockBatch {
   double* Dinv = nullptr;
   double* Pbuf = nullptr;    // [batch][Kt][NB*NB]  panel side buffer of the left-looking inverse: P(c)^T tiles (zero-initialised once)
   long strideP() const { return (long)Kt * NB * NB; }
+  const void* maps = nullptr;  // TMA descriptors of (A, A2, Dinv, Pbuf) for the FULL workspace (engine_maps_create); owned by the plan
   double* logdet = nullptr;  // [batch]
   int* info = nullptr;       // [batch]
   int n = 0;                 // logical dimension
@@ -55,6 +56,10 @@ int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches)
 // Same result with W = L^-1 formed level by level (two launches of independent long-K tiles per level): for a few large
 // matrices.  Accepts the factor of either potrf engine.  Requires b.A2 and b.Pbuf (tensor maps).
 int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launches);
+// TMA descriptors of a workspace, built once (the maps cover the whole workspace, so they serve every sub-batch of it).
+// `out` receives nullptr when the batch has no panel buffer.  engine_*_ll build a temporary set when b.maps is null.
+int engine_maps_create(const BlockBatch& b, void** out);
+void engine_maps_destroy(void* maps);
 // largest number of 64-blocks per side for which the Takahashi recursion of engine_potri_ll is used (see api.cu)
 constexpr int kTakahashiMaxBlocks = 16;
 

@@ -38,8 +38,9 @@
 #include <cuda.h>
 
 #include <cstdint>
-#include <mutex>
-#include <vector>
+#include <atomic>
+#include <cstdlib>
+#include <new>
 
 namespace nmgp {
 
@@ -48,10 +49,13 @@ namespace {
 constexpr int NB = kNB;      // 64
 constexpr int KC = 16;       // k-chunk per pipeline stage = one 128-byte swizzle row
 constexpr int CPB = NB / KC; // chunks per k-block
-constexpr int STAGES = 3;
+#ifndef NMGP_LL_STAGES
+#define NMGP_LL_STAGES 3
+#endif
+constexpr int STAGES = NMGP_LL_STAGES;
 constexpr int OPB = NB * KC * 8;   // bytes of one operand chunk in shared memory (dense, swizzled): 8192
 constexpr int THREADS = 128;
-constexpr size_t LL_SMEM = (size_t)STAGES * 2 * OPB + 64 + 1024;   // ring + mbarriers + slack for 1024-byte alignment
+constexpr size_t LL_SMEM = (size_t)STAGES * 2 * OPB + 128 + 1024;   // ring + mbarriers (full, empty) + slack for 1024-byte alignment
 
 enum LLMode : int { LL_UPDATE = 0, LL_SOLVE = 1, TK_PANEL = 2, TK_COL = 3, TK_DIAG = 4 };
 
@@ -104,13 +108,44 @@ __device__ __forceinline__ void mma_chunk(const unsigned char* __restrict__ SA, 
   }
 }
 
+// ---- panel_gemm_kernel
+// Work items of one launch: (matrix, tile).  Default (measured best, profiles/r02_engine_ab.txt): grid (gx, batch), CTA
+// (bx, by) takes tiles bx, bx + gx, ... of matrix by and the hardware hands CTAs to SMs as slots free up (a slow CTA delays
+// only its own successor); ~32 waves of CTAs.  Inside a CTA the four warps only meet through the ring: `full[slot]` is
+// completed by the TMA transaction, `empty[slot]` by one arrival per warp, so a warp in its epilogue does not hold up the
+// other three (no CTA-wide barrier in the loop); the producer is thread 0, which issues chunk q + STAGES - 1 once `empty`
+// says that everyone is done with chunk q - 1.
+// Compile-time alternatives kept for A/B timing (tools/build_variant.py), all slower or equal on B200:
+//   NMGP_LL_FLAT=1           persistent grid of exactly the resident CTAs, items dealt round-robin: no partial last wave,
+//                            but static assignment loses to the hardware's dynamic one (+3 % time)
+//   NMGP_LL_PRODUCER_WARP=1  a fifth warp that only issues TMA (3 CTAs/SM at 128 registers, 4 CTAs/SM only at 96 with
+//                            spills): +1.5 % / +20 % time
+//   NMGP_LL_STAGES=4         one more ring stage (3 CTAs/SM): equal
+#ifndef NMGP_LL_PRODUCER_WARP
+#define NMGP_LL_PRODUCER_WARP 0
+#endif
+#ifndef NMGP_LL_FLAT
+#define NMGP_LL_FLAT 0
+#endif
+#ifndef NMGP_LL_CTAS
+#define NMGP_LL_CTAS (NMGP_LL_PRODUCER_WARP ? 3 : 4)
+#endif
+constexpr int PG_THREADS = NMGP_LL_PRODUCER_WARP ? THREADS + 32 : THREADS;
+constexpr int PG_CTAS = NMGP_LL_CTAS;
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 4) panel_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapD,
-                                                                const __grid_constant__ CUtensorMap mapP, LLArgs g) {
+__global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                         const __grid_constant__ CUtensorMap mapD,
+                                                                         const __grid_constant__ CUtensorMap mapP,
+                                                                         LLArgs g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
+  unsigned long long* empty = full + STAGES;
 
   const int s = g.step;
   const int last = g.Kt - 1;
@@ -128,8 +163,98 @@ __global__ void __launch_bounds__(THREADS, 4) panel_gemm_kernel(const __grid_con
   const int nchunks = (nkb - 1) * CPB + ((ragged_k ? vlast : NB) + KC - 1) / KC;
   const int cols_valid = (j == last) ? vlast : NB;
 
-  // Quarter of the tile owned by this warp.  The quarters do unequal work in the triangular modes below and every
-  // warp is pinned to one SM sub-partition (one DMMA pipe each), so the assignment is rotated per CTA.
+  // items of this CTA
+#if NMGP_LL_FLAT
+  const long nitems = (long)g.batch * g.ntiles;
+  const int G = gridDim.x;
+  const int nmy = ((long)blockIdx.x < nitems) ? (int)((nitems - blockIdx.x + G - 1) / G) : 0;
+#else
+  // grid (gx, gy): CTA (bx, by) takes tiles bx, bx + gx, ... of matrices by, by + gy, ...
+  const int per = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nmat_my = ((int)blockIdx.y < g.batch) ? (g.batch - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
+  const int nmy = per * nmat_my;
+#endif
+  const int total = nmy * nchunks;
+  // (matrix, block row) of the tt-th item of this CTA
+  auto item = [&](int tt, int& mat, int& i) {
+#if NMGP_LL_FLAT
+    const long w = (long)blockIdx.x + (long)tt * G;
+    mat = (int)(w / g.ntiles);
+    const int t = (int)(w - (long)mat * g.ntiles);
+#else
+    const int mi = tt / per, ti = tt - mi * per;
+    mat = (int)blockIdx.y + mi * (int)gridDim.y;
+    const int t = (int)blockIdx.x + ti * (int)gridDim.x;
+#endif
+    if (MODE == LL_UPDATE) i = s + t;
+    else if (MODE == TK_DIAG) i = s;
+    else i = s + 1 + t;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < STAGES; ++st) { mbar_init(&full[st], 1); mbar_init(&empty[st], THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- producer: chunk p of this CTA's sequence -> ring slot p % STAGES
+  int p_tt = 0, p_qq = 0, p_mat = 0, p_i = 0;
+  if (nmy > 0) item(0, p_mat, p_i);
+  auto issue = [&](int p) {
+    const int slot = p % STAGES;
+    if (p >= STAGES) mbar_wait(&empty[slot], ((p / STAGES) - 1) & 1);   // all four warps are done with its previous contents
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int qq = p_qq, i = p_i, mat = p_mat;
+    if (++p_qq == nchunks) { p_qq = 0; if (++p_tt < nmy) item(p_tt, p_mat, p_i); }
+    const int kb = qq / CPB, kcol = (qq % CPB) * KC;
+    const int dslot = (mat * g.Kt + s) * 2;    // W_ss (slot + 0) and W_ss^T (slot + 1) in the Dinv tensor
+    const int pslot = mat * g.Kt;              // P(c)^T tiles of this matrix in the Pbuf tensor
+    unsigned char* SA = ring + slot * 2 * OPB;
+    unsigned char* SB = SA + OPB;
+    unsigned long long* bar = &full[slot];
+    mbar_expect_tx(bar, 2 * OPB);
+    if (MODE == LL_UPDATE) {          // A(i,kb) . A(s,kb)^T
+      tma_load_chunk(SA, &mapA, kb * NB + kcol, i * NB, mat, bar);
+      tma_load_chunk(SB, &mapA, kb * NB + kcol, s * NB, mat, bar);
+    } else if (MODE == LL_SOLVE) {    // A(i,s) . W^T          (B[n][k] = W[n][k])
+      tma_load_chunk(SA, &mapA, s * NB + kcol, i * NB, mat, bar);
+      tma_load_chunk(SB, &mapD, kcol, 0, dslot, bar);
+    } else if (MODE == TK_PANEL) {    // L(i,s) . W            (B[n][k] = W^T[n][k])
+      tma_load_chunk(SA, &mapA, s * NB + kcol, i * NB, mat, bar);
+      tma_load_chunk(SB, &mapD, kcol, 0, dslot + 1, bar);
+    } else if (MODE == TK_COL) {      // Z(i,cb) . P(cb)       (B[n][k] = P^T(cb)[n][k])
+      const int cb = s + 1 + kb;
+      tma_load_chunk(SA, &mapA, cb * NB + kcol, i * NB, mat, bar);
+      tma_load_chunk(SB, &mapP, kcol, 0, pslot + cb, bar);
+    } else {
+      if (kb == 0) {                  // W^T W                 (A[m][k] = W^T[m][k], B[n][k] = W^T[n][k])
+        tma_load_chunk(SA, &mapD, kcol, 0, dslot + 1, bar);
+        tma_load_chunk(SB, &mapD, kcol, 0, dslot + 1, bar);
+      } else {                        // P(cb)^T Z(cb,s)       (A[m][k] = P^T(cb)[m][k], B[n][k] = Z(s,cb)[n][k])
+        const int cb = s + kb;
+        tma_load_chunk(SA, &mapP, kcol, 0, pslot + cb, bar);
+        tma_load_chunk(SB, &mapA, cb * NB + kcol, s * NB, mat, bar);
+      }
+    }
+  };
+
+#if NMGP_LL_PRODUCER_WARP
+  if (threadIdx.x >= THREADS) {
+    if (threadIdx.x == THREADS) {
+#pragma unroll 1
+      for (int p = 0; p < total; ++p) issue(p);
+    }
+    return;
+  }
+#else
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int p = 0; p < STAGES - 1 && p < total; ++p) issue(p);
+  }
+#endif
+
+  // ---- consumers.  Quarter of the tile owned by this warp: the quarters do unequal work in the triangular modes below
+  // and every warp is pinned to one SM sub-partition (one DMMA pipe each), so the assignment is rotated per CTA.
   const int warp = ((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & 3, lane = threadIdx.x & 31;
   const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
   const int r = lane >> 2, c = 2 * (lane & 3);
@@ -150,149 +275,84 @@ __global__ void __launch_bounds__(THREADS, 4) panel_gemm_kernel(const __grid_con
     if (MODE == TK_DIAG) return (m0 == NB / 2 || n0 == NB / 2) && qq < HALF;
     return false;
   };
-  // block row of the tt-th tile of this CTA
-  auto tile_row = [&](int tt) -> int {
-    const int t = blockIdx.x + tt * gridDim.x;
-    if (MODE == LL_UPDATE) return s + t;
-    if (MODE == TK_DIAG) return s;
-    return s + 1 + t;
-  };
-  const int nmy = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total = nmy * nchunks;
 
-  if (threadIdx.x == 0) {
-    for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  int gq = 0;   // chunks consumed by this CTA so far (all matrices): ring slot and mbarrier phase follow it
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
-    double* Am = g.A + (long)mat * g.strideA;
-    double* Pm = g.Pbuf + (long)mat * g.strideP;
-    const int dslot = (mat * g.Kt + s) * 2;    // W_ss (slot + 0) and W_ss^T (slot + 1) in the Dinv tensor
-    const int pslot = mat * g.Kt;              // P(c)^T tiles of this matrix in the Pbuf tensor
-
-    // producer side (thread 0 only): the next chunk of this matrix -> ring slot `slot`
-    int itt = 0, iqq = 0;   // tile / chunk-in-tile of the next chunk to be issued
-    auto issue = [&](int slot) {
-      const int tt = itt, qq = iqq;
-      if (++iqq == nchunks) { iqq = 0; ++itt; }
-      const int i = tile_row(tt);
-      const int kb = qq / CPB, kcol = (qq % CPB) * KC;
-      unsigned char* SA = ring + slot * 2 * OPB;
-      unsigned char* SB = SA + OPB;
-      unsigned long long* bar = &full[slot];
-      mbar_expect_tx(bar, 2 * OPB);
-      if (MODE == LL_UPDATE) {          // A(i,kb) . A(s,kb)^T
-        tma_load_chunk(SA, &mapA, kb * NB + kcol, i * NB, mat, bar);
-        tma_load_chunk(SB, &mapA, kb * NB + kcol, s * NB, mat, bar);
-      } else if (MODE == LL_SOLVE) {    // A(i,s) . W^T          (B[n][k] = W[n][k])
-        tma_load_chunk(SA, &mapA, s * NB + kcol, i * NB, mat, bar);
-        tma_load_chunk(SB, &mapD, kcol, 0, dslot, bar);
-      } else if (MODE == TK_PANEL) {    // L(i,s) . W            (B[n][k] = W^T[n][k])
-        tma_load_chunk(SA, &mapA, s * NB + kcol, i * NB, mat, bar);
-        tma_load_chunk(SB, &mapD, kcol, 0, dslot + 1, bar);
-      } else if (MODE == TK_COL) {      // Z(i,cb) . P(cb)       (B[n][k] = P^T(cb)[n][k])
-        const int cb = s + 1 + kb;
-        tma_load_chunk(SA, &mapA, cb * NB + kcol, i * NB, mat, bar);
-        tma_load_chunk(SB, &mapP, kcol, 0, pslot + cb, bar);
+  // ---- epilogue of tile (i, j) of matrix `mat`: registers only
+  auto epilogue = [&](int mat, int i, bool active) {
+    if (active) {
+      double* Am = g.A + (long)mat * g.strideA;
+      if (MODE == TK_PANEL) {   // P(i)^T = -(L(i,s) W)^T
+        double* PT = g.Pbuf + (long)mat * g.strideP + (long)i * NB * NB;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
+            PT[(long)col * NB + row] = -acc[a][b][0];
+            PT[(long)(col + 1) * NB + row] = -acc[a][b][1];
+          }
       } else {
-        if (kb == 0) {                  // W^T W                 (A[m][k] = W^T[m][k], B[n][k] = W^T[n][k])
-          tma_load_chunk(SA, &mapD, kcol, 0, dslot + 1, bar);
-          tma_load_chunk(SB, &mapD, kcol, 0, dslot + 1, bar);
-        } else {                        // P(cb)^T Z(cb,s)       (A[m][k] = P^T(cb)[m][k], B[n][k] = Z(s,cb)[n][k])
-          const int cb = s + kb;
-          tma_load_chunk(SA, &mapP, kcol, 0, pslot + cb, bar);
-          tma_load_chunk(SB, &mapA, cb * NB + kcol, s * NB, mat, bar);
-        }
+        double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
+        // the mirror tile: Z(j,i) = Z(i,j)^T, or the upper-right quarter of the symmetric diagonal tile
+        const bool mirror = (MODE == TK_COL) || (MODE == TK_DIAG && m0 == NB / 2 && n0 == 0);
+        double* U = Am + ((long)j * NB) * g.ld + (long)i * NB;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
+            double2* p = reinterpret_cast<double2*>(C + (long)row * g.ld + col);
+            double2 v;
+            if (MODE == LL_UPDATE) {
+              v = *p;
+              v.x -= acc[a][b][0];
+              v.y -= acc[a][b][1];
+            } else {
+              v.x = acc[a][b][0];
+              v.y = acc[a][b][1];
+            }
+            *p = v;
+            if (mirror) {
+              U[(long)col * g.ld + row] = v.x;
+              U[(long)(col + 1) * g.ld + row] = v.y;
+            }
+          }
       }
-    };
-
-    double acc[4][4][2];
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  };
 
-    if (threadIdx.x == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll 1
-      for (int q = 0; q < STAGES - 1 && q < total; ++q) issue((gq + q) % STAGES);
+  int tt = 0, qq = 0, mat = 0, i = 0;
+  if (nmy > 0) item(0, mat, i);
+  for (int q = 0; q < total; ++q) {
+    const int slot = q % STAGES;
+#if !NMGP_LL_PRODUCER_WARP
+    if (threadIdx.x == 0 && q + STAGES - 1 < total) issue(q + STAGES - 1);
+#endif
+    const int rows_valid = (i == last) ? vlast : NB;
+    // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
+    // of A(k,k); Z(j,j) is symmetric and mirrored in the epilogue)
+    const bool tri_skip = upper_quarter && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
+    const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
+    mbar_wait(&full[slot], (q / STAGES) & 1);
+    if (active && !zero_chunk(qq)) {
+      const unsigned char* SA = ring + slot * 2 * OPB;
+      mma_chunk(SA + (m0 + lr) * 128, SA + OPB + (n0 + lr) * 128, off, acc);
     }
-    // ---- epilogue of tile (i, j): registers only
-    auto epilogue = [&](int i, bool active) {
-      if (active) {
-        if (MODE == TK_PANEL) {   // P(i)^T = -(L(i,s) W)^T
-          double* PT = Pm + (long)i * NB * NB;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
-              PT[(long)col * NB + row] = -acc[a][b][0];
-              PT[(long)(col + 1) * NB + row] = -acc[a][b][1];
-            }
-        } else {
-          double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
-          // the mirror tile: Z(j,i) = Z(i,j)^T, or the upper-right quarter of the symmetric diagonal tile
-          const bool mirror = (MODE == TK_COL) || (MODE == TK_DIAG && m0 == NB / 2 && n0 == 0);
-          double* U = Am + ((long)j * NB) * g.ld + (long)i * NB;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
-              double2* p = reinterpret_cast<double2*>(C + (long)row * g.ld + col);
-              double2 v;
-              if (MODE == LL_UPDATE) {
-                v = *p;
-                v.x -= acc[a][b][0];
-                v.y -= acc[a][b][1];
-              } else {
-                v.x = acc[a][b][0];
-                v.y = acc[a][b][1];
-              }
-              *p = v;
-              if (mirror) {
-                U[(long)col * g.ld + row] = v.x;
-                U[(long)(col + 1) * g.ld + row] = v.y;
-              }
-            }
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-    };
-
-    int tt = 0, qq = 0;
-    for (int q = 0; q < total; ++q) {
-      const int slot = (gq + q) % STAGES;
-      __syncthreads();                 // every warp is done with the previous chunk: its slot may be refilled
-      if (threadIdx.x == 0 && q + STAGES - 1 < total) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue((gq + q + STAGES - 1) % STAGES);
-      }
-      const int i = tile_row(tt);
-      const int rows_valid = (i == last) ? vlast : NB;
-      // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
-      // of A(k,k); Z(j,j) is symmetric and mirrored in the epilogue)
-      const bool tri_skip = upper_quarter && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
-      const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
-      mbar_wait(&full[slot], ((gq + q) / STAGES) & 1);
-      if (active && !zero_chunk(qq)) {
-        const unsigned char* SA = ring + slot * 2 * OPB;
-        mma_chunk(SA + (m0 + lr) * 128, SA + OPB + (n0 + lr) * 128, off, acc);
-      }
-      if (++qq < nchunks) continue;
-      epilogue(i, active);
-      qq = 0;
-      ++tt;
-    }
-    gq += total;
-    __syncthreads();   // all warps have consumed the last chunk before the next matrix's prologue refills the ring
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);   // this warp's reads of the slot are complete
+    if (++qq < nchunks) continue;
+    epilogue(mat, i, active);
+    qq = 0;
+    if (++tt < nmy) item(tt, mat, i);
   }
 }
 
@@ -545,52 +605,69 @@ int make_map(CUtensorMap* m, const double* base, long cols, long rows, long coun
 }
 
 struct MapSet {
-  const double *A, *A2, *D, *P;
-  int nP, Kt, batch;
   CUtensorMap mA, mA2, mD, mP;
 };
 
-// tensor maps are pure functions of (pointers, layout): a tiny cache keyed by them (a plan reuses the same workspace)
-int get_maps(const BlockBatch& b, const MapSet** out) {
-  static std::mutex mu;
-  static std::vector<MapSet*> cache;
-  std::lock_guard<std::mutex> lock(mu);
-  for (MapSet* ms : cache)
-    if (ms->A == b.A && ms->A2 == b.A2 && ms->D == b.Dinv && ms->P == b.Pbuf && ms->nP == b.nP && ms->Kt == b.Kt &&
-        ms->batch >= b.batch) {
-      *out = ms;
-      return 0;
-    }
-  MapSet* ms = new MapSet();
-  ms->A = b.A; ms->A2 = b.A2; ms->D = b.Dinv; ms->P = b.Pbuf; ms->nP = b.nP; ms->Kt = b.Kt; ms->batch = b.batch;
-  int rc = make_map(&ms->mA, b.A, b.nP, b.nP, b.batch, b.strideA());
-  if (rc == 0) rc = make_map(&ms->mA2, b.A2 ? b.A2 : b.A, b.nP, b.nP, b.batch, b.strideA());
-  if (rc == 0) rc = make_map(&ms->mD, b.Dinv, NB, NB, (long)b.batch * b.Kt * 2, (long)NB * NB);
-  if (rc == 0) rc = make_map(&ms->mP, b.Pbuf, NB, NB, (long)b.batch * b.Kt, (long)NB * NB);
-  if (rc != 0) { delete ms; return rc; }
-  if (cache.size() >= 64) { delete cache.front(); cache.erase(cache.begin()); }
-  cache.push_back(ms);
-  *out = ms;
+// Tensor maps are pure functions of (pointers, layout).  A plan builds them once for its workspace (engine_maps_create,
+// owned by the plan and released with it); a BlockBatch without them (unit entry points) gets a set built per call.  The
+// kernels take the maps BY VALUE (__grid_constant__), so a set may be released as soon as the launches are queued.
+int build_maps(const BlockBatch& b, MapSet* ms) {
+  NMGP_TRY(make_map(&ms->mA, b.A, b.nP, b.nP, b.batch, b.strideA()));
+  NMGP_TRY(make_map(&ms->mA2, b.A2 ? b.A2 : b.A, b.nP, b.nP, b.batch, b.strideA()));
+  NMGP_TRY(make_map(&ms->mD, b.Dinv, NB, NB, (long)b.batch * b.Kt * 2, (long)NB * NB));
+  NMGP_TRY(make_map(&ms->mP, b.Pbuf, NB, NB, (long)b.batch * b.Kt, (long)NB * NB));
   return 0;
 }
 
-// tiles of one matrix are split over gx CTAs; enough CTAs for ~8 waves of the 148 x 3 resident slots
+struct MapRef {
+  MapSet local;
+  const MapSet* ms = nullptr;
+  int init(const BlockBatch& b) {
+    if (b.maps) { ms = static_cast<const MapSet*>(b.maps); return 0; }
+    NMGP_TRY(build_maps(b, &local));
+    ms = &local;
+    return 0;
+  }
+};
+
+// co-resident CTAs of a kernel on the current device (SMs x occupancy), cached per device and call site
+template <typename K>
+int resident_ctas(K kernel, int threads, size_t smem, std::atomic<int>* cache) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const bool slot = dev >= 0 && dev < kMaxDevices;
+  if (slot) { const int c = cache[dev].load(std::memory_order_relaxed); if (c > 0) return c; }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int v = per_sm * sm_count();
+  if (slot) cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
+// one persistent CTA per resident slot, work items dealt round-robin (see panel_gemm_kernel)
 template <int MODE>
 int launch_ll(const MapSet& ms, const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
   if (ntiles <= 0 || g0.batch <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(panel_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
-    configured = true;
-  }
+  NMGP_SMEM_ATTR_PER_DEVICE(panel_gemm_kernel<MODE>, LL_SMEM);
+  static std::atomic<int> slots[kMaxDevices];
   LLArgs g = g0;
   g.ntiles = ntiles;
+#if NMGP_LL_FLAT
+  const long nitems = (long)g.batch * ntiles;
+  long grid = resident_ctas(panel_gemm_kernel<MODE>, PG_THREADS, LL_SMEM, slots);
+  if (grid > nitems) grid = nitems;
+  panel_gemm_kernel<MODE><<<(unsigned)grid, PG_THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
+#else
+  // tiles of one matrix are split over gx CTAs; enough CTAs for ~`waves` waves of the resident slots (hardware-dynamic
+  // assignment of CTAs to SMs: a slow CTA delays nothing but its own successor)
+  static const int waves = getenv("NMGP_LL_WAVES") ? atoi(getenv("NMGP_LL_WAVES")) : 32;   // A/B timing: 8 -> 32: -1.5 % time
   const int gy = g.batch < 65535 ? g.batch : 65535;
-  int gx = (148 * 3 * 8 + gy - 1) / gy;
+  int gx = (int)(((long)resident_ctas(panel_gemm_kernel<MODE>, PG_THREADS, LL_SMEM, slots) * waves + gy - 1) / gy);
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, gy);
-  panel_gemm_kernel<MODE><<<grid, THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
+  panel_gemm_kernel<MODE><<<grid, PG_THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
+#endif
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -611,8 +688,9 @@ LLArgs make_ll(const BlockBatch& b) {
 int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
   if (!b.Pbuf) { set_last_error("engine_potrf_ll: no panel buffer"); return -1; }
-  const MapSet* ms = nullptr;
-  NMGP_TRY(get_maps(b, &ms));
+  MapRef mr;
+  NMGP_TRY(mr.init(b));
+  const MapSet* ms = mr.ms;
   LLArgs g = make_ll(b);
   for (int k = 0; k < b.Kt; ++k) {
     g.step = k;
@@ -638,17 +716,13 @@ int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launch
     ntiles = MODE == PANEL_ALL ? Kt * (Kt - 1) / 2 : (MODE == TRTRI_ROW ? Kt - 1 : Kt * (Kt + 1) / 2);
   }
   if (ntiles <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(inverse_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
-    configured = true;
-  }
+  NMGP_SMEM_ATTR_PER_DEVICE(inverse_kernel<MODE>, LL_SMEM);
   g.ntiles = ntiles;
   const int gy = g.batch < 65535 ? g.batch : 65535;
   int gx;
   if (MODE == TRTRI_ROW) gx = Kt - 1;          // one CTA per row (its tiles depend on each other)
   else {
-    gx = (148 * 4 * 8 + gy - 1) / gy;          // ~8 waves of the 148 x 4 resident slots
+    gx = (sm_count() * 4 * 8 + gy - 1) / gy;   // ~8 waves of the resident slots (4 CTAs per SM)
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
   }
@@ -664,8 +738,9 @@ int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launch
 int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
   if (!b.A2) { set_last_error("engine_potri_ll_stable: no second matrix buffer"); return -1; }
-  const MapSet* ms = nullptr;
-  NMGP_TRY(get_maps(b, &ms));
+  MapRef mr;
+  NMGP_TRY(mr.init(b));
+  const MapSet* ms = mr.ms;
   LLArgs g = make_ll(b);
   NMGP_TRY(launch_inv<PANEL_ALL>(*ms, g, st, launches));
   NMGP_TRY(launch_inv<TRTRI_ROW>(*ms, g, st, launches));
@@ -680,8 +755,9 @@ int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches)
 int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
   if (!b.A2 || !b.Pbuf) { set_last_error("engine_potri_ll_recursive: no second matrix buffer"); return -1; }
-  const MapSet* ms = nullptr;
-  NMGP_TRY(get_maps(b, &ms));
+  MapRef mr;
+  NMGP_TRY(mr.init(b));
+  const MapSet* ms = mr.ms;
   LLArgs g = make_ll(b);
   for (int hs = 1; hs < b.Kt; hs *= 2) {
     NMGP_TRY(launch_inv<REC_T>(*ms, g, st, launches, hs));
@@ -691,11 +767,25 @@ int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launch
   return 0;
 }
 
+int engine_maps_create(const BlockBatch& b, void** out) {
+  *out = nullptr;
+  if (!b.A || !b.Dinv || !b.Pbuf || b.batch <= 0) return 0;   // nothing the left-looking engine could run on
+  MapSet* ms = new (std::nothrow) MapSet();
+  if (!ms) { set_last_error("engine_maps_create: out of host memory"); return -1; }
+  const int rc = build_maps(b, ms);
+  if (rc != 0) { delete ms; return rc; }
+  *out = ms;
+  return 0;
+}
+
+void engine_maps_destroy(void* maps) { delete static_cast<MapSet*>(maps); }
+
 int engine_potri_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
   if (!b.Pbuf) { set_last_error("engine_potri_ll: no panel buffer"); return -1; }
-  const MapSet* ms = nullptr;
-  NMGP_TRY(get_maps(b, &ms));
+  MapRef mr;
+  NMGP_TRY(mr.init(b));
+  const MapSet* ms = mr.ms;
   LLArgs g = make_ll(b);
   for (int j = b.Kt - 1; j >= 0; --j) {
     g.step = j;

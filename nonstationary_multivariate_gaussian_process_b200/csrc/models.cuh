@@ -46,6 +46,17 @@ struct Scratch {
   double* G1;     // [cs][N][nv1]
 };
 
+// ---- stand-alone helpers of kronecker_operation.py / kernels.py / distributions.py (kron.cu; cold paths)
+int launch_pairwise_sqdist(const double* x1, int N1, const double* x2, int N2, double* out, cudaStream_t st);
+int launch_kron(const double* t1, int h1, int w1, const double* t2, int h2, int w2, double* out, cudaStream_t st);
+int launch_kron_mv(const double* B, int M1, int M2, const double* K, int N1, int N2, const double* y, double* out,
+                   double* scratch, cudaStream_t st);
+int launch_gram(const double* L, int R, int M, double* out, cudaStream_t st);
+int launch_sym_eig(const double* B, int M, double* lam, double* V, cudaStream_t st);
+// sigma2 I + B (x) K through eig(B) + M Cholesky factorisations: out2 = {log det, r^T inverse r}, inv_out the dense inverse
+int kron_eig_solve(const double* B, int M, const double* K, int N, double sigma2, double* inv_out, const double* r,
+                   double* out2, int* info_out, cudaStream_t st);
+
 int padded_M(int M);  // template bucket for the nonseparable contraction (>= M)
 
 // ---- elementwise covariance kernels (unit entry points + plan creation)

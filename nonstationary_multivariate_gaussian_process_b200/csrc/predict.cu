@@ -393,11 +393,7 @@ int launch_predict_prior(const double* x, const double* Lp, const double* Z, int
   while (wpb > 1 && (size_t)wpb * N * sizeof(double) > 200u * 1024u) wpb >>= 1;
   const size_t smem = (size_t)wpb * N * sizeof(double);
   if (smem > 227u * 1024u) { set_last_error("predict: N too large for the prior-conditional kernel"); return -1; }
-  static size_t configured = 0;
-  if (smem > 48u * 1024u && smem > configured) {
-    NMGP_CUDA_TRY(cudaFuncSetAttribute(pred_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48u * 1024u) NMGP_SMEM_ATTR_PER_DEVICE(pred_prior_kernel, smem);
   dim3 grid((G + wpb - 1) / wpb, cs);
   pred_prior_kernel<<<grid, 32 * wpb, smem, st>>>(x, Lp, Z, N, nv, xstar, G, alpha * alpha, beta, mu, mean_out, s2_out);
   NMGP_LAUNCH_CHECK();

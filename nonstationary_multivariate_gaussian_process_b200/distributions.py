@@ -1,7 +1,7 @@
 """Densities with the reference's signatures (Utility/distributions.py).
 
 Inside the objectives of `logpos` these are fused into the CUDA path; the stand-alone versions below serve callers
-that use them directly.  The Kronecker density is evaluated on the GPU (library eigensolvers, cold path).
+that use them directly.  The Kronecker densities run on this library's kernels (`nmgp_kron_eig_solve`, csrc/kron.cu).
 """
 from __future__ import annotations
 
@@ -20,34 +20,29 @@ def multivariate_normal_logpdf(y, mu, logdetSigma, invSigma):
 
 
 def multivariate_normal_logpdf0(y, mu, B, K, sigma2):
-    """Un-normalised log N(y; mu, B (x) K + sigma2 I), y output-major (distributions.py:26-52)."""
+    """Un-normalised log N(y; mu, B (x) K + sigma2 I), y output-major (distributions.py:26-52): eig(B) + M Cholesky
+    factorisations on the batched engine (`nmgp_kron_eig_solve`) instead of the reference's two symeig calls."""
     torch = _lib.require_cuda()
     dev = torch.as_tensor(y).device
-    Bg, Kg, yg, mg = kronecker_operation._gpu(B, K, y, mu)
-    wB, vB = torch.linalg.eigh(Bg)
-    wK, vK = torch.linalg.eigh(Kg)
-    a = kronecker_operation.kron_mv(vB.t(), vK.t(), yg - mg)
-    t = (wB.view(-1, 1) * wK.view(1, -1)).reshape(-1)
-    s2 = torch.as_tensor(sigma2, dtype=t.dtype).to(t.device)
-    return (-0.5 * torch.log(t + s2).sum() - 0.5 * torch.dot(a / (s2 + t), a)).to(dev)
+    r = torch.as_tensor(y, dtype=torch.float64) - torch.as_tensor(mu, dtype=torch.float64)
+    logdet, quad, _ = kronecker_operation._eig_solve(sigma2, B, K, r=r)
+    return (-0.5 * logdet - 0.5 * quad).to(dev)
 
 
-# The reference's "robust" variant perturbs the diagonals with unseeded random jitter to dodge NaNs of its
-# eigen-gradient (distributions.py:55-96); the value path here has no such failure mode.
+# The reference's "robust" variant perturbs the diagonals of B and K with UNSEEDED uniform jitter of size 1e-6 to dodge
+# NaNs of its eigen-gradient (distributions.py:55-96); the Cholesky path has no such failure mode, so the variant is the
+# plain density (it differs from the reference's draw-dependent value by O(1e-6) relative, like two reference calls do).
 multivariate_normal_logpdf1 = multivariate_normal_logpdf0
 
 
 def multivariate_normal_logpdf2(y, mu, B, K, sigma2):
-    """Dense check of the same density (distributions.py:99-113)."""
+    """The reference's dense cross-check of the same density (distributions.py:99-113: kronecker_product + logdet +
+    inverse).  Here: the explicit inverse and log-determinant from `kron_inv` / `kron_logdet`, then the dense formula."""
     torch = _lib.require_cuda()
     dev = torch.as_tensor(y).device
-    Bg, Kg, yg, mg = kronecker_operation._gpu(B, K, y, mu)
-    n = Bg.shape[0] * Kg.shape[0]
-    s2 = torch.as_tensor(sigma2, dtype=Bg.dtype).to(Bg.device)
-    Sigma = torch.kron(Bg, Kg) + s2 * torch.eye(n, dtype=Bg.dtype, device=Bg.device)
-    Lc = torch.linalg.cholesky(Sigma)
-    z = torch.linalg.solve_triangular(Lc, (yg - mg).unsqueeze(-1), upper=False).squeeze(-1)
-    return (-torch.log(torch.diagonal(Lc)).sum() - 0.5 * torch.dot(z, z)).to(dev)
+    logdet, _, inv = kronecker_operation._eig_solve(sigma2, B, K, want_inverse=True)
+    yg, mg = kronecker_operation._gpu(y, mu)
+    return multivariate_normal_logpdf(yg, mg, logdet, inv).to(dev)
 
 
 def inverse_gamma_logpdf_u(x, alpha=1., beta=1.):

@@ -29,13 +29,19 @@ def _ptr(t):
 
 
 def pairwise_distances(x, y=None):
-    """|x_i|^2 + |y_j|^2 - 2 x_i.y_j for N x 1 inputs (kernels.py:5-21); evaluated on the GPU with torch ops."""
+    """|x_i|^2 + |y_j|^2 - 2 x_i.y_j for N x 1 inputs (kernels.py:5-21), by `nmgp_pairwise_sqdist`."""
     torch = _lib.require_cuda()
+    lib = _lib.load_library()
     dev_in = torch.as_tensor(x).device
     xs = _prep(x, "pairwise_distances")
-    ys = xs if y is None else _prep(y, "pairwise_distances")
-    d = (xs * xs).view(-1, 1) + (ys * ys).view(1, -1) - 2.0 * (xs.view(-1, 1) * ys.view(1, -1))
-    return d.to(dev_in)
+    ys = None if y is None else _prep(y, "pairwise_distances")
+    n1, n2 = xs.numel(), (xs.numel() if ys is None else ys.numel())
+    out = torch.empty((n1, n2), dtype=torch.float64, device=xs.device)
+    if n1 and n2:
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.nmgp_pairwise_sqdist(xs.data_ptr(), n1, _ptr(ys), n2, out.data_ptr(), ctypes.c_void_p(stream)),
+                   "nmgp_pairwise_sqdist")
+    return out.to(dev_in)
 
 
 def RBF_cov(X1, X2=None, alpha=1., beta=1.):

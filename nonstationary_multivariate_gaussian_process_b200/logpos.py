@@ -20,6 +20,7 @@ There is no CPU fallback: without a CUDA device or without the built library the
 from __future__ import annotations
 
 import collections
+import warnings
 
 import numpy as np
 
@@ -50,17 +51,50 @@ def vec2pars_S(pars, M):
 
 
 def generate_K_index_SVC(L_f_list):
-    """Stack the per-time-point factors and form L L^T, time-major (logpos.py:111-118); evaluated on the GPU."""
+    """Stack the per-time-point factors and form L L^T, time-major (logpos.py:111-118), by `nmgp_gram`."""
+    import ctypes
     torch = _lib.require_cuda()
     dev = L_f_list[0].device
-    L = torch.cat([l.cuda() for l in L_f_list], dim=0)
-    return (L @ L.t()).to(dev)
+    L = torch.cat([torch.as_tensor(l, dtype=torch.float64).detach().cuda() for l in L_f_list], dim=0).contiguous()
+    out = torch.empty((L.shape[0], L.shape[0]), dtype=torch.float64, device=L.device)
+    _lib.check(_lib.load_library().nmgp_gram(L.data_ptr(), L.shape[0], L.shape[1], out.data_ptr(),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "nmgp_gram")
+    return out.to(dev)
 
 
 # ------------------------------------------------------------------------------------- plan cache
+# A MAP / HMC loop calls the objective thousands of times with the SAME Y and x tensors.  Hashing their contents needs them
+# on the host (a D2H copy + synchronisation for CUDA tensors), so the content hash is remembered per
+# (storage address, version counter, shape, dtype, device): in-place edits bump the version and re-hash.  CPU tensors are
+# additionally spot-checked (up to 32 strided elements) on every call, which catches a buffer rewritten behind torch's back
+# (e.g. through a numpy view); CUDA tensors are trusted between version bumps -- pass `plan=` to
+# `nlogpos_obj*_batched` for explicit control.
+_FP_CACHE: "collections.OrderedDict[tuple, tuple]" = collections.OrderedDict()
+_FP_CACHE_SIZE = 64
+
+
+def _spot(t):
+    flat = t.detach().reshape(-1)
+    n = flat.numel()
+    if n == 0:
+        return ()
+    step = max(1, n // 32)
+    return tuple(flat[::step][:32].tolist())
+
+
 def _fingerprint(t):
+    key = (t.data_ptr(), t._version, tuple(t.shape), t.dtype, str(t.device))
+    hit = _FP_CACHE.get(key)
+    spot = _spot(t) if not t.is_cuda else None
+    if hit is not None and hit[1] == spot:
+        _FP_CACHE.move_to_end(key)
+        return hit[0]
     a = t.detach().cpu().contiguous().numpy()
-    return (a.shape, hash(a.tobytes()))
+    fp = (a.shape, hash(a.tobytes()))
+    _FP_CACHE[key] = (fp, spot)
+    while len(_FP_CACHE) > _FP_CACHE_SIZE:
+        _FP_CACHE.popitem(last=False)
+    return fp
 
 
 def _get_plan(model, Y, x, hyper, prior, indx=None):
@@ -85,6 +119,11 @@ def clear_plan_cache():
     while _PLAN_CACHE:
         _, p = _PLAN_CACHE.popitem()
         p.close()
+    _FP_CACHE.clear()
+
+
+class NmgpNotPositiveDefinite(RuntimeWarning):
+    """The covariance of a subject was not positive definite at the given parameters (Cholesky pivot `info` failed)."""
 
 
 # ------------------------------------------------------------------------------------- autograd bridge
@@ -132,8 +171,16 @@ def _evaluate(plan, pars):
 
 
 def _single(model, pars, Y, x, hyper, verbose, Prior, indx=None):
+    """Failure contract: if the covariance is not positive definite at `pars` the value and its
+    gradient are NaN -- the in-band signal the reference's own callers test for (logpos.py:267) and wrap in try/except
+    (Nonseparable_model_mpisim.py:330-334) -- and a NmgpNotPositiveDefinite warning names the failing pivot.  (The
+    reference's LU-based inverse / logdet return NaN or garbage without any signal in that case.)  With CUDA `pars` the
+    call stays asynchronous and only the NaN is reported."""
     plan = _get_plan(model, Y, x, hyper, Prior, indx)
-    vals, _ = _evaluate(plan, pars)
+    vals, info = _evaluate(plan, pars)
+    if not info.is_cuda and int(info[0]) != 0:
+        warnings.warn(f"{model} objective: covariance not positive definite (Cholesky pivot {int(info[0])}); "
+                      "value and gradient are NaN", NmgpNotPositiveDefinite, stacklevel=3)
     if not verbose:
         return vals[0, 0]
     n = batched.N_VERBOSE[model]
@@ -194,6 +241,32 @@ def logpos_SVC(tilde_l, uL_vecs, tilde_sigma2_err, Y, x, mu_tilde_l, alpha_tilde
     pars = torch.cat([tilde_l.reshape(-1), uL_vecs.reshape(-1), tilde_sigma2_err.reshape(1)])
     return _positive(nlogpos_obj_SVC(pars, Y, x, mu_tilde_l, alpha_tilde_l, beta_tilde_l, mu_L, alpha_L, beta_L, a, b,
                                      verbose, Prior), verbose)
+
+
+# ------------------------------------------------------------------------------------- deviance (logpos.py:189-213)
+def deviance(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, Y, x):
+    """-2 x the (un-normalised) separable log-likelihood, `L_vec` being the CONSTRAINED row-major triangle (no exp on
+    its diagonal, unlike `logpos`: logpos.py:189-213 forms L L^T from it directly).  The reference goes through
+    kron_inv + kron_logdet (two symeig); here it is the separable plan evaluated with Prior=False -- B = L L^T does
+    not depend on the signs of L's diagonal, so log|diag| is the equivalent unconstrained vector."""
+    torch = _lib.require_cuda()
+    Y = torch.as_tensor(Y, dtype=torch.float64)
+    M = Y.shape[1]
+    Lv = torch.as_tensor(L_vec, dtype=torch.float64).reshape(-1)
+    diag = torch.zeros(Lv.shape[0], dtype=torch.bool, device=Lv.device)
+    diag[torch.cumsum(torch.arange(1, M + 1), 0) - 1] = True
+    uL = torch.where(diag, torch.log(torch.abs(torch.where(diag, Lv, torch.ones_like(Lv)))), Lv)
+    pars = torch.cat([torch.as_tensor(tilde_l, dtype=torch.float64).reshape(-1),
+                      torch.as_tensor(tilde_sigma, dtype=torch.float64).reshape(-1), uL,
+                      torch.as_tensor(tilde_sigma2_err, dtype=torch.float64).reshape(1)])
+    return 2.0 * nlogpos_obj(pars, Y, x, verbose=False, Prior=False)
+
+
+def deviance_obj(pars, Y, x):
+    """(logpos.py:189-199)"""
+    N, M = Y.shape
+    tilde_l, tilde_sigma, L_vec, tilde_sigma2_err = vec2pars(pars, N, M)
+    return deviance(tilde_l, tilde_sigma, L_vec, tilde_sigma2_err, Y, x)
 
 
 # ------------------------------------------------------------------------------------- irregular sampling ("Hadamard")

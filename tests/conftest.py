@@ -17,10 +17,41 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+def manifest():
+    with open(os.path.join(GOLDEN_DIR, "MANIFEST.json")) as f:
+        return json.load(f)
+
+
+def big_cases():
+    """full-size fixtures (C3 n = 5000, C5 shape at n = 4096 / 8192 / 16 384; tests/golden/make_golden_big.py)"""
+    return [c for c in manifest().get("big_cases", []) if os.path.exists(os.path.join(GOLDEN_DIR, c + ".npz"))]
+
+
 def golden_cases():
-    """log-posterior + gradient fixtures (tests/golden/make_golden.py)"""
+    """log-posterior + gradient fixtures (tests/golden/make_golden.py); the full-size ones are listed by big_cases()"""
+    big = set(manifest().get("big_cases", []))
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("predict", "hadamard", "empirical", "hyper", "map_")))
+                  if not os.path.basename(p).startswith(("predict", "hadamard", "empirical", "hyper", "map_", "units"))
+                  and os.path.basename(p)[:-4] not in big)
+
+
+def tolerances(name):
+    """Per-fixture bounds on the prior-bearing quantities: 3 x the largest error measured over all engines on B200
+    (tools/report_parity.py -> tools/update_tolerances.py), never below north_star's 1e-9.  A fixture without an entry is
+    held to 1e-9 throughout."""
+    t = manifest().get("tolerances", {}).get(name, {})
+    return {k: max(float(t.get(k, 0.0)), 1e-9) for k in ("total", "prior", "grad")}
+
+
+def prior_blocks(g):
+    """[(slice of pars under GP prior k, name)] for k = 0, 1 (logpos.py:271-281 separable, :357-365 nonseparable)"""
+    N, M = g["N"], g["M"]
+    T = M * (M + 1) // 2
+    if g["model"] == "nonseparable":
+        return [(slice(0, N), "tilde_l"), (slice(N, N + N * T), "uL_vecs")]
+    if g["model"] == "separable":
+        return [(slice(0, N), "tilde_l"), (slice(N, 2 * N), "tilde_sigma")]
+    return []
 
 
 def hadamard_cases():

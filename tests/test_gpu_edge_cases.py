@@ -79,3 +79,35 @@ def test_single_new_input_and_sample(cuda_device):
         assert int(info[0]) == 0
         assert rel_err(mu_f[0, 0, 0].cpu().numpy(), pct[0, 1]) < 1e-8, (N, M)
         assert rel_err(np.sqrt(s2_y[0, 0, 0].cpu().numpy()), (pct[0, 2] - pct[0, 1]) / 1.96) < 1e-7, (N, M)
+
+
+@pytest.mark.parametrize("log_s2", [-4.0, -8.0, -11.5])
+def test_takahashi_sweep_on_ill_conditioned_covariances_at_its_size_limit(log_s2, cuda_device):
+    """The Takahashi inverse sweep ('left': what the 10 000-subject sweep uses for <= 16 block columns) is not backward
+    stable in general: the error of the trailing inverse block is carried into every new block column.  At its size limit
+    (n = 1024 = 16 blocks) and with the noise variance lowered to exp(-11.5) ~ 1e-5 (cond(Sigma) grows by ~2000 against the
+    drivers' exp(-4)) its gradient must still agree with the backward-stable W^T W inverse ('left_stable') far inside the
+    1e-9 contract -- otherwise the algorithm choice by batch size (api.cu:run_potri) would make a subject's gradient depend
+    on how many subjects share its chunk or rank."""
+    from nonstationary_multivariate_gaussian_process_b200 import synth
+    from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+    N, M, S = 128, 8, 4
+    subs = []
+    for s in range(S):
+        x, Y, _ = synth.sample_subject(N, M, 40 + s)
+        p = synth.start_point("nonseparable", N, M, 40 + s, 0.02)
+        p[-1] = log_s2
+        subs.append((x, Y, p))
+    xs, Ys, ps = (np.stack(a) for a in zip(*subs))
+    out = {}
+    for engine in ("left", "left_stable"):
+        plan = LogPosteriorPlan("nonseparable", xs, Ys, HYPER["nonseparable"], prior=False)
+        plan.set_engine(engine)
+        vals, grad, info = plan.value_and_grad_host(torch.from_numpy(ps))
+        plan.close()
+        assert int(info.abs().sum()) == 0
+        out[engine] = (vals.numpy(), grad.numpy())
+    for s in range(S):
+        ev = rel_err(out["left"][0][s, 0], out["left_stable"][0][s, 0])
+        eg = rel_err(out["left"][1][s], out["left_stable"][1][s])
+        assert ev < 1e-12 and eg < 1e-10, (log_s2, s, ev, eg)

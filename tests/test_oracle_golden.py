@@ -125,3 +125,33 @@ def test_hadamard_oracle_matches_reference_golden(name):
     for k in range(len(g["vals"])):
         assert rel_err(vals[k], g["vals"][k]) < VAL_TOL, (name, k, vals[k], g["vals"][k])
     assert rel_err(grad.numpy(), g["grad"]) < GRAD_TOL, name
+
+
+# ---- function-level pins: the oracle's covariance builders against matrices produced by the reference's own
+# kernels.py / logpos.py:339-352 (tests/golden/make_golden_units.py)
+import glob as _glob
+import torch
+import os as _os
+
+_UNITS = sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "units_*.npz")))
+
+
+@pytest.mark.parametrize("path", _UNITS, ids=[_os.path.basename(p)[:-4] for p in _UNITS])
+def test_oracle_covariances_match_reference_matrices(path):
+    u = np.load(path)
+    N, M = int(u["N1"]), int(u["M"])
+    T = M * (M + 1) // 2
+    x = torch.from_numpy(u["x1"])
+    rel = lambda a, b: float(np.abs(np.asarray(a) - b).max() / np.abs(b).max())
+    assert rel(O.sq_dist(x), u["pd_self"]) < 1e-15
+    assert rel(O.rbf_cov(x, float(u["alpha"]), float(u["beta"])), u["rbf_self"]) < 1e-15
+    assert rel(O.gibbs_cov(x, torch.from_numpy(u["ell1"]), torch.from_numpy(u["sig1"])), u["gibbs_self"]) < 1e-15
+    p = torch.from_numpy(u["pars_svc"])
+    cov = O.nonseparable_cov(x, p[:N], p[N:N + N * T], M) + torch.exp(p[-1]) * torch.eye(N * M, dtype=torch.float64)
+    assert rel(cov, u["svc_cov"]) < 1e-14
+    # the reference's own identities, at the level the reference attains them
+    assert float(u["identity_kron_mv"]) < 1e-12
+    assert float(u["identity_logpdf0_vs_dense"]) < 1e-10 and float(u["identity_logpdf0_vs_logpdf2"]) < 1e-10
+    y, mu = torch.from_numpy(u["y"]), torch.from_numpy(u["mu"])
+    v = O.kron_eig_loglik(y - mu, torch.from_numpy(u["B"]), torch.from_numpy(u["gibbs_self"]), torch.tensor(float(u["sigma2"]), dtype=torch.float64))
+    assert abs(float(v) - float(u["logpdf0"])) / abs(float(u["logpdf0"])) < 1e-12
