@@ -1,13 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the NMGP batched log-posterior + gradient hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
+    python bench.py --gpus N --steps K --warmup W [--workload C4]     # our CUDA path (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...            # the reference's CPU algorithm on the host cores
 
-Workload (BASELINE.json configs[3], the configuration the metric is quoted on): the nonseparable model batched over
-10 000 synthetic subjects of M=6 outputs x N=100 time points (n = NM = 600 per subject), subject-sharded over the
-ranks ("strong" scaling: the 10 000 subjects are split over the GPUs).  One step = one evaluation of
--log posterior, its components and its gradient for every subject.  Prints ONE JSON line (rank 0).
+Workloads = BASELINE.json `configs` (default C4, the configuration the metric is quoted on):
+  C1  stationary   M=2  N=50   one subject: the full 1000-iteration Adam MAP fit of Stationary_model.py:106-131 (1000 evaluations/step)
+  C2  separable    M=5  N=200  one subject: 200 value+gradient evaluations per step
+  C3  nonseparable M=10 N=500  one subject (n = NM = 5000): 5 evaluations per step
+  C4  nonseparable M=6  N=100  10 000 subjects (n = 600), subject-sharded over the ranks: one sweep per step
+  C5  nonseparable M=8  N=2048 256 subjects (n = 16 384), subject-sharded over the ranks: one sweep per step
+One evaluation = -log posterior, its components and its gradient for one subject.  `value` = evaluations/s of the whole job
+with the inputs resident in HBM; `e2e` = the same through the reference-facing host-buffer call (nmgp_logpost_grad_host, or
+the drop-in `logpos.nlogpos_obj_S` MAP loop for C1) with host<->device copies inside the timed region.  Single-subject
+workloads at N > 1 run one replica per rank (the path does not shard below a subject).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -16,6 +22,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +40,18 @@ HYPER = {
     "nonseparable": {"mu_tilde_l": 0.0, "alpha_tilde_l": 10.0, "beta_tilde_l": 1.0, "mu_L": 0.0, "alpha_L": 1.0,
                      "beta_L": 1.0, "a": 1e-2, "b": 1e-2},
 }
-FP64_PEAK_TFLOPS = 37.15   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA.8x8x4), profiles/r01_fp64_peak.txt
+# fallback FP64 tensor peak when the live probe cannot run (tools/fp64_peak.cu on this pool's B200, profiles/r02_fp64_peak.txt)
+FP64_PEAK_FALLBACK_TFLOPS = 37.15
+
+WORKLOADS = {
+    "C1": dict(model="stationary", N=50, M=2, subjects=1, kind="map", iters=1000, lr=0.1,
+               what="full 1000-iteration Adam MAP fit (Stationary_model.py:106-131), 1000 evaluations per step"),
+    "C2": dict(model="separable", N=200, M=5, subjects=1, kind="single", reps=200, what="200 evaluations of one subject per step"),
+    "C3": dict(model="nonseparable", N=500, M=10, subjects=1, kind="single", reps=5,
+               what="5 evaluations of one subject (dense n = 5000) per step"),
+    "C4": dict(model="nonseparable", N=100, M=6, subjects=10000, kind="batch", what="one sweep over all subjects per step"),
+    "C5": dict(model="nonseparable", N=2048, M=8, subjects=256, kind="batch", what="one sweep over all subjects per step"),
+}
 
 
 def parse_args():
@@ -42,14 +60,22 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="nonseparable", choices=list(HYPER))
-    ap.add_argument("--subjects", type=int, default=10000)
-    ap.add_argument("--N", type=int, default=100)
-    ap.add_argument("--M", type=int, default=6)
+    ap.add_argument("--workload", default="C4", choices=list(WORKLOADS))
+    ap.add_argument("--model", default=None, choices=list(HYPER))
+    ap.add_argument("--subjects", type=int, default=None)
+    ap.add_argument("--N", type=int, default=None)
+    ap.add_argument("--M", type=int, default=None)
     ap.add_argument("--cpu-subjects-per-core", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    for k in ("model", "subjects", "N", "M"):
+        if getattr(a, k) is not None:
+            w[k] = getattr(a, k)
+    a.w = w
+    a.model, a.subjects, a.N, a.M = w["model"], w["subjects"], w["N"], w["M"]
+    return a
 
 
 def algorithmic_flops(model, N, M):
@@ -61,60 +87,114 @@ def algorithmic_flops(model, N, M):
     return nmat * n ** 3 / 3.0, nmat * 2.0 * n ** 3 / 3.0
 
 
-# ------------------------------------------------------------------------------------------ reference arm
-def run_cpu_workers(model, N, M, per_core, cores, first=0):
-    """One single-threaded oracle process per host core (the reference's deployment mode); returns evals/s."""
-    procs = []
+def evals_per_step(a, world):
+    w = a.w
+    if w["kind"] == "batch":
+        return a.subjects
+    per = w["iters"] if w["kind"] == "map" else w["reps"]
+    return per * world            # one replica per rank
+
+
+def workload_config(a, world):
+    n = a.N * a.M if a.model == "nonseparable" else a.N
+    shard = (f"subject-sharded over {world} GPU(s)" if a.w["kind"] == "batch"
+             else f"one replica per GPU ({world}): the path does not shard below a subject")
+    big = a.w["kind"] == "batch" or n >= 2048
+    return {"workload": f"{a.workload}: {a.model} model, {a.subjects} synthetic subject(s) (SIM_code/sim.py recipe) x (M={a.M}, N={a.N}), "
+                        f"value+gradient per subject; {a.w['what']}; {shard}",
+            "name": a.workload, "subjects": a.subjects, "M": a.M, "N": a.N, "matrix_dim": n,
+            "evals_per_step": evals_per_step(a, world),
+            "cache": ("per-step working set (covariance workspace) far exceeds the 126 MB L2; no flush needed" if big else
+                      "launch-latency-bound single-subject workload (working set < L2 by design: the MAP / HMC loops of the "
+                      "drivers re-evaluate one subject); an L2 flush between evaluations would measure a different workload")}
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def run_cpu_workers(model, N, M, per_core, cores, first=0, data=None, threads=1, extra=()):
+    """Oracle processes on the host cores; returns (evals/s, slowest seconds, wall, n_eval, [out files]).
+    data = list of npz paths (one per worker: the bench's own inputs) or None (model draws by seed)."""
+    procs, outs = [], []
     t0 = time.perf_counter()
     for c in range(cores):
         cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_bench.py"), "--model", model, "--N", str(N), "--M",
-               str(M), "--first", str(first + c * per_core), "--count", str(per_core), "--threads", "1"]
-        env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+               str(M), "--first", str(first + c * per_core), "--count", str(per_core), "--threads", str(threads)] + list(extra)
+        if data is not None:
+            out = data[c][:-4] + "_out.npz"
+            cmd += ["--data", data[c], "--out", out]
+            outs.append(out)
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
-    secs = []
+    secs, counts = [], []
     for p in procs:
         out, err = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("cpu worker failed: " + err[-2000:])
-        secs.append(json.loads(out.strip().splitlines()[-1])["seconds"])
+        j = json.loads(out.strip().splitlines()[-1])
+        secs.append(j["seconds"])
+        counts.append(j["count"])
     wall = time.perf_counter() - t0
-    n_eval = per_core * cores
-    return n_eval / max(secs), max(secs), wall, n_eval
+    n_eval = sum(counts)
+    return n_eval / max(secs), max(secs), wall, n_eval, outs
+
+
+def cpu_leg(a, data_files=None):
+    """A bounded sample of the workload on the host cores with the oracle (the reference's algorithm).  Returns
+    (evals/s, cores used, description, out files)."""
+    cores = os.cpu_count() or 1
+    w = a.w
+    if a.workload == "C4" or (w["kind"] == "batch" and a.N * a.M <= 1200):
+        per = a.cpu_subjects_per_core if data_files is None else None
+        if data_files is not None:
+            v, sec, _, n_eval, outs = run_cpu_workers(a.model, a.N, a.M, 0, len(data_files), data=data_files)
+        else:
+            v, sec, _, n_eval, outs = run_cpu_workers(a.model, a.N, a.M, per, cores)
+        return v, (len(data_files) if data_files else cores), (
+            f"{n_eval} subjects of the same workload, one single-threaded process per core "
+            f"(oracle/nmgp_oracle.py: dense inverse + logdet + autograd, the reference's algorithm), {sec:.1f} s"), outs
+    if w["kind"] == "map":
+        v, sec, _, n_eval, outs = run_cpu_workers(a.model, a.N, a.M, 1, 1, threads=cores, data=data_files,
+                                                  extra=["--map-iters", str(w["iters"]), "--lr", str(w["lr"])])
+        return v, cores, f"the same {w['iters']}-iteration Adam MAP fit with the oracle as objective, one process, {cores} threads, {sec:.1f} s", outs
+    if a.workload == "C5" or a.N * a.M > 6000:
+        # one n = 16 384 evaluation of the reference takes ~200 s and ~30 GB: time the same model at n = 4096 and scale by n^3
+        Np = 4096 // a.M
+        v, sec, _, n_eval, outs = run_cpu_workers(a.model, Np, a.M, 1, 1, threads=cores)
+        scale = (a.N / Np) ** 3
+        return v / scale, cores, (f"n^3 extrapolation: one evaluation at N={Np} (n={Np * a.M}) took {sec:.1f} s with {cores} threads, "
+                                  f"x {scale:.0f} for n={a.N * a.M} (the unmodified reference needs 194 s per evaluation at this "
+                                  "size on 8 cores: tests/golden/make_golden_big.py)"), []
+    count = 2 if a.N * a.M >= 2048 else 20
+    if data_files is not None:
+        v, sec, _, n_eval, outs = run_cpu_workers(a.model, a.N, a.M, 0, 1, threads=cores, data=data_files,
+                                                  extra=["--repeat", str(count)])
+    else:
+        v, sec, _, n_eval, outs = run_cpu_workers(a.model, a.N, a.M, count, 1, threads=cores)
+    return v, cores, f"{n_eval} evaluation(s) of the same subject shape, one process, {cores} threads, {sec:.1f} s", outs
 
 
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per = a.cpu_subjects_per_core
-    for _ in range(min(a.warmup, 1)):
-        run_cpu_workers(a.model, a.N, a.M, 1, cores)
-    step_secs, n_eval = [], per * cores
+    if min(a.warmup, 1) and a.workload == "C4":
+        run_cpu_workers(a.model, a.N, a.M, 1, os.cpu_count() or 1)
+    rates, desc, cores = [], "", 1
+    t0 = time.perf_counter()
     for s in range(a.steps):
-        _, sec, _, _ = run_cpu_workers(a.model, a.N, a.M, per, cores, first=s * n_eval)
-        step_secs.append(sec)
-    total = sum(step_secs)
-    value = n_eval * a.steps / total
-    sample = (f"{n_eval} of the {a.subjects} subjects per step, {cores} single-threaded processes x {per} subjects "
-              f"(oracle/nmgp_oracle.py: dense inverse + logdet + autograd, the reference's algorithm)")
+        v, cores, desc, _ = cpu_leg(a)
+        rates.append(v)
+    total = time.perf_counter() - t0
+    value = len(rates) / sum(1.0 / r for r in rates)          # steps process equal samples: harmonic mean of the rates
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / max(a.steps, 1), "higher_is_better": True,
+        "scaling": "strong" if a.w["kind"] == "batch" else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(a, a.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "per step: " + desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def workload_config(a, world):
-    n = a.N * a.M if a.model == "nonseparable" else a.N
-    return {"workload": f"{a.model} model, {a.subjects} synthetic subjects (SIM_code/sim.py recipe) x (M={a.M}, N={a.N}), "
-                        f"value+gradient per subject, subject-sharded over {world} GPU(s)",
-            "subjects": a.subjects, "M": a.M, "N": a.N, "matrix_dim": n,
-            "cache": "per-step working set (covariance workspace) far exceeds the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------ inputs
@@ -190,7 +270,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
             f = [t.strip() for t in ln.split(",")]
@@ -199,6 +279,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
@@ -207,15 +288,36 @@ class ClockSampler:
         sm.sort()
         # median of the samples taken under load (upper half: the sampler also sees the idle edges)
         med = sm[(3 * len(sm)) // 4] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
+
+
+def fp64_peak_probe(device_index):
+    """Live DMMA.8x8x4 peak of this device (nmgp_fp64_dmma_probe, 0.4 s) with the SM clock it ran at."""
+    import ctypes
+
+    import torch
+
+    from nonstationary_multivariate_gaussian_process_b200 import _lib
+    lib = _lib.load_library()
+    sampler = ClockSampler(device_index)
+    tf, sec = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    rc = lib.nmgp_fp64_dmma_probe(0.4, ctypes.byref(tf), ctypes.byref(sec),
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    clk = sampler.stop()
+    if rc != 0 or not tf.value > 0:
+        return FP64_PEAK_FALLBACK_TFLOPS, "fallback: tools/fp64_peak.cu figure (profiles/r02_fp64_peak.txt); the live probe failed", clk
+    return tf.value, (f"live: nmgp_fp64_dmma_probe, register-only mma.sync.m8n8k4.f64 for {sec.value:.2f} s on this device in this "
+                      f"process (MEASURED_PEAKS.json has no FP64 entry; tools/fp64_peak.cu gives 37.15 on this pool)"), clk
 
 
 # ------------------------------------------------------------------------------------------ our arm
 def ours(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
-    from nonstationary_multivariate_gaussian_process_b200 import sharding
+    from nonstationary_multivariate_gaussian_process_b200 import logpos, sharding
     from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
 
     if not torch.cuda.is_available():
@@ -227,13 +329,19 @@ def ours(a):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    w = a.w
+    batch_kind = w["kind"] == "batch"
 
-    lo, hi = sharding.shard_range(a.subjects, rank, world)
+    if batch_kind:
+        lo, hi = sharding.shard_range(a.subjects, rank, world)
+    else:
+        lo, hi = 0, a.subjects                      # one replica per rank
     S = hi - lo
     x, Y, pars_h = make_inputs(a, lo, hi, device)
     plan = LogPosteriorPlan(a.model, x, Y, HYPER[a.model], prior=True, device=device)
     pars_d = pars_h.to(device)
     P = plan.P
+    n_eval_step = evals_per_step(a, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,15 +357,28 @@ def ours(a):
         return float(t.item())
 
     hyper_names = plan.hyper_names()
+    buf = (torch.empty((S, 6), dtype=torch.float64, device=device), torch.empty((S, P), dtype=torch.float64, device=device),
+           torch.empty((S,), dtype=torch.int32, device=device))
+    launches_step = [0]
 
     def step_device():
-        # one sweep: value + gradient of every local subject and, in the same pass, the gradient with respect to the
-        # hyper-parameters shared by all subjects; the only collective is one all-reduce of 17 doubles
-        vals, grad, hgrad, info = plan.value_grad_and_hyper_grad(pars_d)
-        vec = sharding.local_sweep_vector(vals, info, hgrad)
-        if world > 1:
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-        return vec
+        if batch_kind:
+            # one sweep: value + gradient of every local subject and, in the same pass, the gradient with respect to the
+            # hyper-parameters shared by all subjects; the only collective is one all-reduce of 17 doubles
+            vals, grad, hgrad, info = plan.value_grad_and_hyper_grad(pars_d)
+            vec = sharding.local_sweep_vector(vals, info, hgrad)
+            if world > 1:
+                dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+            launches_step[0] = plan.last_launches + 1
+            return vec
+        if w["kind"] == "map":
+            p, trace, info = plan.map_fit(pars_d, steps=w["iters"], lr=w["lr"], record_every=w["iters"])
+            launches_step[0] = (plan.last_launches + 1) * w["iters"]
+            return trace[-1, 0]
+        for _ in range(w["reps"]):
+            vals, grad, info = plan.value_and_grad(pars_d, out=buf)
+        launches_step[0] = plan.last_launches * w["reps"]
+        return vals[0]
 
     # ---- device-resident timing (value)
     for _ in range(a.warmup):
@@ -272,28 +393,54 @@ def ours(a):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
-    launches = plan.last_launches * a.steps
+    launches = launches_step[0] * a.steps
     sv = summary.tolist()
-    summary = dict(zip(sharding.SUMMARY_FIELDS, sv[:8]))
-    shared_hyper_grad = dict(zip(hyper_names, sv[8:8 + len(hyper_names)]))
 
-    # ---- end to end through the host-buffer C call (pinned host memory in, results out)
+    # ---- end to end through the reference-facing call (pinned host memory in, results out)
     e2e = None
+    vals_h = grad_h = None
     if not a.no_e2e:
-        pin = plan.pinned_pars()
-        pin.copy_(pars_h)
-        for _ in range(min(a.warmup, 3)):
-            plan.value_and_grad_host(pin, pinned_io=True)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            vals_h, grad_h, info_h = plan.value_and_grad_host(pin, pinned_io=True)
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        e2e = {"value": a.subjects * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * P * 8,
-               "d2h_bytes_per_step": S * (P * 8 + 6 * 8 + 4), "ms_per_step": 1e3 * dt / a.steps,
-               "path": "nmgp_logpost_grad_host (pinned host pars -> vals, grad, info on the host)"}
+        if w["kind"] == "map":
+            # the driver's own loop through the drop-in objective: CPU leaf tensor, nlogpos_obj_S, .backward(), torch Adam
+            Yc, xc = Y[0].cpu(), x[0]
+
+            def map_loop():
+                p = pars_h[0].clone().requires_grad_(True)
+                opt = torch.optim.Adam([p], lr=w["lr"])
+                for _ in range(w["iters"]):
+                    opt.zero_grad()
+                    neg = logpos.nlogpos_obj_S(p, Yc, xc, **HYPER[a.model])
+                    neg.backward()
+                    opt.step()
+                return p
+            map_loop()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                map_loop()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            e2e = {"value": n_eval_step * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": w["iters"] * P * 8,
+                   "d2h_bytes_per_step": w["iters"] * (P * 8 + 6 * 8 + 4), "ms_per_step": 1e3 * dt / a.steps,
+                   "path": "drop-in logpos.nlogpos_obj_S(pars, Y, x, **hyper) + .backward() + torch.optim.Adam on CPU leaf tensors: "
+                           "the loop of Stationary_model.py:106-131 (host pars in, value and gradient out, every iteration)"}
+        else:
+            pin = plan.pinned_pars()
+            pin.copy_(pars_h)
+            reps = 1 if batch_kind else w["reps"]
+            for _ in range(min(a.warmup, 3)):
+                plan.value_and_grad_host(pin, pinned_io=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps * reps):
+                vals_h, grad_h, info_h = plan.value_and_grad_host(pin, pinned_io=True)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            e2e = {"value": n_eval_step * a.steps / dt, "unit": UNIT, "h2d_bytes_per_step": reps * S * P * 8,
+                   "d2h_bytes_per_step": reps * S * (P * 8 + 6 * 8 + 4), "ms_per_step": 1e3 * dt / a.steps,
+                   "path": "nmgp_logpost_grad_host (pinned host pars -> vals, grad, info on the host)"}
 
     # ---- live per-phase timing for the roofline (CUDA events inside the C call, separate from `value`)
     phases = None
@@ -302,41 +449,86 @@ def ours(a):
     f_potrf, f_potri = algorithmic_flops(a.model, a.N, a.M)
     t_fact = (phases["potrf"] + phases["potri"]) * 1e-3
     achieved = S * (f_potrf + f_potri) / t_fact / 1e12 if t_fact > 0 else 0.0
-    # DRAM traffic of the same kernels from the committed ncu pass (profiles/r01_launches_final.txt): 353 GB per sweep of
-    # 10 000 subjects over 168 engine launches (3 chunks x 56) -> bytes per launch, scaled to this rank's subjects
-    traffic = 353e9 / 168.0 * (S / 10000.0) if (a.model == "nonseparable" and a.N == 100 and a.M == 6) else None
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
-                "traffic_note": "average dram__bytes_read+write per launch over the 168 panel_gemm/diag64 launches of one "
-                                "sweep (ncu, profiles/r01_launches_final.txt); algorithmic minimum (every tile read once "
-                                "per use from L2-missing operands) is ~250 GB per sweep",
-                "kernel": "panel_gemm_kernel<mode> (left-looking potrf + Takahashi inverse: 64x64 DMMA.8x8x4 tiles fed by "
-                          "TMA, cp.async.bulk.tensor + 128B swizzle + mbarrier ring) + diag64_kernel; achieved = S*n^3 flop / "
-                          "(t_potrf + t_potri), phase times from CUDA events inside nmgp_logpost_grad_profile",
-                "peak_source": "FP64 DMMA peak measured on this pool's B200 (tools/fp64_peak.cu, "
-                               "profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
+    peak, peak_source, peak_clk = fp64_peak_probe(local_rank) if rank == 0 else (FP64_PEAK_FALLBACK_TFLOPS, "", None)
+    # DRAM traffic per launch of the factorisation kernels: an ncu measurement of a previous state of the same kernels on the
+    # same workload, reported only for the configuration it was taken on (C4, one GPU, 3 chunks x 56 launches)
+    traffic, traffic_source = None, "not measured in this run (ncu only); see profiles/"
+    if a.workload == "C4" and world == 1 and a.subjects == 10000:
+        traffic = 353e9 / 168.0
+        traffic_source = ("static: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of round 1's engine on this workload "
+                          "(profiles/r01_launches_final.txt: 353 GB per sweep over 168 engine launches); not re-measured per run")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_source,
+                "kernel": "panel_gemm_kernel<mode> / inverse_kernel<mode> (left-looking potrf + guarded Takahashi / W^T W inverse: 64x64 "
+                          "DMMA.8x8x4 tiles fed by TMA, cp.async.bulk.tensor + 128B swizzle + mbarrier ring) + diag64_kernel; "
+                          "achieved = S*n^3 flop / (t_potrf + t_potri), phase times from CUDA events inside nmgp_logpost_grad_profile",
+                "peak_source": peak_source, "peak_clocks": peak_clk,
                 "algorithmic_flops_per_eval": f_potrf + f_potri,
                 "potrf_tflops": S * f_potrf / (phases["potrf"] * 1e-3) / 1e12 if phases["potrf"] > 0 else None,
-                "phase_ms": phases}
+                "potri_tflops": S * f_potri / (phases["potri"] * 1e-3) / 1e12 if phases["potri"] > 0 else None,
+                "phase_ms": phases,
+                "note": None if a.model == "nonseparable" else
+                "single-subject separable / stationary evaluations are launch-latency-bound (a few microseconds of arithmetic "
+                "per kernel): the fraction is reported for completeness, the figure of merit is ms per evaluation"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": a.subjects * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": n_eval_step * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if batch_kind else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
-            "sweep_summary": {k: summary[k] for k in ("neg_logpost", "n_failed", "n_subjects")},
-            "shared_hyper_grad": shared_hyper_grad,
             "plan": {"chunk": plan.chunk, "device_bytes": plan.device_bytes, "subjects_this_rank": S},
         }
+        if batch_kind:
+            summary_d = dict(zip(sharding.SUMMARY_FIELDS, sv[:8]))
+            line["sweep_summary"] = {k: summary_d[k] for k in ("neg_logpost", "n_failed", "n_subjects")}
+            line["shared_hyper_grad"] = dict(zip(hyper_names, sv[8:8 + len(hyper_names)]))
         if world == 1 and not a.no_cpu_baseline:
+            # CPU leg on the bench's OWN inputs (first subjects of the workload): timing + the in-run parity figure
+            tmp = tempfile.mkdtemp(prefix="nmgp_bench_")
             cores = os.cpu_count() or 1
-            v, sec, wall, n_eval = run_cpu_workers(a.model, a.N, a.M, a.cpu_subjects_per_core, cores)
-            line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{n_eval} subjects of the same workload: {cores} single-threaded processes x "
-                          f"{a.cpu_subjects_per_core} (oracle/nmgp_oracle.py, the reference's algorithm), {sec:.1f} s"}
+            files = None
+            if a.workload != "C5" and a.N * a.M <= 6000:
+                xh, Yh, ph = x.numpy(), Y.cpu().numpy(), pars_h.numpy()
+                if batch_kind:
+                    per = min(a.cpu_subjects_per_core, max(1, S // cores))
+                    files = []
+                    for c in range(cores):
+                        sl = slice(c * per, (c + 1) * per)
+                        f = os.path.join(tmp, f"in_{c}.npz")
+                        np.savez(f, x=xh[sl], Y=Yh[sl], pars=ph[sl])
+                        files.append(f)
+                else:
+                    f = os.path.join(tmp, "in_0.npz")
+                    np.savez(f, x=xh[:1], Y=Yh[:1], pars=ph[:1])
+                    files = [f]
+            v, used, desc, outs = cpu_leg(a, files)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": desc}
+            if outs and w["kind"] != "map" and vals_h is not None:
+                ev = el = eg = 0.0
+                k = 0
+                for o in outs:
+                    z = np.load(o)
+                    for i in range(z["vals"].shape[0]):
+                        rv, rg = z["vals"][i], z["grad"][i]
+                        gv, gg = vals_h[k].numpy(), grad_h[k].numpy()
+                        ev = max(ev, abs(gv[0] - rv[0]) / abs(rv[0]))
+                        el = max(el, abs(gv[1] - rv[1]) / abs(rv[1]))
+                        eg = max(eg, float(np.linalg.norm(gg - rg) / np.linalg.norm(rg)))
+                        k += 1
+                line["parity"] = {"subjects": k, "max_rel_total": ev, "max_rel_loglik": el, "max_rel_grad": eg,
+                                  "against": "oracle/nmgp_oracle.py (the reference's algorithm on the CPU) on the bench's own x, Y, pars; "
+                                             "totals and gradients include the GP-prior terms (cond 1e8..2e10: conditioning floor "
+                                             "~1e-8 / ~1e-7, tests/test_prior_conditioning_floor.py); the likelihood is held to 1e-9"}
+            elif outs and w["kind"] == "map":
+                z = np.load(outs[0])
+                p_gpu, tr, _ = plan.map_fit(pars_d, steps=w["iters"], lr=w["lr"])
+                tr = tr[:, 0, 0].cpu().numpy()
+                line["parity"] = {"map_iterations": int(w["iters"]),
+                                  "max_rel_trace": float(np.max(np.abs(tr - z["trace"]) / np.abs(z["trace"]))),
+                                  "max_abs_final_pars": float(np.max(np.abs(p_gpu[0].cpu().numpy() - z["pars"]))),
+                                  "against": "the same Adam loop with oracle/nmgp_oracle.py as objective (CPU), same start point"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

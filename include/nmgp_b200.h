@@ -244,6 +244,10 @@ int nmgp_gibbs_cov(const double* x1, const double* sigma1, const double* ell1, i
  * (The plan itself builds the same matrix time-major and blocked; this entry exists for parity tests.) */
 int nmgp_nonseparable_cov(const double* x, const double* pars, int batch, int N, int M, double* out, void* stream);
 
+/* Live FP64 tensor-pipe (DMMA.8x8x4) peak of the current device: register-only mma.sync.m8n8k4.f64 for at least
+ * `min_seconds` (<= 10), CUDA-event timed on `stream`.  bench.py's roofline denominator (no reference counterpart). */
+int nmgp_fp64_dmma_probe(double min_seconds, double* tflops_out, double* seconds_out, void* stream);
+
 /* ---- stand-alone helpers behind the reference-signature mirrors (cold paths; all device pointers, FP64, row-major) ----
  * nmgp_pairwise_sqdist: out[i,j] = (x1_i^2 + x2_j^2) - 2 x1_i x2_j for N x 1 inputs, x2 NULL = x1
  *                       (Utility/kernels.py:5-21 `pairwise_distances`, same operation order).

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libnmgp_b200.so")
 # different -D switches.  Not a fallback: the file must exist, and it is this package's own CUDA library either way.
 if os.environ.get("NMGP_B200_LIB"):
     LIB_PATH = os.path.abspath(os.environ["NMGP_B200_LIB"])
-SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "hadamard.cu", "hyper.cu", "kron.cu", "api.cu"]
+SOURCES = ["engine.cu", "engine_ll.cu", "diag.cu", "models.cu", "predict.cu", "hadamard.cu", "hyper.cu", "kron.cu", "probe.cu", "api.cu"]
 HEADERS = ["common.cuh", "engine.cuh", "models.cuh", "jacobi.cuh", os.path.join("..", "..", "include", "nmgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -145,6 +145,8 @@ def _declare(lib):
     lib.nmgp_gibbs_cov.argtypes = [dp, dp, dp, c.c_int, dp, dp, dp, c.c_int, dp, vp]
     lib.nmgp_nonseparable_cov.restype = c.c_int
     lib.nmgp_nonseparable_cov.argtypes = [dp, dp, c.c_int, c.c_int, c.c_int, dp, vp]
+    lib.nmgp_fp64_dmma_probe.restype = c.c_int
+    lib.nmgp_fp64_dmma_probe.argtypes = [c.c_double, c.POINTER(c.c_double), c.POINTER(c.c_double), vp]
     lib.nmgp_pairwise_sqdist.restype = c.c_int
     lib.nmgp_pairwise_sqdist.argtypes = [dp, c.c_int, dp, c.c_int, dp, vp]
     lib.nmgp_kron.restype = c.c_int
@@ -166,7 +168,7 @@ def _declare(lib):
 
 EXPORTS = ["nmgp_last_error", "nmgp_n_params", "nmgp_plan_create", "nmgp_plan_create_hadamard", "nmgp_plan_destroy", "nmgp_logpost_grad", "nmgp_hyper_grad", "nmgp_plan_set_hyper", "nmgp_sweep_reduce", "nmgp_logpost_grad_hyper",
            "nmgp_logpost_grad_host", "nmgp_logpost_grad_profile", "nmgp_plan_set_engine", "nmgp_plan_set_graph", "nmgp_plan_graph_replays", "nmgp_plan_last_launches", "nmgp_plan_device_bytes", "nmgp_plan_chunk",
-           "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_pairwise_sqdist", "nmgp_kron", "nmgp_kron_mv", "nmgp_gram", "nmgp_sym_eig", "nmgp_kron_eig_solve", "nmgp_potrf_batched",
+           "nmgp_plan_block", "nmgp_adam_step", "nmgp_hmc_kick", "nmgp_hmc_drift", "nmgp_hmc_accept", "nmgp_predict_prior_moments", "nmgp_predict_moments", "nmgp_predict_moments_sep", "nmgp_rbf_cov", "nmgp_gibbs_cov", "nmgp_nonseparable_cov", "nmgp_fp64_dmma_probe", "nmgp_pairwise_sqdist", "nmgp_kron", "nmgp_kron_mv", "nmgp_gram", "nmgp_sym_eig", "nmgp_kron_eig_solve", "nmgp_potrf_batched",
            "nmgp_potrf_potri_batched"]
 
 

@@ -42,17 +42,6 @@ struct nmgp_plan {
   void* maps = nullptr;      // TMA descriptors of the workspace (engine_maps_create); rebuilt when A2 appears
   double* A2_own = nullptr;  // second matrix buffer, allocated on first use by an inverse that needs it (not in `allocs`)
   Scratch w{};
-  // Second workspace of multi-chunk plans (evaluate_pipelined): chunk c works in slot c & 1, so the memory-bound covariance
-  // build of chunk c+1 and the gradient contraction of chunk c-1 run UNDER the tensor-bound factorisation of chunk c.
-  bool dual = false;
-  BlockBatch bb2;
-  void* maps2 = nullptr;
-  double* A2_own2 = nullptr;
-  Scratch w2{};
-  double *hq0b = nullptr, *hq1b = nullptr;
-  cudaStream_t aux = nullptr;                  // forward / backward passes of the pipelined evaluation (high priority)
-  std::vector<cudaEvent_t> ev_fwd, ev_fac, ev_pri;   // per chunk: forward done, factorisation done, prior solves done
-  cudaEvent_t ev_aux_done = nullptr;
   // staging for the host-buffer call
   double *pars_d = nullptr, *vals_d = nullptr, *grad_d = nullptr;
   int* info_d = nullptr;
@@ -167,12 +156,12 @@ size_t per_subject_bytes(const nmgp_plan* pl) {
   return d * sizeof(double) + nm * sizeof(int);
 }
 
-int alloc_workspace(nmgp_plan* pl, int slot = 0) {
+int alloc_workspace(nmgp_plan* pl) {
   const size_t cs = pl->chunk, N = pl->N, M = pl->M, n = pl->n, nm = pl->nmat;
   const bool svc = pl->model == NMGP_NONSEPARABLE;
   const bool had = pl->model >= NMGP_HADAMARD;
   const size_t MT = svc ? padded_M(pl->M) : 0;
-  BlockBatch& b = slot ? pl->bb2 : pl->bb;
+  BlockBatch& b = pl->bb;
   b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
   NMGP_TRY(dev_alloc(pl, &b.A, cs * nm * (size_t)pl->nP * pl->nP));
   b.A2 = nullptr;   // only the W^T W inverses need it: ensure_second_buffer() (C4's Takahashi sweep never does: -10.9 GB)
@@ -184,9 +173,11 @@ int alloc_workspace(nmgp_plan* pl, int slot = 0) {
   NMGP_CUDA_TRY(cudaStreamSynchronize(0));
   NMGP_TRY(dev_alloc(pl, &b.logdet, cs * nm));
   NMGP_TRY(dev_alloc(pl, &b.info, cs * nm));
-  NMGP_TRY(engine_maps_create(b, slot ? &pl->maps2 : &pl->maps));
-  b.maps = slot ? pl->maps2 : pl->maps;
-  Scratch& w = slot ? pl->w2 : pl->w;
+  NMGP_TRY(dev_alloc(pl, &b.pivmin, cs * nm));
+  NMGP_TRY(dev_alloc(pl, &b.pivmax, cs * nm));
+  NMGP_TRY(engine_maps_create(b, &pl->maps));
+  b.maps = pl->maps;
+  Scratch& w = pl->w;
   NMGP_TRY(dev_alloc(pl, &w.ell, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.sig, cs * N));
   NMGP_TRY(dev_alloc(pl, &w.s2, cs));
@@ -394,14 +385,7 @@ int nmgp_n_params(int model, int N, int M) {
 int nmgp_plan_destroy(nmgp_plan* pl) {
   if (!pl) return 0;
   engine_maps_destroy(pl->maps);
-  engine_maps_destroy(pl->maps2);
   if (pl->A2_own) cudaFree(pl->A2_own);
-  if (pl->A2_own2) cudaFree(pl->A2_own2);
-  if (pl->aux) cudaStreamDestroy(pl->aux);
-  if (pl->ev_aux_done) cudaEventDestroy(pl->ev_aux_done);
-  for (cudaEvent_t e : pl->ev_fwd) cudaEventDestroy(e);
-  for (cudaEvent_t e : pl->ev_fac) cudaEventDestroy(e);
-  for (cudaEvent_t e : pl->ev_pri) cudaEventDestroy(e);
   for (void* p : pl->allocs) cudaFree(p);
   if (pl->pred_scratch) cudaFree(pl->pred_scratch);
   if (pl->trace_scratch) cudaFree(pl->trace_scratch);
@@ -523,33 +507,7 @@ static int plan_create_impl(nmgp_plan** out, int model, int S, int N, int M, con
       chunk = (S + nch - 1) / nch;
     }
     pl->chunk = (int)chunk;
-    const size_t before_ws = pl->dev_bytes;
     if ((rc = alloc_workspace(pl))) break;
-    {
-      // multi-chunk plans: a second workspace for the chunk pipeline, when it fits comfortably
-      const size_t ws_bytes = pl->dev_bytes - before_ws;
-      const int nch0 = (S + pl->chunk - 1) / pl->chunk;
-      size_t f2 = 0, t2 = 0;
-      static const bool no_dual = getenv("NMGP_NO_PIPELINE") != nullptr;   // A/B timing
-      if (nch0 >= 2 && !no_dual && cudaMemGetInfo(&f2, &t2) == cudaSuccess && f2 > ws_bytes + ws_bytes / 2 + (4ull << 30)) {
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        bool ok = alloc_workspace(pl, 1) == 0 &&
-                  cudaStreamCreateWithPriority(&pl->aux, cudaStreamNonBlocking, greatest) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&pl->ev_aux_done, cudaEventDisableTiming) == cudaSuccess;
-        for (int c = 0; ok && c < nch0; ++c) {
-          cudaEvent_t e1 = nullptr, e2 = nullptr, e3 = nullptr;
-          ok = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&e3, cudaEventDisableTiming) == cudaSuccess;
-          if (e1) pl->ev_fwd.push_back(e1);
-          if (e2) pl->ev_fac.push_back(e2);
-          if (e3) pl->ev_pri.push_back(e3);
-        }
-        if (!ok) { cudaGetLastError(); rc = NMGP_ECUDA; set_last_error("nmgp_plan_create: second workspace / pipeline streams failed"); break; }
-        pl->dual = true;
-      }
-    }
     if (pl->nprior) {
       const double a0 = hyper[1], b0 = hyper[2], a1 = hyper[4], b1 = hyper[5];
       if ((rc = factor_prior(pl, a0, b0, pl->Wp0, pl->hld0, st))) break;
@@ -595,7 +553,9 @@ static int run_potrf(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* 
   return use_left_looking(pl, b) ? engine_potrf_ll(b, st, launches) : engine_potrf(b, st, launches);
 }
 // Inverse from the factor.  Three formulations, chosen by regime (measured on B200, profiles/r01_inverse_ab.txt):
-//  * Takahashi sweep (engine_potri_ll): fewest bytes per matrix; best for thousands of mid-size matrices (10 000 x n = 600:
+//  * Takahashi sweep (engine_potri_ll, behind the conditioning guard of engine_potri_ll_guarded: an ill-conditioned matrix
+//    -- small noise variance against the signal -- is routed to the W^T W path on the device): fewest bytes per matrix; best
+//    for thousands of mid-size matrices (10 000 x n = 600:
 //    19.5 ms vs 21.2 ms per 3334).  It propagates the error of the trailing inverse block into every new block column,
 //    multiplied by |L(B,j) L_jj^-1| -- for smooth GP covariances that factor exceeds 1 and the error grows geometrically
 //    with the number of block columns (exact at Kt = 16, 5e-7 at Kt = 32, garbage at Kt = 64) -- so only up to
@@ -608,29 +568,25 @@ constexpr int kTakahashiMinBatch = 1024;
 // The W^T W inverses keep W^T in a second matrix buffer.  It is allocated when an evaluation first takes such a path (never
 // inside a graph capture: the first evaluation of every variant launches directly) and stays with the plan.
 static int ensure_second_buffer(nmgp_plan* pl, BlockBatch& b) {
-  const bool second = pl->dual && b.A == pl->bb2.A;     // which workspace `b` is a view of
-  BlockBatch& home = second ? pl->bb2 : pl->bb;
-  double*& own = second ? pl->A2_own2 : pl->A2_own;
-  void*& maps = second ? pl->maps2 : pl->maps;
-  if (!home.A2) {
-    const size_t bytes = (size_t)home.batch * home.strideA() * sizeof(double);
-    if (cudaMalloc(&own, bytes) != cudaSuccess) {
+  if (!pl->bb.A2) {
+    const size_t bytes = (size_t)pl->bb.batch * pl->bb.strideA() * sizeof(double);
+    if (cudaMalloc(&pl->A2_own, bytes) != cudaSuccess) {
       cudaGetLastError();
-      own = nullptr;
+      pl->A2_own = nullptr;
       set_last_error("inverse: cudaMalloc of " + std::to_string(bytes) + " bytes for the second matrix buffer failed");
       return NMGP_ENOMEM;
     }
-    NMGP_CUDA_TRY(cudaMemset(own, 0, bytes));   // multiplied by exact zeros before it is written: must be finite
+    NMGP_CUDA_TRY(cudaMemset(pl->A2_own, 0, bytes));   // multiplied by exact zeros before it is written: must be finite
     pl->dev_bytes += bytes;
-    home.A2 = own;
-    engine_maps_destroy(maps);
-    maps = nullptr;
-    home.maps = nullptr;
-    NMGP_TRY(engine_maps_create(home, &maps));
-    home.maps = maps;
+    pl->bb.A2 = pl->A2_own;
+    engine_maps_destroy(pl->maps);
+    pl->maps = nullptr;
+    pl->bb.maps = nullptr;
+    NMGP_TRY(engine_maps_create(pl->bb, &pl->maps));
+    pl->bb.maps = pl->maps;
   }
-  b.A2 = home.A2;
-  b.maps = home.maps;
+  b.A2 = pl->bb.A2;
+  b.maps = pl->bb.maps;
   return 0;
 }
 static int run_potri(nmgp_plan* pl, BlockBatch& b, cudaStream_t st, long* launches) {
@@ -640,18 +596,19 @@ static int run_potri(nmgp_plan* pl, BlockBatch& b, cudaStream_t st, long* launch
     case 1: return engine_potri(b, st, launches);
     case 2:
       if (!ll) return engine_potri(b, st, launches);
-      if (pl->stable_inverse || b.Kt > kTakahashiMaxBlocks) {
-        NMGP_TRY(ensure_second_buffer(pl, b));
-        return engine_potri_ll_stable(b, st, launches);
-      }
-      return engine_potri_ll(b, st, launches);
+      NMGP_TRY(ensure_second_buffer(pl, b));
+      if (pl->stable_inverse || b.Kt > kTakahashiMaxBlocks) return engine_potri_ll_stable(b, st, launches);
+      return engine_potri_ll_guarded(b, st, launches);
     case 4:
       if (!has_p) return engine_potri(b, st, launches);
       NMGP_TRY(ensure_second_buffer(pl, b));
       return engine_potri_ll_recursive(b, st, launches);
     default: break;
   }
-  if (ll && b.Kt <= kTakahashiMaxBlocks && b.batch >= kTakahashiMinBatch) return engine_potri_ll(b, st, launches);
+  if (ll && b.Kt <= kTakahashiMaxBlocks && b.batch >= kTakahashiMinBatch) {
+    NMGP_TRY(ensure_second_buffer(pl, b));
+    return engine_potri_ll_guarded(b, st, launches);
+  }
   if (has_p && b.Kt > 1) {
     NMGP_TRY(ensure_second_buffer(pl, b));
     return engine_potri_ll_recursive(b, st, launches);
@@ -716,22 +673,18 @@ static int hyper_setup(nmgp_plan* pl, cudaStream_t st, HyperRaw* h) {
   if (pl->nprior && !pl->hq0) {
     NMGP_TRY(dev_alloc(pl, &pl->hq0, (size_t)pl->chunk * prior_quad_blocks(pl->N) * 4));
     NMGP_TRY(dev_alloc(pl, &pl->hq1, (size_t)pl->chunk * prior_quad_blocks(pl->N) * 4));
-    if (pl->dual) {
-      NMGP_TRY(dev_alloc(pl, &pl->hq0b, (size_t)pl->chunk * prior_quad_blocks(pl->N) * 4));
-      NMGP_TRY(dev_alloc(pl, &pl->hq1b, (size_t)pl->chunk * prior_quad_blocks(pl->N) * 4));
-    }
   }
   return 0;
 }
 
 // the hyper-parameter gradient of chunk [s0, s0 + cs) once Z0/Z1/G0/G1 and s2 of that chunk are in the scratch
 static int hyper_chunk(nmgp_plan* pl, const HyperRaw& h, int s0, int cs, const double* ps, double* hgrad, cudaStream_t st,
-                       long* launches, int slot = 0) {
+                       long* launches) {
   const int N = pl->N;
   const double* xs = pl->x + (size_t)s0 * N;
-  const Scratch& w = slot ? pl->w2 : pl->w;
-  double* hq0 = slot ? pl->hq0b : pl->hq0;
-  double* hq1 = slot ? pl->hq1b : pl->hq1;
+  const Scratch& w = pl->w;
+  double* hq0 = pl->hq0;
+  double* hq1 = pl->hq1;
   if (pl->nprior && h.prior) {
     NMGP_TRY(launch_prior_quad(xs, w.Z0, w.G0, cs, N, 1, pl->hyper[1], pl->hyper[2], hq0, st, launches));
     NMGP_TRY(launch_prior_quad(xs, w.Z1, w.G1, cs, N, pl->nv1, pl->hyper[4], pl->hyper[5], hq1, st, launches));
@@ -742,102 +695,12 @@ static int hyper_chunk(nmgp_plan* pl, const HyperRaw& h, int s0, int cs, const d
                              hgrad + (size_t)s0 * NMGP_NHYPER, st, launches);
 }
 
-// Chunk pipeline of multi-chunk plans.  The memory-bound passes around the factorisation -- covariance build before it,
-// gradient contraction after it: 12 % of a 10 000-subject sweep, 30-50 % DRAM-busy while the tensor pipe idles -- run on a
-// high-priority stream `aux` in the OTHER workspace, under the factorisation of the neighbouring chunk, whose CTAs leave the
-// DMMA pipe busy on the same SMs:
-//     aux :  F(0) F(1)       B(0) F(2)       B(1) F(3)  ...            B(last)
-//     st  :       X(0)            X(1)            X(2)  ...  X(last)   (join)
-// F = prep + kernel matrices + covariance build, X = potrf + inverse, B = contraction + rank-one terms + finish.  Chunk c
-// uses slot c & 1; B(c-1) precedes F(c+1) on `aux`, which is what frees the slot.  The GP-prior solves fork off F(c) onto the
-// plan's side streams as before and join B(c).  Everything the caller sees stays ordered on `st` (fork at entry, join at
-// exit).  Results are bit-identical to the sequential path: same kernels, same operands, same order within a subject.
-static int evaluate_pipelined(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st,
-                              const ChunkSync* sync, double* hgrad, const HyperRaw& hraw, long* launches_out) {
-  long launches = 0;
-  const int N = pl->N, M = pl->M, P = pl->P;
-  const bool had = pl->model >= NMGP_HADAMARD;
-  const int nch = (pl->S + pl->chunk - 1) / pl->chunk;
-  cudaStream_t aux = pl->aux;
-  NMGP_CUDA_TRY(cudaEventRecord(pl->ev_aux_done, st));          // fork: after whatever the caller queued on `st`
-  NMGP_CUDA_TRY(cudaStreamWaitEvent(aux, pl->ev_aux_done, 0));
-  auto forward = [&](int c) -> int {
-    const int s0 = c * pl->chunk, cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk, slot = c & 1;
-    BlockBatch b = slot ? pl->bb2 : pl->bb;
-    const Scratch& w = slot ? pl->w2 : pl->w;
-    b.batch = cs * pl->nmat;
-    const double* xs = pl->x + (size_t)s0 * N;
-    const double* Ys = pl->Y + (size_t)s0 * N * (had ? 1 : M);
-    const int* ixs = had ? pl->indx + (size_t)s0 * N : nullptr;
-    const double* ps = pars + (size_t)s0 * P;
-    if (sync && sync->before) NMGP_CUDA_TRY(cudaStreamWaitEvent(aux, sync->before[c], 0));
-    if (had) NMGP_TRY(had_forward(pl->model - NMGP_HADAMARD, cs, N, M, xs, ixs, ps, P, pl->hc, w, b, aux, &launches));
-    else if (pl->model == NMGP_NONSEPARABLE) NMGP_TRY(svc_forward(cs, N, M, xs, ps, P, pl->hc, w, b, aux, &launches));
-    else NMGP_TRY(sep_forward(pl->model, cs, N, M, xs, Ys, ps, P, pl->hc, w, b, aux, &launches));
-    NMGP_CUDA_TRY(cudaEventRecord(pl->ev_fwd[c], aux));
-    // prior solves (+ the hyper-parameter gradient) on the side streams, off the forward pass
-    if (pl->nprior) {
-      const double* L0 = pl->Wp0 + (size_t)s0 * N * N;
-      const double* L1 = pl->Wp1 + (size_t)s0 * N * N;
-      const bool back = grad || hgrad;
-      NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_fwd[c], 0));
-      NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side2, pl->ev_fwd[c], 0));
-      NMGP_TRY(launch_prior_solve(L0, w.R0, w.Z0, cs, N, 1, 0, pl->side, &launches));
-      if (back) NMGP_TRY(launch_prior_solve(L0, w.Z0, w.G0, cs, N, 1, 1, pl->side, &launches));
-      NMGP_TRY(launch_prior_solve(L1, w.R1, w.Z1, cs, N, pl->nv1, 0, pl->side2, &launches));
-      if (back) NMGP_TRY(launch_prior_solve(L1, w.Z1, w.G1, cs, N, pl->nv1, 1, pl->side2, &launches));
-      NMGP_CUDA_TRY(cudaEventRecord(pl->ev_join2, pl->side2));
-      NMGP_CUDA_TRY(cudaStreamWaitEvent(pl->side, pl->ev_join2, 0));
-      if (hgrad) NMGP_TRY(hyper_chunk(pl, hraw, s0, cs, ps, hgrad, pl->side, &launches, slot));
-      NMGP_CUDA_TRY(cudaEventRecord(pl->ev_pri[c], pl->side));
-    } else if (hgrad) {
-      NMGP_TRY(hyper_chunk(pl, hraw, s0, cs, ps, hgrad, aux, &launches, slot));
-    }
-    return 0;
-  };
-  NMGP_TRY(forward(0));
-  for (int c = 0; c < nch; ++c) {
-    const int s0 = c * pl->chunk, cs = pl->S - s0 < pl->chunk ? pl->S - s0 : pl->chunk, slot = c & 1;
-    if (c + 1 < nch) NMGP_TRY(forward(c + 1));
-    BlockBatch b = slot ? pl->bb2 : pl->bb;
-    const Scratch& w = slot ? pl->w2 : pl->w;
-    b.batch = cs * pl->nmat;
-    NMGP_CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_fwd[c], 0));
-    NMGP_TRY(run_potrf(pl, b, st, &launches));
-    NMGP_TRY(run_potri(pl, b, st, &launches));
-    NMGP_CUDA_TRY(cudaEventRecord(pl->ev_fac[c], st));
-    NMGP_CUDA_TRY(cudaStreamWaitEvent(aux, pl->ev_fac[c], 0));
-    if (pl->nprior) NMGP_CUDA_TRY(cudaStreamWaitEvent(aux, pl->ev_pri[c], 0));
-    const double* Ys = pl->Y + (size_t)s0 * N * (had ? 1 : M);
-    const int* ixs = had ? pl->indx + (size_t)s0 * N : nullptr;
-    const double* ps = pars + (size_t)s0 * P;
-    double* vs = vals + (size_t)s0 * NMGP_NVALS;
-    double* gs = grad ? grad + (size_t)s0 * P : nullptr;
-    int* is = info + s0;
-    const double* h0 = pl->hld0 ? pl->hld0 + s0 : nullptr;
-    const double* h1 = pl->hld1 ? pl->hld1 + s0 : nullptr;
-    if (had) NMGP_TRY(had_backward(pl->model - NMGP_HADAMARD, cs, N, M, Ys, ixs, ps, P, pl->hc, w, b, h0, h1, vs, gs, is, aux, &launches));
-    else if (pl->model == NMGP_NONSEPARABLE) NMGP_TRY(svc_backward(cs, N, M, Ys, ps, P, pl->hc, w, b, h0, h1, vs, gs, is, aux, &launches));
-    else NMGP_TRY(sep_backward(pl->model, cs, N, M, ps, P, pl->hc, w, b, h0, h1, vs, gs, is, aux, &launches));
-    if (sync && sync->after) NMGP_CUDA_TRY(cudaEventRecord(sync->after[c], aux));
-  }
-  NMGP_CUDA_TRY(cudaEventRecord(pl->ev_aux_done, aux));         // join
-  NMGP_CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_aux_done, 0));
-  *launches_out = launches;
-  return 0;
-}
-
 static int evaluate(nmgp_plan* pl, const double* pars, double* vals, double* grad, int* info, cudaStream_t st,
                     float* phase_ms, const ChunkSync* sync = nullptr, double* hgrad = nullptr) {
   long launches = 0;
   const int N = pl->N, M = pl->M, P = pl->P;
   HyperRaw hraw{};
   if (hgrad) NMGP_TRY(hyper_setup(pl, st, &hraw));
-  if (pl->dual && !phase_ms && pl->S > pl->chunk) {   // the profiling call keeps the phases apart on one stream
-    NMGP_TRY(evaluate_pipelined(pl, pars, vals, grad, info, st, sync, hgrad, hraw, &launches));
-    pl->last_launches = launches;
-    return 0;
-  }
   cudaEvent_t ev[NMGP_NPHASES + 1];
   if (phase_ms) {
     for (int i = 0; i <= NMGP_NPHASES; ++i) NMGP_CUDA_TRY(cudaEventCreate(&ev[i]));

@@ -20,6 +20,10 @@ struct BlockBatch {
   const void* maps = nullptr;  // TMA descriptors of (A, A2, Dinv, Pbuf) for the FULL workspace (engine_maps_create); owned by the plan
   double* logdet = nullptr;  // [batch]
   int* info = nullptr;       // [batch]
+  // [batch] smallest / largest pivot (diagonal entry of L) seen by the diagonal-block steps; optional.  Their squared ratio
+  // is the conditioning indicator the guarded inverse uses to route a matrix (engine_potri_ll_guarded).
+  double* pivmin = nullptr;
+  double* pivmax = nullptr;
   int n = 0;                 // logical dimension
   int nP = 0;                // padded dimension (multiple of NB)
   int Kt = 0;                // blocks per side
@@ -60,6 +64,13 @@ int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launch
 // `out` receives nullptr when the batch has no panel buffer.  engine_*_ll build a temporary set when b.maps is null.
 int engine_maps_create(const BlockBatch& b, void** out);
 void engine_maps_destroy(void* maps);
+// The production inverse for thousands of mid-size matrices: every matrix takes the Takahashi sweep (fewest bytes) unless its
+// factor says it is ill-conditioned -- (min pivot / max pivot)^2 < threshold(Kt) -- in which case the backward-stable W^T W
+// path handles it; both launch sequences are queued, each kernel skips the matrices of the other (decided on the device: no
+// host synchronisation, graph-capturable).  Measured (profiles/r02_takahashi_stress.txt): the sweep's gradient error grows
+// from 4e-13 at noise variance e^-4 to 4e-9 at e^-8 and 5e-3 at e^-10 for n = 600 (10 block columns), and ~500x per two more
+// block columns; the W^T W path stays below 2e-7 everywhere.  Requires b.pivmin / b.pivmax (written by potrf), b.A2, b.Pbuf.
+int engine_potri_ll_guarded(const BlockBatch& b, cudaStream_t st, long* launches);
 // largest number of 64-blocks per side for which the Takahashi recursion of engine_potri_ll is used (see api.cu)
 constexpr int kTakahashiMaxBlocks = 16;
 

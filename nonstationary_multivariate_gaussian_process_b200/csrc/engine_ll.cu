@@ -65,7 +65,20 @@ struct LLArgs {
   double* Pbuf;
   long strideA, strideP;
   int ld, Kt, batch, step, n8, ntiles;
+  // routing of the guarded inverse: 0 = every matrix; 1 = only well-conditioned matrices (Takahashi kernels);
+  // 2 = only ill-conditioned ones (W^T W kernels).  ill-conditioned: pivmin^2 < guard_thr * pivmax^2.
+  int guard;
+  double guard_thr;
+  const double* pivmin;
+  const double* pivmax;
 };
+
+__device__ __forceinline__ bool guard_skips(const LLArgs& g, int mat) {
+  if (g.guard == 0) return false;
+  const double a = g.pivmin[mat], b = g.pivmax[mat];
+  const bool ill = a * a < g.guard_thr * b * b;
+  return g.guard == 1 ? ill : !ill;
+}
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier PTX
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -147,6 +160,9 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
   unsigned long long* empty = full + STAGES;
 
+#if !NMGP_LL_FLAT
+  if (g.guard != 0 && guard_skips(g, blockIdx.y)) return;   // gridDim.y == batch (launch_ll): one matrix per CTA; uniform
+#endif
   const int s = g.step;
   const int last = g.Kt - 1;
   const int vlast = g.n8 - last * NB;  // valid rows/cols of the last block (multiple of 8)
@@ -450,6 +466,7 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
   int gq = 0;
 
   for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
+    if (guard_skips(g, mat)) continue;   // CTA-uniform; nothing of this matrix has touched the ring yet
     double* Am = g.A + (long)mat * g.strideA;
     double* A2m = g.A2 + (long)mat * g.strideA;
     const int dbase = mat * Kt * 2;
@@ -662,6 +679,7 @@ int launch_ll(const MapSet& ms, const LLArgs& g0, int ntiles, cudaStream_t st, l
   // assignment of CTAs to SMs: a slow CTA delays nothing but its own successor)
   static const int waves = getenv("NMGP_LL_WAVES") ? atoi(getenv("NMGP_LL_WAVES")) : 32;   // A/B timing: 8 -> 32: -1.5 % time
   const int gy = g.batch < 65535 ? g.batch : 65535;
+  if (g.guard != 0 && gy != g.batch) { set_last_error("guarded inverse: more than 65535 matrices in one batch"); return -1; }
   int gx = (int)(((long)resident_ctas(panel_gemm_kernel<MODE>, PG_THREADS, LL_SMEM, slots) * waves + gy - 1) / gy);
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
@@ -680,6 +698,7 @@ LLArgs make_ll(const BlockBatch& b) {
   g.ld = b.nP; g.Kt = b.Kt; g.batch = b.batch; g.step = 0;
   g.n8 = (int)round_up(b.n, 8);
   g.ntiles = 0;
+  g.guard = 0; g.guard_thr = 0.0; g.pivmin = b.pivmin; g.pivmax = b.pivmax;
   return g;
 }
 
@@ -763,6 +782,39 @@ int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launch
     NMGP_TRY(launch_inv<REC_T>(*ms, g, st, launches, hs));
     NMGP_TRY(launch_inv<REC_W>(*ms, g, st, launches, hs));
   }
+  NMGP_TRY(launch_inv<LAUUM>(*ms, g, st, launches));
+  return 0;
+}
+
+// threshold on (min pivot / max pivot)^2 below which a matrix leaves the Takahashi sweep: calibrated on the grid of
+// profiles/r02_takahashi_stress.txt with a margin of ~4x in the noise variance (sweep error <= 2e-10 at the threshold)
+static double takahashi_guard_threshold(int Kt) {
+  static const char* ev = getenv("NMGP_TAKAHASHI_GUARD");   // A/B timing: 0 = no guard (raw sweep), x = threshold
+  if (ev) return atof(ev);
+  return Kt <= 10 ? 5e-4 : 2.5e-3;
+}
+
+int engine_potri_ll_guarded(const BlockBatch& b, cudaStream_t st, long* launches) {
+  if (b.batch <= 0) return 0;
+  const double thr = takahashi_guard_threshold(b.Kt);
+  if (!(thr > 0.0) || !b.pivmin || !b.pivmax || NMGP_LL_FLAT) return engine_potri_ll(b, st, launches);
+  if (!b.Pbuf || !b.A2) { set_last_error("engine_potri_ll_guarded: no panel / second matrix buffer"); return -1; }
+  MapRef mr;
+  NMGP_TRY(mr.init(b));
+  const MapSet* ms = mr.ms;
+  LLArgs g = make_ll(b);
+  g.guard_thr = thr;
+  g.guard = 1;                                   // Takahashi sweep: the well-conditioned matrices
+  for (int j = b.Kt - 1; j >= 0; --j) {
+    g.step = j;
+    NMGP_TRY(launch_ll<TK_PANEL>(*ms, g, b.Kt - 1 - j, st, launches));
+    NMGP_TRY(launch_ll<TK_COL>(*ms, g, b.Kt - 1 - j, st, launches));
+    NMGP_TRY(launch_ll<TK_DIAG>(*ms, g, 1, st, launches));
+  }
+  g.guard = 2;                                   // W^T W: the rest (normally none: three launches of CTAs that return at once)
+  g.step = 0;
+  NMGP_TRY(launch_inv<PANEL_ALL>(*ms, g, st, launches));
+  NMGP_TRY(launch_inv<TRTRI_ROW>(*ms, g, st, launches));
   NMGP_TRY(launch_inv<LAUUM>(*ms, g, st, launches));
   return 0;
 }

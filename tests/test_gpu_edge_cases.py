@@ -81,14 +81,16 @@ def test_single_new_input_and_sample(cuda_device):
         assert rel_err(np.sqrt(s2_y[0, 0, 0].cpu().numpy()), (pct[0, 2] - pct[0, 1]) / 1.96) < 1e-7, (N, M)
 
 
-@pytest.mark.parametrize("log_s2", [-4.0, -8.0, -11.5])
-def test_takahashi_sweep_on_ill_conditioned_covariances_at_its_size_limit(log_s2, cuda_device):
-    """The Takahashi inverse sweep ('left': what the 10 000-subject sweep uses for <= 16 block columns) is not backward
-    stable in general: the error of the trailing inverse block is carried into every new block column.  At its size limit
-    (n = 1024 = 16 blocks) and with the noise variance lowered to exp(-11.5) ~ 1e-5 (cond(Sigma) grows by ~2000 against the
-    drivers' exp(-4)) its gradient must still agree with the backward-stable W^T W inverse ('left_stable') far inside the
-    1e-9 contract -- otherwise the algorithm choice by batch size (api.cu:run_potri) would make a subject's gradient depend
-    on how many subjects share its chunk or rank."""
+@pytest.mark.parametrize("log_s2", [-4.0, -6.0, -8.0, -11.5])
+def test_guarded_takahashi_sweep_on_ill_conditioned_covariances_at_its_size_limit(log_s2, cuda_device):
+    """The Takahashi inverse sweep (what the 10 000-subject sweep uses for <= 16 block columns) is not backward stable: the
+    error of the trailing inverse block is carried into every new block column, and for smooth covariances with little
+    noise it grows geometrically (measured, profiles/r02_takahashi_stress.txt: n = 1024, noise variance e^-8: gradient off by
+    5e-3; e^-11.5: garbage).  The production path therefore routes ill-conditioned matrices -- (min pivot / max pivot)^2 of
+    the factor below a threshold -- to the backward-stable W^T W inverse on the device (engine_potri_ll_guarded).  At the
+    sweep's size limit (n = 1024 = 16 blocks), from the drivers' noise level down to e^-11.5, engine 'left' (guarded sweep)
+    must agree with 'left_stable' (W^T W for everything) inside the 1e-9 contract, so that a subject's gradient does not
+    depend on which path its batch size selects (api.cu:run_potri)."""
     from nonstationary_multivariate_gaussian_process_b200 import synth
     from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
     N, M, S = 128, 8, 4
@@ -110,4 +112,4 @@ def test_takahashi_sweep_on_ill_conditioned_covariances_at_its_size_limit(log_s2
     for s in range(S):
         ev = rel_err(out["left"][0][s, 0], out["left_stable"][0][s, 0])
         eg = rel_err(out["left"][1][s], out["left_stable"][1][s])
-        assert ev < 1e-12 and eg < 1e-10, (log_s2, s, ev, eg)
+        assert ev < 1e-11 and eg < 1e-9, (log_s2, s, ev, eg)

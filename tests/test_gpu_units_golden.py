@@ -173,8 +173,7 @@ def test_not_positive_definite_is_nan_with_a_warning(cuda_device):
     N, M = 20, 2
     x, Y, _ = synth.sample_subject(N, M, 0)
     p = synth.start_point("nonseparable", N, M, 0, 0.0)
-    p[-1] = -800.0                 # sigma2_err = exp(-800) = 0
-    p[:N] = 5.0                    # length scales e^5: K_x numerically rank one -> a pivot fails
+    p[0] = 800.0                   # ell_0 = exp(800) = inf: row 0 of K_x is NaN -> the first pivot is not a positive number
     pt = torch.from_numpy(p).requires_grad_(True)
     with pytest.warns(logpos.NmgpNotPositiveDefinite):
         v = logpos.nlogpos_obj_SVC(pt, torch.from_numpy(Y), torch.from_numpy(x), Prior=False)

@@ -139,11 +139,20 @@ __global__ void k_dmma884_smem(double* out, int iters) {
   if (r == 123.456) out[0] = r;
 }
 
+static void row(const char* what, int threads, int cps, double flop, double ms) {
+  if (ms < 0) printf("threads %4d cta/sm %d  %-16s launch failed (too many registers for this CTA size): skipped\n", threads, cps, what);
+  else printf("threads %4d cta/sm %d  %-16s %7.2f TF/s\n", threads, cps, what, flop / ms * 1e-9);
+}
+
+// best-of-`reps` duration of f() in ms, or a negative value when the launch itself fails (e.g. 1024 threads x more than 64
+// registers do not fit an SM): an unlaunched kernel must not be timed -- round 1's table printed 3e5..1e6 "TF/s" for those.
 template <typename F>
 static double time_ms(F f, int reps) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  f(); f(); f();
+  f();
+  if (cudaGetLastError() != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return -1.0; }
+  f(); f();
   CK(cudaDeviceSynchronize());
   float best = 1e30f;
   for (int r = 0; r < reps; ++r) {
@@ -171,15 +180,15 @@ int main(int argc, char** argv) {
       double warps = (double)grid * threads / 32;
       double ms;
       ms = time_ms([&] { k_dfma<8><<<grid, threads>>>(out, iters, 0.5); }, 5);
-      printf("threads %4d cta/sm %d  DFMA ilp8        %7.2f TF/s\n", threads, cps, 2.0 * 8 * iters * grid * threads / ms * 1e-9);
+      row("DFMA ilp8", threads, cps, 2.0 * 8 * iters * grid * threads, ms);
       ms = time_ms([&] { k_dmma884<8><<<grid, threads>>>(out, iters, 0.5); }, 5);
-      printf("threads %4d cta/sm %d  DMMA m8n8k4 x8   %7.2f TF/s\n", threads, cps, 2.0 * 256 * 8 * iters * warps / ms * 1e-9);
+      row("DMMA m8n8k4 x8", threads, cps, 2.0 * 256 * 8 * iters * warps, ms);
       ms = time_ms([&] { k_dmma1684<8><<<grid, threads>>>(out, iters, 0.5); }, 5);
-      printf("threads %4d cta/sm %d  DMMA m16n8k4 x8  %7.2f TF/s\n", threads, cps, 2.0 * 512 * 8 * iters * warps / ms * 1e-9);
+      row("DMMA m16n8k4 x8", threads, cps, 2.0 * 512 * 8 * iters * warps, ms);
       ms = time_ms([&] { k_dmma1688<8><<<grid, threads>>>(out, iters, 0.5); }, 5);
-      printf("threads %4d cta/sm %d  DMMA m16n8k8 x8  %7.2f TF/s\n", threads, cps, 2.0 * 1024 * 8 * iters * warps / ms * 1e-9);
+      row("DMMA m16n8k8 x8", threads, cps, 2.0 * 1024 * 8 * iters * warps, ms);
       ms = time_ms([&] { k_dmma16816<4><<<grid, threads>>>(out, iters, 0.5); }, 5);
-      printf("threads %4d cta/sm %d  DMMA m16n8k16 x4 %7.2f TF/s\n", threads, cps, 2.0 * 2048 * 4 * iters * warps / ms * 1e-9);
+      row("DMMA m16n8k16 x4", threads, cps, 2.0 * 2048 * 4 * iters * warps, ms);
     }
   }
   {
@@ -201,11 +210,13 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e0));
     int n = 0;
     for (; n < 200; ++n) k_dmma884<8><<<grid, threads>>>(out, iters, 0.5);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("sustained DMMA m8n8k4 (%.1f s): %7.2f TF/s\n", ms * 1e-3, 2.0 * 256 * 8 * iters * warps * n / ms * 1e-9);
     CK(cudaEventRecord(e0));
     for (n = 0; n < 200; ++n) k_dfma<8><<<grid, threads>>>(out, iters, 0.5);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("sustained DFMA (%.1f s): %7.2f TF/s\n", ms * 1e-3, 2.0 * 8 * iters * (double)grid * threads * n / ms * 1e-9);

@@ -1,4 +1,5 @@
-"""Accuracy of the two inverse formulations on ill-conditioned covariances (GPU box): Takahashi sweep ('left') vs the
+"""NMGP_TAKAHASHI_GUARD=0 python tools/run_takahashi_stress.py  -> the RAW sweep;  without the variable: the guarded one.
+Accuracy of the two inverse formulations on ill-conditioned covariances (GPU box): Takahashi sweep ('left') vs the
 backward-stable W^T W inverse ('left_stable'), both against the CPU oracle (the reference's LU inverse + autograd), for a
 grid of matrix sizes (block columns Kt) and noise variances.  Evidence for api.cu:run_potri's choice and for
 tests/test_gpu_edge_cases.py::test_takahashi_sweep_*.   usage: python tools/run_takahashi_stress.py"""
