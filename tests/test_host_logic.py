@@ -174,3 +174,38 @@ def test_hyper_adam_matches_torch_adam_and_keeps_positive_values_positive():
         HyperAdam(hyper, ("nope",), lr=0.1)
     nan = opt.step(hyper, {"mu_L": float("nan"), "alpha_L": float("nan")})
     assert nan["mu_L"] == hyper["mu_L"] and nan["alpha_L"] == hyper["alpha_L"]
+
+
+def test_prediction_draws_consume_the_random_stream_like_one_tensor_per_draw():
+    """prediction._draw_interleaved (in-place normal_() on views) against the reference's pattern -- a fresh tensor per
+    `Normal(loc, scale).sample()` call, per new input and sample (Utility/prediction.py:1104-1169) -- under the same seed."""
+    import time
+    import torch
+    from nonstationary_multivariate_gaussian_process_b200 import prediction as P
+    f64 = torch.float64
+    for G, ns, T, M in [(7, 5, 21, 6), (3, 4, 3, 2), (4, 3, 55, 10), (5, 2, 15, 5), (5, 2, 16, 16)]:
+        torch.manual_seed(1234)
+        ref_l, ref_u, ref_y = torch.empty((G, ns), dtype=f64), torch.empty((G, ns, T), dtype=f64), torch.empty((G, ns, M), dtype=f64)
+        for gi in range(G):
+            for s in range(ns):
+                ref_l[gi, s] = torch.empty((), dtype=f64).normal_()
+                ref_u[gi, s] = torch.empty(T, dtype=f64).normal_()
+                ref_y[gi, s] = torch.empty(M, dtype=f64).normal_()
+        tail_ref = torch.rand(1)
+        torch.manual_seed(1234)
+        z_l, z_u, z_y = torch.empty((G, ns), dtype=f64), torch.empty((G, ns, T), dtype=f64), torch.empty((G, ns, M), dtype=f64)
+        P._draw_interleaved(z_l, z_u, z_y)
+        assert torch.equal(z_l, ref_l) and torch.equal(z_u, ref_u) and torch.equal(z_y, ref_y)
+        assert torch.equal(torch.rand(1), tail_ref)          # the generator is left in the same state
+    # two-buffer and one-buffer modes (pred_cov / pred_smoothness)
+    torch.manual_seed(5)
+    a = torch.stack([torch.empty((), dtype=f64).normal_() for _ in range(12)]).reshape(4, 3)
+    torch.manual_seed(5)
+    b = torch.empty((4, 3), dtype=f64)
+    P._draw_interleaved(b)
+    assert torch.equal(a, b)
+    # the drivers' shape: 201 new inputs x 100 samples (Nonseparable_model.py:377-399)
+    z = [torch.empty((201, 100), dtype=f64), torch.empty((201, 100, 21), dtype=f64), torch.empty((201, 100, 6), dtype=f64)]
+    t0 = time.perf_counter()
+    P._draw_interleaved(*z)
+    assert time.perf_counter() - t0 < 2.0
