@@ -11,6 +11,7 @@
 // torch.symeig at Utility/distributions.py:37,40 (block formulation) and the Cholesky
 // inside MultivariateNormal at logpos.py:274,279,358,365.
 #include "engine.cuh"
+#include "tile_mma.cuh"
 
 #include <cstdlib>
 
@@ -19,8 +20,10 @@ namespace nmgp {
 namespace {
 
 constexpr int NB = kNB;          // 64
-constexpr int LDS = NB + 4;      // shared tile stride (doubles): == 4 mod 16 -> conflict-free DMMA fragment loads
-constexpr int TILE_THREADS = 128;
+using tile::LDS;
+using tile::TILE_THREADS;
+using tile::load_tile;
+using tile::warp_mma;
 constexpr size_t TILE_SMEM = 2ull * NB * LDS * sizeof(double);
 
 enum Mode : int {
@@ -49,46 +52,6 @@ __device__ __forceinline__ void tri_decode(int t, int& a, int& b) {
   while ((long)a * (a + 1) / 2 > t) --a;
   while ((long)(a + 1) * (a + 2) / 2 <= t) ++a;
   b = t - a * (a + 1) / 2;
-}
-
-// straight copy of one NB x NB tile (row stride ld) into shared [NB][LDS]
-__device__ __forceinline__ void load_tile(double* __restrict__ S, const double* __restrict__ src, int ld) {
-  constexpr int V2 = NB / 2;  // double2 per row
-#pragma unroll 4
-  for (int idx = threadIdx.x; idx < NB * V2; idx += TILE_THREADS) {
-    const int r = idx / V2, c2 = idx % V2;
-    const double2 v = *reinterpret_cast<const double2*>(src + (long)r * ld + 2 * c2);
-    *reinterpret_cast<double2*>(S + r * LDS + 2 * c2) = v;
-  }
-}
-
-// acc(32x32 per warp) += opA(32 x NB) * opB(32 x NB)^T.   KM: S[row][k],  MM: S[k][row].
-template <bool A_KM, bool B_KM>
-__device__ __forceinline__ void warp_mma(const double* __restrict__ SA, const double* __restrict__ SB, int m0, int n0,
-                                         double (&acc)[4][4][2]) {
-  const int lane = threadIdx.x & 31;
-  const int lr = lane >> 2, lk = lane & 3;
-  const double* pa = A_KM ? SA + (m0 + lr) * LDS + lk : SA + lk * LDS + m0 + lr;
-  const double* pb = B_KM ? SB + (n0 + lr) * LDS + lk : SB + lk * LDS + n0 + lr;
-  constexpr int a_sub = A_KM ? 8 * LDS : 8;  // next 8-row subtile
-  constexpr int b_sub = B_KM ? 8 * LDS : 8;
-  constexpr int a_k = A_KM ? 4 : 4 * LDS;    // next k-step of 4
-  constexpr int b_k = B_KM ? 4 : 4 * LDS;
-#pragma unroll 4
-  for (int k = 0; k < NB; k += 4) {
-    double a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[i] = pa[i * a_sub];
-      b[i] = pb[i * b_sub];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    pa += a_k;
-    pb += b_k;
-  }
 }
 
 template <int MODE>
@@ -344,6 +307,12 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
   const int Kt = b.Kt;
   int W = Kt >= 128 ? 8 : 2;   // measured (profiles/r01_potrf_panel_width.txt): n = 5000 is chain-bound for any W, n = 16 384 gains up to W = 8
   if (const char* ev = getenv("NMGP_POTRF_W")) { const int w = atoi(ev); if (w >= 1 && w <= 16) W = w; }   // A/B timing
+  // 128-wide diagonal steps (diag.cu:diag128_kernel; needs the side buffer for W21 and the multiply-by-inverse panel): half
+  // the chain links and a third fewer launches, but NOT faster -- the two dependent 64 x 64 Choleskys (17.5 us each) dominate the
+  // link either way, and the four small products between them run on one SM (measured, profiles/r02_diag128.txt: n = 5000
+  // 4.11 vs 4.05 ms, n = 16 384 53.4 vs 53.8 ms).  Kept for A/B timing (NMGP_DIAG128=1), off by default.
+  static const bool want_wide = getenv("NMGP_DIAG128") != nullptr && atoi(getenv("NMGP_DIAG128")) != 0;
+  const bool wide_diag = !stable_panel && b.Pbuf != nullptr && want_wide && W >= 2;
   // helper stream and events: created once per (host thread, device) and reused by every call
   struct Helper {
     int device = -1;
@@ -377,11 +346,19 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
   int last_e = -1, panel = 0;
   for (int p0 = 0; rc == 0 && p0 < Kt; p0 += W, ++panel) {
     const int p1 = p0 + W < Kt ? p0 + W : Kt, e = panel & 1;
-    for (int k = p0; rc == 0 && k < p1; ++k) {
+    for (int k = p0; rc == 0 && k < p1;) {
       g.step = k;
+      if (wide_diag && k + 1 < p1) {
+        // two block columns per chain link: 128 x 128 diagonal block + the panel below it, then the rest of this panel (rank 128)
+        if ((rc = engine_diag128_step(b, k, crit, launches))) break;
+        if (k + 2 < p1) rc = launch_syrk_wide<false>(g, k + 2, p1, k, 2, crit, launches);
+        k += 2;
+        continue;
+      }
       if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
       if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches))) break;
       if (k + 1 < p1) rc = launch_syrk_wide<false>(g, k + 1, p1, k, 1, crit, launches);   // rest of this panel, rank 64
+      ++k;
     }
     if (rc != 0 || !cu(cudaEventRecord(evP[e], crit))) break;
     last_e = e;

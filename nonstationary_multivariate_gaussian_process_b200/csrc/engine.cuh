@@ -49,6 +49,10 @@ int engine_potri(const BlockBatch& b, cudaStream_t st, long* launches);
 // One diagonal-block step (factor A(k,k), W_kk = L_kk^-1 into Dinv, log det, info) -- shared by both engines.
 int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches, bool accurate = false);
 
+// 128-wide diagonal step for a handful of large matrices: blocks k and k+1 in ONE launch (both diagonal factorisations, the
+// tile between them, W21 of the 128 x 128 inverse into Pbuf slot k) followed by the panel below both block columns.
+int engine_diag128_step(const BlockBatch& b, int k, cudaStream_t st, long* launches);
+
 // Left-looking potrf / Takahashi inverse for large batches of mid-size matrices (engine_ll.cu).  Same results layout as
 // engine_potrf / engine_potri.  Requires b.Pbuf, and A's padding and upper block triangle to hold finite values
 // (the plan zero-fills the workspace once).
