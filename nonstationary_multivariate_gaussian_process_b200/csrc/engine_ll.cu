@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
                                                                          const __grid_constant__ CUtensorMap mapP,
                                                                          LLArgs g) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET arithmetic on the shared pointer (an integer round trip would make every operand fetch a
+  // generic LD instead of LDS: the compiler loses the address space)
+  unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
   unsigned long long* empty = full + STAGES;
 
@@ -411,7 +413,9 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap mapA2,
                                                              const __grid_constant__ CUtensorMap mapD, LLArgs g) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET arithmetic on the shared pointer (an integer round trip would make every operand fetch a
+  // generic LD instead of LDS: the compiler loses the address space)
+  unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
 
   const int Kt = g.Kt, last = g.Kt - 1;
