@@ -57,48 +57,77 @@ __global__ void had_prep_kernel(int variant, const double* __restrict__ pars, in
     for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) R1[(long)c * N * T + idx] = p[N + idx] - mu1;
 }
 
-// Sigma in the engine's padded layout (both triangles, identity padding)
-__global__ void had_build_kernel(const double* __restrict__ Kx, const double* __restrict__ R, const double* __restrict__ Rt,
-                                 const double* __restrict__ s2v, int N, int M, double* __restrict__ A, long strideA, int ld) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  const int p = blockIdx.y;
+// Sigma in the engine's padded layout (both triangles, identity padding).  A CTA writes a patch of HB_ROWS rows x 128
+// columns: each thread keeps the factor row of ITS column in registers and walks the patch's rows, whose factor rows sit in
+// shared memory -- per element one K_x load, M FMAs and one store (the first version re-read M factor entries from L2 for
+// every element: 17 ms for 3000 x (N = 600), a fifth of the HBM rate).
+constexpr int HB_ROWS = 16;
+template <int MM>
+__global__ void __launch_bounds__(128) had_build_kernel(const double* __restrict__ Kx, const double* __restrict__ R,
+                                                        const double* __restrict__ Rt, const double* __restrict__ s2v, int N,
+                                                        double* __restrict__ A, long strideA, int ld) {
+  __shared__ double rs[HB_ROWS][MM];
+  const int q = blockIdx.x * 128 + threadIdx.x;
+  const int p0 = blockIdx.y * HB_ROWS;
   const int c = blockIdx.z;
-  if (q >= ld) return;
-  double v;
-  if (p < N && q < N) {
-    const double* rp = R + ((long)c * N + p) * RM;          // uniform over the warp
-    const double* rq = Rt + (long)c * RM * N + q;             // coalesced
-    double ki = 0.0;
-    for (int k = 0; k < M; ++k) ki += rp[k] * rq[(long)k * N];
-    v = Kx[((long)c * N + p) * N + q] * ki;
-    if (p == q) v += s2v[c];
-  } else {
-    v = (p == q) ? 1.0 : 0.0;
+  for (int idx = threadIdx.x; idx < HB_ROWS * MM; idx += 128) {
+    const int pr = idx / MM, k = idx % MM;
+    rs[pr][k] = (p0 + pr < N) ? R[((long)c * N + p0 + pr) * RM + k] : 0.0;
   }
-  A[(long)c * strideA + (long)p * ld + q] = v;
+  double rq[MM];
+#pragma unroll
+  for (int k = 0; k < MM; ++k) rq[k] = (q < N) ? Rt[((long)c * RM + k) * N + q] : 0.0;
+  __syncthreads();
+  if (q >= ld) return;
+  const double s2 = s2v[c];
+  double* Ac = A + (long)c * strideA;
+#pragma unroll 4
+  for (int pr = 0; pr < HB_ROWS; ++pr) {
+    const int p = p0 + pr;
+    if (p >= ld) break;
+    double v;
+    if (p < N && q < N) {
+      double ki = 0.0;
+#pragma unroll
+      for (int k = 0; k < MM; ++k) ki += rs[pr][k] * rq[k];
+      v = Kx[((long)c * N + p) * N + q] * ki;
+      if (p == q) v += s2;
+    } else {
+      v = (p == q) ? 1.0 : 0.0;
+    }
+    Ac[(long)p * ld + q] = v;
+  }
 }
 
-// One warp per row n.  PASS 0 (weights = row n of Sigma^-1): alpha[n], W[n][k] = sum_n' z K_x R[n'][k], V[n][k] = sum z CK R.
+// One warp per row n, eight rows per CTA; the transposed factor table Rt [M][N] of the subject is staged in shared memory
+// once per CTA (it was re-read from L2 by every lane for every element: 104 GB of L2 traffic per sweep at N = 600).
+// PASS 0 (weights = row n of Sigma^-1): alpha[n], W[n][k] = sum_n' z K_x R[n'][k], V[n][k] = sum z CK R.
 // PASS 1 (weights = alpha): Sa[n][k] = sum_n' alpha_n' K_x[n,n'] R[n'][k], Ca[n][k] = sum alpha_n' CK[n,n'] R[n'][k].
-template <int PASS>
-__global__ void __launch_bounds__(256) had_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N, int M,
+template <int PASS, int MM>
+__global__ void __launch_bounds__(256) had_contract_kernel(const double* __restrict__ A, long strideA, int ld, int N,
                                                            const double* __restrict__ y, const double* __restrict__ Kx,
                                                            const double* __restrict__ CK, const double* __restrict__ Rt,
                                                            double* __restrict__ alpha, double* __restrict__ Wo,
-                                                           double* __restrict__ Vo) {
+                                                           double* __restrict__ Vo, int rt_in_smem) {
+  extern __shared__ __align__(16) double rts[];      // [MM][N] when rt_in_smem
   const int c = blockIdx.y;
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const double* Rg = Rt + (long)c * RM * N;
+  if (rt_in_smem) {
+    for (int idx = threadIdx.x; idx < MM * N; idx += 256) rts[idx] = Rg[idx];     // rows k < MM of the [RM][N] table are contiguous
+    __syncthreads();
+  }
   if (n >= N) return;
+  const double* Rc = rt_in_smem ? rts : Rg;
   const double* zr = A + (long)c * strideA + (long)n * ld;
   const double* kr = Kx + ((long)c * N + n) * N;
   const double* cr = CK + ((long)c * N + n) * N;
-  const double* Rc = Rt + (long)c * RM * N;
   const double* al = alpha + (long)c * N;
   const double* yc = y + (long)c * N;
-  double w[RM], v[RM], a = 0.0;
+  double w[MM], v[MM], a = 0.0;
 #pragma unroll
-  for (int k = 0; k < RM; ++k) w[k] = v[k] = 0.0;
+  for (int k = 0; k < MM; ++k) w[k] = v[k] = 0.0;
   // the row is streamed once from HBM by this warp alone: four 32-wide slices are loaded before any arithmetic so that
   // enough bytes are in flight (one slice per iteration ran at 1 TB/s)
   for (int j0 = 0; j0 < N; j0 += 128) {
@@ -118,12 +147,11 @@ __global__ void __launch_bounds__(256) had_contract_kernel(const double* __restr
       if (j >= N) continue;
       const double wk = z[u] * zk[u], wc = z[u] * zc[u];
 #pragma unroll
-      for (int k = 0; k < RM; ++k)
-        if (k < M) {
-          const double r = Rc[(long)k * N + j];
-          w[k] += wk * r;
-          v[k] += wc * r;
-        }
+      for (int k = 0; k < MM; ++k) {
+        const double r = Rc[(long)k * N + j];
+        w[k] += wk * r;
+        v[k] += wc * r;
+      }
     }
   }
   if (PASS == 0) {
@@ -131,13 +159,17 @@ __global__ void __launch_bounds__(256) had_contract_kernel(const double* __restr
     if (lane == 0) alpha[(long)c * N + n] = a;
   }
 #pragma unroll
-  for (int k = 0; k < RM; ++k)
-    if (k < M) {
-      const double ws = warp_sum(w[k]), vs = warp_sum(v[k]);
-      if (lane == 0) {
-        Wo[((long)c * N + n) * RM + k] = ws;
-        Vo[((long)c * N + n) * RM + k] = vs;
-      }
+  for (int k = 0; k < MM; ++k) {
+    const double ws = warp_sum(w[k]), vs = warp_sum(v[k]);
+    if (lane == 0) {
+      Wo[((long)c * N + n) * RM + k] = ws;
+      Vo[((long)c * N + n) * RM + k] = vs;
+    }
+  }
+  if (lane == 0)
+    for (int k = MM; k < RM; ++k) {      // the finish kernel reads all RM slots
+      Wo[((long)c * N + n) * RM + k] = 0.0;
+      Vo[((long)c * N + n) * RM + k] = 0.0;
     }
 }
 
@@ -279,8 +311,10 @@ int had_forward(int variant, int cs, int N, int M, const double* x, const int* i
   had_prep_kernel<<<cs, 256, 0, st>>>(variant, pars, P, N, M, indx, h.mu0, h.mu1, w.ell, w.sig, w.s2, w.Lst, w.Ua, w.R0, w.R1);
   NMGP_LAUNCH_CHECK();
   NMGP_TRY(launch_kx(x, w.ell, w.sig, cs, N, w.Kx, w.CK, st, launches));
-  dim3 gb((b.nP + 127) / 128, b.nP, cs);
-  had_build_kernel<<<gb, 128, 0, st>>>(w.Kx, w.Lst, w.Ua, w.s2, N, M, b.A, b.strideA(), b.nP);
+  dim3 gb((b.nP + 127) / 128, (b.nP + HB_ROWS - 1) / HB_ROWS, cs);
+#define NMGP_HB_CASE(MM) case MM: had_build_kernel<MM><<<gb, 128, 0, st>>>(w.Kx, w.Lst, w.Ua, w.s2, N, b.A, b.strideA(), b.nP); break;
+  switch (M) { NMGP_FOR_EACH_M(NMGP_HB_CASE) default: set_last_error("M out of range"); return -1; }
+#undef NMGP_HB_CASE
   NMGP_LAUNCH_CHECK();
   return 0;
 }
@@ -290,12 +324,27 @@ int had_backward(int variant, int cs, int N, int M, const double* y, const int* 
                  double* vals, double* grad, int* info, cudaStream_t st, long* launches) {
   if (cs <= 0) return 0;
   dim3 gc((N + 7) / 8, cs);
-  had_contract_kernel<0><<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, y, w.Kx, w.CK, w.Ua, w.alpha, w.Wout, w.Vout);
-  NMGP_LAUNCH_CHECK();
-  if (grad != nullptr) {
-    had_contract_kernel<1><<<gc, 256, 0, st>>>(b.A, b.strideA(), b.nP, N, M, y, w.Kx, w.CK, w.Ua, w.alpha, w.Sa, w.Ca);
-    NMGP_LAUNCH_CHECK();
-  }
+  // the factor table in shared memory when it fits beside a useful number of CTAs per SM (M N doubles <= 96 KB)
+  const size_t rt_bytes = (size_t)M * N * sizeof(double);
+  const int in_smem = rt_bytes <= 96u * 1024u ? 1 : 0;
+  const size_t smem = in_smem ? rt_bytes : 0;
+#define NMGP_HC_CASE(MM)                                                                                                      \
+  case MM:                                                                                                                    \
+    if (smem > 48u * 1024u) {                                                                                                 \
+      NMGP_SMEM_ATTR_PER_DEVICE((had_contract_kernel<0, MM>), smem);                                                          \
+      NMGP_SMEM_ATTR_PER_DEVICE((had_contract_kernel<1, MM>), smem);                                                          \
+    }                                                                                                                         \
+    had_contract_kernel<0, MM><<<gc, 256, smem, st>>>(b.A, b.strideA(), b.nP, N, y, w.Kx, w.CK, w.Ua, w.alpha, w.Wout, w.Vout, \
+                                                      in_smem);                                                               \
+    NMGP_LAUNCH_CHECK();                                                                                                      \
+    if (grad != nullptr) {                                                                                                    \
+      had_contract_kernel<1, MM><<<gc, 256, smem, st>>>(b.A, b.strideA(), b.nP, N, y, w.Kx, w.CK, w.Ua, w.alpha, w.Sa, w.Ca,   \
+                                                        in_smem);                                                             \
+      NMGP_LAUNCH_CHECK();                                                                                                    \
+    }                                                                                                                         \
+    break;
+  switch (M) { NMGP_FOR_EACH_M(NMGP_HC_CASE) default: set_last_error("M out of range"); return -1; }
+#undef NMGP_HC_CASE
   had_finish_kernel<<<cs, 256, 0, st>>>(variant, N, M, P, pars, y, indx, h, b.A, b.strideA(), b.nP, b.logdet, b.info, w.alpha,
                                         w.s2, w.Lst, w.Wout, w.Vout, w.Sa, w.Ca, w.Z0, w.Z1, w.G0, w.G1, hld0, hld1, vals, grad,
                                         info);

@@ -8,6 +8,7 @@
 #include "jacobi.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace nmgp {
 
@@ -905,7 +906,6 @@ int padded_M(int M) {
   return -1;
 }
 
-#define NMGP_FOR_EACH_M(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
 #define NMGP_LAUNCH_CHECK()                 \
   do {                                      \
@@ -958,6 +958,8 @@ int launch_prior_solve(const double* Lp, const double* rhs, double* out, int cs,
   const int nvc32 = (nv + 31) / 32;
   // warp-per-problem kernel only when there are enough problems to fill the GPU (>= one warp per SM sub-partition); for
   // a handful of subjects one warp's serial N^2/2 FMAs lose to the blocked path below (measured: N=500 4.9 vs 1.4 ms)
+  // (also for long series: at N = 600, 3000 subjects, 21 right-hand sides the blocked path below is slower still -- 31.5 vs
+  // 24.1 ms for the four solves, profiles/r02_hadamard.txt; both are far from the 17 GB they read)
   if ((long)cs * nvc32 >= 592) {
     const int grid = (int)(((long)cs * nvc32 + PWB - 1) / PWB);
     if (trans) prior_solve_warp_kernel<1><<<grid, 32 * PWB, 0, st>>>(Lp, rhs, out, cs, N, nv, nvc32);

@@ -57,6 +57,8 @@ int launch_sym_eig(const double* B, int M, double* lam, double* V, cudaStream_t 
 int kron_eig_solve(const double* B, int M, const double* K, int N, double sigma2, double* inv_out, const double* r,
                    double* out2, int* info_out, cudaStream_t st);
 
+#define NMGP_FOR_EACH_M(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
 int padded_M(int M);  // template bucket for the nonseparable contraction (>= M)
 
 // ---- elementwise covariance kernels (unit entry points + plan creation)
