@@ -454,9 +454,10 @@ def ours(a):
     # same workload, reported only for the configuration it was taken on (C4, one GPU, 3 chunks x 56 launches)
     traffic, traffic_source = None, "not measured in this run (ncu only); see profiles/"
     if a.workload == "C4" and world == 1 and a.subjects == 10000:
-        traffic = 353e9 / 168.0
-        traffic_source = ("static: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of round 1's engine on this workload "
-                          "(profiles/r01_launches_final.txt: 353 GB per sweep over 168 engine launches); not re-measured per run")
+        traffic = 312e9 / 177.0
+        traffic_source = ("static: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of this engine on this workload "
+                          "(profiles/r02_launches_final.txt: 312 GB per sweep over the 177 panel_gemm / inverse / diag64 launches of "
+                          "3 chunks; round 1: 353 GB; compulsory 43 GB); not re-measured per run")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_source,
                 "kernel": "panel_gemm_kernel<mode> / inverse_kernel<mode> (left-looking potrf + guarded Takahashi / W^T W inverse: 64x64 "
