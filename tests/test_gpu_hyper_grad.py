@@ -13,6 +13,22 @@ def _scaled_err(got, want):
     return float((np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * np.abs(want).max())).max())
 
 
+# Per-slot bounds against the reference's autograd, relative to the largest entry of the slot over the fixture's subjects
+# (measured on B200, tools/report_hyper_parity.py; bound = ~4 x the worst fixture).  alpha / beta / mu of the GP priors go
+# through the ill-conditioned prior covariance (cond 1e8..2e10: the floor of tests/test_prior_conditioning_floor.py), the
+# scalar-prior slots do not; the reference's own `b` slot comes from a central difference (make_golden_hyper.py).
+def _slot_tol(name):
+    if name.startswith("alpha_"):
+        return 1e-5          # measured <= 2.8e-6
+    if name.startswith("beta_"):
+        return 6e-7          # measured <= 1.4e-7
+    if name in ("mu_tilde_l", "mu_tilde_sigma", "mu_L"):
+        return 3e-7          # measured <= 5.6e-8
+    if name == "b":
+        return 5e-7          # measured <= 1.1e-7 (finite-difference reference)
+    return 1e-12             # a, c, sigma_tilde_l: measured <= 4e-14
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_hyper_grad_matches_reference_autograd(name, cuda_device):
     import torch
@@ -24,11 +40,18 @@ def test_hyper_grad_matches_reference_autograd(name, cuda_device):
     hg = plan.hyper_grad(pars).cpu().numpy()
     hg2 = plan.hyper_grad(pars).cpu().numpy()          # second call: cached traces
     assert np.array_equal(hg, hg2)
+    names = plan.hyper_names()
+    ref = d["hgrad"]
+    for k, nm in enumerate(names):
+        scale = max(float(np.abs(ref[:, k]).max()), 1e-300)
+        if d["model"] == "stationary" and nm in ("mu_tilde_l", "sigma_tilde_l"):
+            tol = 1e-12      # scalar Normal prior on tilde_l: no covariance involved
+        else:
+            tol = _slot_tol(nm)
+        assert float(np.abs(hg[:, k] - ref[:, k]).max()) / scale < tol, (name, nm, hg[:, k], ref[:, k])
     for s in range(d["pars"].shape[0]):
         orc = O.hyper_grad(d["model"], d["pars"][s], d["x"][s], d["M"], **d["hyper"])
-        # the prior covariances have condition numbers up to 1e10: every route carries ~1e-6 relative noise in the
-        # alpha / beta slots; the mu / a / b / c / sigma slots are tight
-        assert _scaled_err(hg[s], d["hgrad"][s]) < 2e-5, (name, s, hg[s], d["hgrad"][s])
+        # the oracle's dense closed form carries the same conditioning noise in the alpha / beta slots
         assert _scaled_err(hg[s], orc) < 2e-5, (name, s, hg[s], orc)
     # evaluation after the hyper-gradient call is unaffected (shared scratch)
     vals, grad, info = plan.value_and_grad(pars)
