@@ -164,7 +164,7 @@ int alloc_workspace(nmgp_plan* pl) {
   BlockBatch& b = pl->bb;
   b.n = pl->n; b.nP = pl->nP; b.Kt = pl->Kt; b.NB = kNB; b.batch = (int)(cs * nm);
   NMGP_TRY(dev_alloc(pl, &b.A, cs * nm * (size_t)pl->nP * pl->nP));
-  b.A2 = nullptr;   // only the W^T W inverses need it: ensure_second_buffer() (C4's Takahashi sweep never does: -10.9 GB)
+  b.A2 = nullptr;   // allocated by the first evaluation that takes an inverse path with a W^T W stage: ensure_second_buffer()
   NMGP_TRY(dev_alloc(pl, &b.Dinv, cs * nm * (size_t)pl->Kt * 2 * kNB * kNB));
   NMGP_TRY(dev_alloc(pl, &b.Pbuf, cs * nm * (size_t)pl->Kt * kNB * kNB));
   // the left-looking engine multiplies padding / not-yet-written upper tiles by exact zeros: they must be finite
@@ -567,7 +567,7 @@ static int run_potrf(nmgp_plan* pl, const BlockBatch& b, cudaStream_t st, long* 
 constexpr int kTakahashiMinBatch = 1024;
 // The W^T W inverses keep W^T in a second matrix buffer.  It is allocated when an evaluation first takes such a path (never
 // inside a graph capture: the first evaluation of every variant launches directly) and stays with the plan.
-static int ensure_second_buffer(nmgp_plan* pl, BlockBatch& b) {
+static int ensure_second_buffer(nmgp_plan* pl, BlockBatch& b, cudaStream_t st) {
   if (!pl->bb.A2) {
     const size_t bytes = (size_t)pl->bb.batch * pl->bb.strideA() * sizeof(double);
     if (cudaMalloc(&pl->A2_own, bytes) != cudaSuccess) {
@@ -576,7 +576,9 @@ static int ensure_second_buffer(nmgp_plan* pl, BlockBatch& b) {
       set_last_error("inverse: cudaMalloc of " + std::to_string(bytes) + " bytes for the second matrix buffer failed");
       return NMGP_ENOMEM;
     }
-    NMGP_CUDA_TRY(cudaMemset(pl->A2_own, 0, bytes));   // multiplied by exact zeros before it is written: must be finite
+    // multiplied by exact zeros before it is written: must be finite.  Stream-ordered on the evaluation's own stream (a plain
+    // cudaMemset runs on the legacy stream, which a non-blocking caller stream does not wait for).
+    NMGP_CUDA_TRY(cudaMemsetAsync(pl->A2_own, 0, bytes, st));
     pl->dev_bytes += bytes;
     pl->bb.A2 = pl->A2_own;
     engine_maps_destroy(pl->maps);
@@ -596,21 +598,21 @@ static int run_potri(nmgp_plan* pl, BlockBatch& b, cudaStream_t st, long* launch
     case 1: return engine_potri(b, st, launches);
     case 2:
       if (!ll) return engine_potri(b, st, launches);
-      NMGP_TRY(ensure_second_buffer(pl, b));
+      NMGP_TRY(ensure_second_buffer(pl, b, st));
       if (pl->stable_inverse || b.Kt > kTakahashiMaxBlocks) return engine_potri_ll_stable(b, st, launches);
       return engine_potri_ll_guarded(b, st, launches);
     case 4:
       if (!has_p) return engine_potri(b, st, launches);
-      NMGP_TRY(ensure_second_buffer(pl, b));
+      NMGP_TRY(ensure_second_buffer(pl, b, st));
       return engine_potri_ll_recursive(b, st, launches);
     default: break;
   }
   if (ll && b.Kt <= kTakahashiMaxBlocks && b.batch >= kTakahashiMinBatch) {
-    NMGP_TRY(ensure_second_buffer(pl, b));
+    NMGP_TRY(ensure_second_buffer(pl, b, st));
     return engine_potri_ll_guarded(b, st, launches);
   }
   if (has_p && b.Kt > 1) {
-    NMGP_TRY(ensure_second_buffer(pl, b));
+    NMGP_TRY(ensure_second_buffer(pl, b, st));
     return engine_potri_ll_recursive(b, st, launches);
   }
   return engine_potri(b, st, launches);
