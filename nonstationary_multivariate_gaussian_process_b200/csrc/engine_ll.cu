@@ -615,9 +615,15 @@ int make_map(CUtensorMap* m, const double* base, long cols, long rows, long coun
   cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)stride * 8};
   cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)NB, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  // L2 promotion: a box row is ONE 128-byte line of a matrix row and the next k-chunk of the ring is the neighbouring line of
+  // the same rows, so promoting the fetch to 256 bytes could bring it into L2 with the same DRAM burst -- measured: no
+  // difference (110.05 / 110.28 / 110.04 ms per C4 sweep for 128 / 256 / none, profiles/r02_engine_ab.txt).  NMGP_TMA_L2: A/B.
+  static const int l2 = getenv("NMGP_TMA_L2") ? atoi(getenv("NMGP_TMA_L2")) : 128;
+  const CUtensorMapL2promotion promo = l2 == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : (l2 == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : (l2 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
     return -2;
