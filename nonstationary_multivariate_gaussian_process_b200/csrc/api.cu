@@ -175,6 +175,8 @@ int alloc_workspace(nmgp_plan* pl) {
   NMGP_TRY(dev_alloc(pl, &b.info, cs * nm));
   NMGP_TRY(dev_alloc(pl, &b.pivmin, cs * nm));
   NMGP_TRY(dev_alloc(pl, &b.pivmax, cs * nm));
+  NMGP_TRY(dev_alloc(pl, &b.sched, 2));
+  NMGP_CUDA_TRY(cudaMemsetAsync(b.sched, 0, 2 * sizeof(int), 0));
   NMGP_TRY(engine_maps_create(b, &pl->maps));
   b.maps = pl->maps;
   Scratch& w = pl->w;

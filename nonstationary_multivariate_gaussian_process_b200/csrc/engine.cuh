@@ -24,6 +24,7 @@ struct BlockBatch {
   // is the conditioning indicator the guarded inverse uses to route a matrix (engine_potri_ll_guarded).
   double* pivmin = nullptr;
   double* pivmax = nullptr;
+  int* sched = nullptr;      // [2] zero-initialised scheduler word of the left-looking engine's dynamic tile queue; optional
   int n = 0;                 // logical dimension
   int nP = 0;                // padded dimension (multiple of NB)
   int Kt = 0;                // blocks per side

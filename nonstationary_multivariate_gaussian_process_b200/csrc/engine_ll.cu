@@ -71,6 +71,7 @@ struct LLArgs {
   double guard_thr;
   const double* pivmin;
   const double* pivmax;
+  int* sched;   // [2] {next item, CTAs out of work}, zero between launches (the kernel resets them); nullptr = static grid
 };
 
 __device__ __forceinline__ bool guard_skips(const LLArgs& g, int mat) {
@@ -122,29 +123,22 @@ __device__ __forceinline__ void mma_chunk(const unsigned char* __restrict__ SA, 
 }
 
 // ---- panel_gemm_kernel
-// Work items of one launch: (matrix, tile).  Default (measured best, profiles/r02_engine_ab.txt): grid (gx, batch), CTA
-// (bx, by) takes tiles bx, bx + gx, ... of matrix by and the hardware hands CTAs to SMs as slots free up (a slow CTA delays
-// only its own successor); ~32 waves of CTAs.  Inside a CTA the four warps only meet through the ring: `full[slot]` is
-// completed by the TMA transaction, `empty[slot]` by one arrival per warp, so a warp in its epilogue does not hold up the
-// other three (no CTA-wide barrier in the loop); the producer is thread 0, which issues chunk q + STAGES - 1 once `empty`
-// says that everyone is done with chunk q - 1.
-// Compile-time alternatives kept for A/B timing (tools/build_variant.py), all slower or equal on B200:
-//   NMGP_LL_FLAT=1           persistent grid of exactly the resident CTAs, items dealt round-robin: no partial last wave,
-//                            but static assignment loses to the hardware's dynamic one (+3 % time)
-//   NMGP_LL_PRODUCER_WARP=1  a fifth warp that only issues TMA (3 CTAs/SM at 128 registers, 4 CTAs/SM only at 96 with
-//                            spills): +1.5 % / +20 % time
-//   NMGP_LL_STAGES=4         one more ring stage (3 CTAs/SM): equal
-#ifndef NMGP_LL_PRODUCER_WARP
-#define NMGP_LL_PRODUCER_WARP 0
-#endif
-#ifndef NMGP_LL_FLAT
-#define NMGP_LL_FLAT 0
-#endif
-#ifndef NMGP_LL_CTAS
-#define NMGP_LL_CTAS (NMGP_LL_PRODUCER_WARP ? 3 : 4)
-#endif
-constexpr int PG_THREADS = NMGP_LL_PRODUCER_WARP ? THREADS + 32 : THREADS;
-constexpr int PG_CTAS = NMGP_LL_CTAS;
+// Work items of one launch: (matrix, tile), w = matrix * ntiles + tile, the same k-chunk sequence for every item.
+//  * Scheduling.  With a scheduler word (LLArgs::sched, plans) the grid is the set of co-resident CTAs and every CTA FETCHES
+//    its next item with an atomic counter: dynamic balance like the hardware's CTA scheduler, but the TMA ring of a CTA never
+//    drains between tiles and the CTA start-up (guard loads, barrier init, first TMA round trip: ~10 % of a one-tile CTA in the
+//    source-level profile) is paid once per launch instead of once per tile.  Items of one matrix are fetched by neighbouring
+//    CTAs at the same time, so the operand they share comes from HBM once.  The last CTA to run dry resets the counters.
+//    Without a scheduler word (unit entry points): grid (gx, batch), CTA (bx, by) takes tiles bx, bx + gx, ... of matrix by.
+//  * Inside a CTA the four warps only meet through the ring: `full[slot]` is completed by the TMA transaction, `empty[slot]`
+//    by one arrival per warp, so a warp in its epilogue does not hold up the other three (no CTA-wide barrier in the loop).
+//    The producer is thread 0: it issues chunk q + STAGES - 1 once `empty` says everyone is done with chunk q - 1, and
+//    publishes the item of every tile it starts in a 4-entry shared ring that the consumers read after the tile's first
+//    `full` wait; a negative entry ends the CTA.
+// Measured alternatives (profiles/r02_engine_ab.txt; the code is in commit 92ea92f): STATIC round-robin deal over a persistent
+// grid +3 % time, dedicated producer warp +1.5 % (3 CTAs/SM) / +20 % (4 CTAs/SM at 96 registers), 4 ring stages equal.
+constexpr int PG_THREADS = THREADS;
+constexpr int PG_CTAS = 4;
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -156,15 +150,15 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
                                                                          const __grid_constant__ CUtensorMap mapP,
                                                                          LLArgs g) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ int item_ring[4];
   // 1024-byte alignment by OFFSET arithmetic on the shared pointer (an integer round trip would make every operand fetch a
   // generic LD instead of LDS: the compiler loses the address space)
   unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + STAGES * 2 * OPB);
   unsigned long long* empty = full + STAGES;
 
-#if !NMGP_LL_FLAT
-  if (g.guard != 0 && guard_skips(g, blockIdx.y)) return;   // gridDim.y == batch (launch_ll): one matrix per CTA; uniform
-#endif
+  const bool dynamic = g.sched != nullptr;
+  if (!dynamic && g.guard != 0 && guard_skips(g, blockIdx.y)) return;   // static grid: gridDim.y == batch, one matrix per CTA
   const int s = g.step;
   const int last = g.Kt - 1;
   const int vlast = g.n8 - last * NB;  // valid rows/cols of the last block (multiple of 8)
@@ -180,30 +174,11 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
   const bool ragged_k = (MODE == TK_COL) || (MODE == TK_DIAG && nkb > 1);
   const int nchunks = (nkb - 1) * CPB + ((ragged_k ? vlast : NB) + KC - 1) / KC;
   const int cols_valid = (j == last) ? vlast : NB;
-
-  // items of this CTA
-#if NMGP_LL_FLAT
   const long nitems = (long)g.batch * g.ntiles;
-  const int G = gridDim.x;
-  const int nmy = ((long)blockIdx.x < nitems) ? (int)((nitems - blockIdx.x + G - 1) / G) : 0;
-#else
-  // grid (gx, gy): CTA (bx, by) takes tiles bx, bx + gx, ... of matrices by, by + gy, ...
-  const int per = ((int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int nmat_my = ((int)blockIdx.y < g.batch) ? (g.batch - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
-  const int nmy = per * nmat_my;
-#endif
-  const int total = nmy * nchunks;
-  // (matrix, block row) of the tt-th item of this CTA
-  auto item = [&](int tt, int& mat, int& i) {
-#if NMGP_LL_FLAT
-    const long w = (long)blockIdx.x + (long)tt * G;
+  // (matrix, block row) of item w
+  auto decode = [&](long w, int& mat, int& i) {
     mat = (int)(w / g.ntiles);
     const int t = (int)(w - (long)mat * g.ntiles);
-#else
-    const int mi = tt / per, ti = tt - mi * per;
-    mat = (int)blockIdx.y + mi * (int)gridDim.y;
-    const int t = (int)blockIdx.x + ti * (int)gridDim.x;
-#endif
     if (MODE == LL_UPDATE) i = s + t;
     else if (MODE == TK_DIAG) i = s;
     else i = s + 1 + t;
@@ -215,15 +190,55 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
   }
   __syncthreads();
 
-  // ---- producer: chunk p of this CTA's sequence -> ring slot p % STAGES
-  int p_tt = 0, p_qq = 0, p_mat = 0, p_i = 0;
-  if (nmy > 0) item(0, p_mat, p_i);
-  auto issue = [&](int p) {
+  // ---- producer (thread 0): chunk p of this CTA's sequence -> ring slot p % STAGES
+  int p = 0, p_qq = 0, p_mat = 0, p_i = 0, p_ts = 0, p_static = 0;
+  bool p_done = false;
+  // static grid: tiles bx, bx + gx, ... of matrices by, by + gy, ...
+  const int per = (!dynamic && (int)blockIdx.x < g.ntiles) ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nmat_my = (!dynamic && (int)blockIdx.y < g.batch) ? (g.batch - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y : 0;
+  auto next_item = [&]() -> long {       // next item of this CTA, or -1
+    for (;;) {
+      long w;
+      if (dynamic) {
+        w = (long)atomicAdd(g.sched, 1);
+        if (w >= nitems) return -1;
+      } else {
+        if (p_static >= per * nmat_my) return -1;
+        const int mi = p_static / per, ti = p_static - mi * per;
+        ++p_static;
+        w = (long)((int)blockIdx.y + mi * (int)gridDim.y) * g.ntiles + (int)blockIdx.x + ti * (int)gridDim.x;
+      }
+      decode(w, p_mat, p_i);
+      if (!dynamic || g.guard == 0 || !guard_skips(g, p_mat)) return w;   // the guarded inverse: items of the other path are skipped
+    }
+  };
+  auto issue_next = [&]() {
+    if (p_done) return;
     const int slot = p % STAGES;
     if (p >= STAGES) mbar_wait(&empty[slot], ((p / STAGES) - 1) & 1);   // all four warps are done with its previous contents
+    if (p_qq == 0) {
+      const long w = next_item();
+      item_ring[p_ts & 3] = (int)w;
+      ++p_ts;
+      if (w < 0) {                       // out of work: wake the consumers with an empty phase, retire the CTA
+        p_done = true;
+        mbar_arrive(&full[slot]);
+        if (dynamic) {
+          __threadfence();
+          const int ncta = (int)(gridDim.x * gridDim.y);
+          if (atomicAdd(g.sched + 1, 1) == ncta - 1) {   // every CTA has fetched its last item: reset for the next launch
+            g.sched[0] = 0;
+            g.sched[1] = 0;
+            __threadfence();
+          }
+        }
+        return;
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const int qq = p_qq, i = p_i, mat = p_mat;
-    if (++p_qq == nchunks) { p_qq = 0; if (++p_tt < nmy) item(p_tt, p_mat, p_i); }
+    if (++p_qq == nchunks) p_qq = 0;
+    ++p;
     const int kb = qq / CPB, kcol = (qq % CPB) * KC;
     const int dslot = (mat * g.Kt + s) * 2;    // W_ss (slot + 0) and W_ss^T (slot + 1) in the Dinv tensor
     const int pslot = mat * g.Kt;              // P(c)^T tiles of this matrix in the Pbuf tensor
@@ -255,44 +270,20 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
       }
     }
   };
-
-#if NMGP_LL_PRODUCER_WARP
-  if (threadIdx.x >= THREADS) {
-    if (threadIdx.x == THREADS) {
-#pragma unroll 1
-      for (int p = 0; p < total; ++p) issue(p);
-    }
-    return;
-  }
-#else
   if (threadIdx.x == 0) {
 #pragma unroll 1
-    for (int p = 0; p < STAGES - 1 && p < total; ++p) issue(p);
+    for (int k = 0; k < STAGES - 1; ++k) issue_next();
   }
-#endif
 
-  // ---- consumers.  Quarter of the tile owned by this warp: the quarters do unequal work in the triangular modes below
-  // and every warp is pinned to one SM sub-partition (one DMMA pipe each), so the assignment is rotated per CTA.
-  const int warp = ((threadIdx.x >> 5) + blockIdx.x + blockIdx.y) & 3, lane = threadIdx.x & 31;
-  const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
+  // ---- consumers.  The quarter of the tile owned by a warp is rotated per ITEM: the quarters do unequal work in the
+  // triangular modes below and every warp is pinned to one SM sub-partition (one DMMA pipe each).
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = lane >> 2, c = 2 * (lane & 3);
   const int lr = lane >> 2, lk = lane & 3;
-  const bool upper_quarter = (m0 == 0 && n0 == NB / 2);
   // per-lane swizzled byte offsets of the four k-steps: 16-byte slot (s + 4*(lk>>1)) ^ (row & 7), half lk & 1
   int off[4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) off[ks] = (((ks + 4 * (lk >> 1)) ^ lr) << 4) + (lk & 1) * 8;
-  // k-chunks that only multiply structural zeros of the triangular W = L_kk^-1 (W[a][b] = 0 for b > a):
-  //   LL_SOLVE  C[m][n] = sum_k A[m][k] W[n][k]   -> columns n < 32 need k < 32 only
-  //   TK_PANEL  C[m][n] = sum_k L[m][k] W[k][n]   -> columns n >= 32 need k >= 32 only
-  //   TK_DIAG   (first k-block) sum_k W[k][m] W[k][n] -> any quarter touching rows/cols >= 32 needs k >= 32 only
-  auto zero_chunk = [&](int qq) -> bool {
-    constexpr int HALF = (NB / 2) / KC;   // chunks per half block
-    if (MODE == LL_SOLVE) return n0 == 0 && qq >= HALF;
-    if (MODE == TK_PANEL) return n0 == NB / 2 && qq < HALF;
-    if (MODE == TK_DIAG) return (m0 == NB / 2 || n0 == NB / 2) && qq < HALF;
-    return false;
-  };
 
   double acc[4][4][2];
 #pragma unroll
@@ -300,8 +291,44 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  // ---- epilogue of tile (i, j) of matrix `mat`: registers only
-  auto epilogue = [&](int mat, int i, bool active) {
+  int q = 0;                      // chunks consumed by this CTA so far
+  for (int ts = 0;; ++ts) {       // tiles
+    int mat = 0, i = 0, m0 = 0, n0 = 0;
+    bool active = false;
+    for (int qq = 0; qq < nchunks; ++qq, ++q) {
+      if (threadIdx.x == 0) issue_next();          // chunk q + STAGES - 1
+      const int slot = q % STAGES;
+      mbar_wait(&full[slot], (q / STAGES) & 1);
+      if (qq == 0) {                               // first chunk of a tile: which item is it?
+        const int w = item_ring[ts & 3];
+        if (w < 0) return;                         // out of work (nothing is in flight: the producer stopped here too)
+        decode(w, mat, i);
+        const int warp = (wid + w) & 3;
+        m0 = (warp >> 1) * 32;
+        n0 = (warp & 1) * 32;
+        const int rows_valid = (i == last) ? vlast : NB;
+        // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
+        // of A(k,k); Z(j,j) is symmetric and mirrored in the epilogue)
+        const bool tri_skip = (m0 == 0 && n0 == NB / 2) && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
+        active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
+      }
+      // k-chunks that only multiply structural zeros of the triangular W = L_kk^-1 (W[a][b] = 0 for b > a):
+      //   LL_SOLVE  C[m][n] = sum_k A[m][k] W[n][k]   -> columns n < 32 need k < 32 only
+      //   TK_PANEL  C[m][n] = sum_k L[m][k] W[k][n]   -> columns n >= 32 need k >= 32 only
+      //   TK_DIAG   (first k-block) sum_k W[k][m] W[k][n] -> any quarter touching rows/cols >= 32 needs k >= 32 only
+      constexpr int HALF = (NB / 2) / KC;   // chunks per half block
+      bool zero = false;
+      if (MODE == LL_SOLVE) zero = n0 == 0 && qq >= HALF;
+      else if (MODE == TK_PANEL) zero = n0 == NB / 2 && qq < HALF;
+      else if (MODE == TK_DIAG) zero = (m0 == NB / 2 || n0 == NB / 2) && qq < HALF;
+      if (active && !zero) {
+        const unsigned char* SA = ring + slot * 2 * OPB;
+        mma_chunk(SA + (m0 + lr) * 128, SA + OPB + (n0 + lr) * 128, off, acc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);   // this warp's reads of the slot are complete
+    }
+    // ---- epilogue of tile (i, j) of matrix `mat`: registers only
     if (active) {
       double* Am = g.A + (long)mat * g.strideA;
       if (MODE == TK_PANEL) {   // P(i)^T = -(L(i,s) W)^T
@@ -324,17 +351,17 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const int row = m0 + 8 * a + r, col = n0 + 8 * b + c;
-            double2* p = reinterpret_cast<double2*>(C + (long)row * g.ld + col);
+            double2* pp = reinterpret_cast<double2*>(C + (long)row * g.ld + col);
             double2 v;
             if (MODE == LL_UPDATE) {
-              v = *p;
+              v = *pp;
               v.x -= acc[a][b][0];
               v.y -= acc[a][b][1];
             } else {
               v.x = acc[a][b][0];
               v.y = acc[a][b][1];
             }
-            *p = v;
+            *pp = v;
             if (mirror) {
               U[(long)col * g.ld + row] = v.x;
               U[(long)(col + 1) * g.ld + row] = v.y;
@@ -346,31 +373,6 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  };
-
-  int tt = 0, qq = 0, mat = 0, i = 0;
-  if (nmy > 0) item(0, mat, i);
-  for (int q = 0; q < total; ++q) {
-    const int slot = q % STAGES;
-#if !NMGP_LL_PRODUCER_WARP
-    if (threadIdx.x == 0 && q + STAGES - 1 < total) issue(q + STAGES - 1);
-#endif
-    const int rows_valid = (i == last) ? vlast : NB;
-    // structurally unnecessary quarter: strictly-upper 32 x 32 of a diagonal tile (potrf reads only the lower triangle
-    // of A(k,k); Z(j,j) is symmetric and mirrored in the epilogue)
-    const bool tri_skip = upper_quarter && i == j && (MODE == LL_UPDATE || MODE == TK_DIAG);
-    const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !tri_skip;
-    mbar_wait(&full[slot], (q / STAGES) & 1);
-    if (active && !zero_chunk(qq)) {
-      const unsigned char* SA = ring + slot * 2 * OPB;
-      mma_chunk(SA + (m0 + lr) * 128, SA + OPB + (n0 + lr) * 128, off, acc);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);   // this warp's reads of the slot are complete
-    if (++qq < nchunks) continue;
-    epilogue(mat, i, active);
-    qq = 0;
-    if (++tt < nmy) item(tt, mat, i);
   }
 }
 
@@ -671,7 +673,7 @@ int resident_ctas(K kernel, int threads, size_t smem, std::atomic<int>* cache) {
   return v;
 }
 
-// one persistent CTA per resident slot, work items dealt round-robin (see panel_gemm_kernel)
+// dynamic scheduling (scheduler word present): one persistent CTA per resident slot; otherwise the static 2-D grid
 template <int MODE>
 int launch_ll(const MapSet& ms, const LLArgs& g0, int ntiles, cudaStream_t st, long* launches) {
   if (ntiles <= 0 || g0.batch <= 0) return 0;
@@ -679,23 +681,22 @@ int launch_ll(const MapSet& ms, const LLArgs& g0, int ntiles, cudaStream_t st, l
   static std::atomic<int> slots[kMaxDevices];
   LLArgs g = g0;
   g.ntiles = ntiles;
-#if NMGP_LL_FLAT
-  const long nitems = (long)g.batch * ntiles;
-  long grid = resident_ctas(panel_gemm_kernel<MODE>, PG_THREADS, LL_SMEM, slots);
-  if (grid > nitems) grid = nitems;
-  panel_gemm_kernel<MODE><<<(unsigned)grid, PG_THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
-#else
-  // tiles of one matrix are split over gx CTAs; enough CTAs for ~`waves` waves of the resident slots (hardware-dynamic
-  // assignment of CTAs to SMs: a slow CTA delays nothing but its own successor)
-  static const int waves = getenv("NMGP_LL_WAVES") ? atoi(getenv("NMGP_LL_WAVES")) : 32;   // A/B timing: 8 -> 32: -1.5 % time
-  const int gy = g.batch < 65535 ? g.batch : 65535;
-  if (g.guard != 0 && gy != g.batch) { set_last_error("guarded inverse: more than 65535 matrices in one batch"); return -1; }
-  int gx = (int)(((long)resident_ctas(panel_gemm_kernel<MODE>, PG_THREADS, LL_SMEM, slots) * waves + gy - 1) / gy);
-  if (gx > ntiles) gx = ntiles;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, gy);
-  panel_gemm_kernel<MODE><<<grid, PG_THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
-#endif
+  const long resident = resident_ctas(panel_gemm_kernel<MODE>, PG_THREADS, LL_SMEM, slots);
+  if (g.sched) {
+    const long nitems = (long)g.batch * ntiles;
+    const long grid = resident < nitems ? resident : nitems;
+    panel_gemm_kernel<MODE><<<(unsigned)grid, PG_THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
+  } else {
+    // tiles of one matrix are split over gx CTAs; ~`waves` waves of the resident slots (hardware-dynamic CTA assignment)
+    static const int waves = getenv("NMGP_LL_WAVES") ? atoi(getenv("NMGP_LL_WAVES")) : 32;   // A/B timing: 8 -> 32: -1.5 % time
+    const int gy = g.batch < 65535 ? g.batch : 65535;
+    if (g.guard != 0 && gy != g.batch) { set_last_error("guarded inverse: more than 65535 matrices in one batch"); return -1; }
+    int gx = (int)((resident * waves + gy - 1) / gy);
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, gy);
+    panel_gemm_kernel<MODE><<<grid, PG_THREADS, LL_SMEM, st>>>(ms.mA, ms.mD, ms.mP, g);
+  }
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -709,6 +710,8 @@ LLArgs make_ll(const BlockBatch& b) {
   g.n8 = (int)round_up(b.n, 8);
   g.ntiles = 0;
   g.guard = 0; g.guard_thr = 0.0; g.pivmin = b.pivmin; g.pivmax = b.pivmax;
+  static const bool no_dyn = getenv("NMGP_LL_STATIC") != nullptr;   // A/B timing: the static 2-D grid
+  g.sched = no_dyn ? nullptr : b.sched;
   return g;
 }
 
@@ -807,7 +810,7 @@ static double takahashi_guard_threshold(int Kt) {
 int engine_potri_ll_guarded(const BlockBatch& b, cudaStream_t st, long* launches) {
   if (b.batch <= 0) return 0;
   const double thr = takahashi_guard_threshold(b.Kt);
-  if (!(thr > 0.0) || !b.pivmin || !b.pivmax || NMGP_LL_FLAT) return engine_potri_ll(b, st, launches);
+  if (!(thr > 0.0) || !b.pivmin || !b.pivmax) return engine_potri_ll(b, st, launches);
   if (!b.Pbuf || !b.A2) { set_last_error("engine_potri_ll_guarded: no panel / second matrix buffer"); return -1; }
   MapRef mr;
   NMGP_TRY(mr.init(b));
