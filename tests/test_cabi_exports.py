@@ -93,3 +93,19 @@ def test_new_entry_points_validate_arguments_without_a_device(lib):
     assert lib.nmgp_hmc_drift(None, None, 1, 4, 0.1, None) == -1
     assert lib.nmgp_hmc_accept(None, None, None, None, None, None, None, None, None, None, None, 1, 4, None) == -1
     assert lib.nmgp_hmc_kick(None, None, None, 0, 0, 0.1, None) == -1          # P must be positive
+
+
+def test_round2_entry_points_validate_arguments_without_a_device(lib):
+    """The helper entries behind the kernels / kronecker_operation / distributions mirrors and the DMMA probe: bad
+    arguments give NMGP_EINVAL (-1) and a message before any CUDA call."""
+    assert lib.nmgp_pairwise_sqdist(None, 3, None, 0, None, None) == -1
+    assert b"nmgp_pairwise_sqdist" in lib.nmgp_last_error()
+    assert lib.nmgp_kron(None, 2, 2, None, 2, 2, None, None) == -1
+    assert lib.nmgp_kron_mv(None, 2, 2, None, 2, 2, None, None, None, None) == -1
+    assert lib.nmgp_gram(None, 4, 2, None, None) == -1
+    assert lib.nmgp_sym_eig(None, 3, None, None, None) == -1
+    assert lib.nmgp_kron_eig_solve(None, 2, None, 5, 0.1, None, None, None, None, None) == -1
+    tf = ctypes.c_double()
+    assert lib.nmgp_fp64_dmma_probe(-1.0, ctypes.byref(tf), None, None) == -1
+    assert lib.nmgp_fp64_dmma_probe(100.0, ctypes.byref(tf), None, None) == -1
+    assert lib.nmgp_fp64_dmma_probe(0.1, None, None, None) == -1
