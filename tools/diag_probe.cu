@@ -15,19 +15,19 @@ int main() {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0); engine_diag_step(b, 0, 0, nullptr, false); cudaEventRecord(e1); cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    long long st[32]; cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
+    long long st[64]; cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
     double ld; int info; cudaMemcpy(&ld, b.logdet, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&info, b.info, 4, cudaMemcpyDeviceToHost);
     printf("rep %d: event %.1f us | cycles: load %lld  chol %lld  storeL+logdet %lld  inverse %lld  sync %lld  total %lld | logdet %.6f info %d\n",
            rep, ms * 1e3, st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[5] - st[0], ld, info);
   }
   // the tensor-pipe kernel's phases (NMGP_DIAG_MMA unset or 1): lap counters 6 / 7 / 8 accumulate over the 8 tile columns
   {
-    long long z[32] = {0};
+    long long z[64] = {0};
     cudaMemcpyToSymbol(g_diag_prof, z, sizeof(z));
     cudaMemcpy(b.A, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     engine_diag_step(b, 0, 0, nullptr, false);
     cudaDeviceSynchronize();
-    long long st[32]; cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
+    long long st[64]; cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
     printf("mma kernel cycles: load %lld | lookahead+factor|trailing %lld  panel %lld  (unused %lld) | storeL %lld  - %lld  rows+stats %lld  end-barrier %lld | total %lld\n",
            st[1] - st[0], st[6], st[7], st[8], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[9] - st[5], st[9] - st[0]);
   }
@@ -44,11 +44,15 @@ int main() {
     cudaFuncSetAttribute(diag64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM_BYTES);
     diag64_mma_kernel<<<1, MMA_THREADS, MMA_SMEM_BYTES>>>(g);
     cudaDeviceSynchronize();
-    long long st[32]; cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
+    long long st[64]; cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
     printf("mma kernel, warm (8th matrix of one CTA): load %lld | lookahead+factor|trailing %lld  panel %lld  (unused %lld) | storeL %lld  - %lld  rows+stats %lld  end-barrier %lld | total %lld  (%s)\n",
            st[1] - st[0], st[6], st[7], st[8], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[9] - st[5], st[9] - st[0], cudaGetErrorString(cudaGetLastError()));
     printf("   factor warp at p = 3 (tile column 4): look-ahead tile %lld  load+pivots %lld  V %lld  stores %lld  barrier %lld\n", st[10] - st[15], st[11] - st[10], st[12] - st[11], st[13] - st[12], st[14] - st[13]);
-    printf("   rows (warp 0 = rows 7, 0): zero+diagonal tiles %lld  t=1 %lld  t=2..4 %lld  t=5..7 %lld | one stamp costs %lld\n", st[17] - st[22], st[18] - st[17], st[19] - st[18], st[20] - st[19], st[22] - st[21]);
+    printf("   per tile column p = -1..6: factor|trailing phase");
+    for (int i = 0; i < 8; ++i) printf(" %lld", st[32 + i]);
+    printf("   panel phase");
+    for (int i = 0; i < 8; ++i) printf(" %lld", st[44 + i]);
+    printf("\n");
     cudaMemcpy(c.A, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     for (int m = 0; m < batch; ++m) cudaMemcpy(c.A + (size_t)m * n * n, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(diag64_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);

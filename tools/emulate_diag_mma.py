@@ -4,6 +4,8 @@ change to the fragment / tile indexing of csrc/diag.cu:diag64_mma_kernel.  (The 
 import numpy as np
 
 NB, PB, MLD = 64, 8, 68
+TRAIL = [0x11, 0x21, 0x31, 0x41, 0x51, 0x61, 0x71, 0x22, 0x32, 0x42, 0x52, 0x62, 0x72, 0x33, 0x43, 0x53, 0x63, 0x73, 0x44, 0x54,
+         0x64, 0x74, 0x55, 0x65, 0x75, 0x66, 0x76, 0x77]
 LANES = np.arange(32)
 R, Q = LANES >> 2, LANES & 3
 
@@ -101,11 +103,6 @@ def run(A):
                     c0, c1 = dmma(c0, c1, a1, b1)
                     M[Ti + 2 * Q] = c0
                     M[Ti + 2 * Q + 1] = c1
-                    l0, l1 = cfrag_to_afrag(c0, c1)
-                    e0, e1 = dmma(z, z, l0, g0)
-                    e0, e1 = dmma(e0, e1, l1, g1)
-                    M[(PB * p + 2 * Q) * MLD + PB * i + R] = e0
-                    M[(PB * p + 2 * Q + 1) * MLD + PB * i + R] = e1
             assert sorted(seen) == list(range(p + 1, 8))
         fw = (p + 1) & 3
         Mnew = M.copy()
@@ -136,11 +133,8 @@ def run(A):
                             continue
                         assert t not in done
                         done.add(t)
-                        c, ln, tt = 0, m, t
-                        while tt >= ln:
-                            tt -= ln; ln -= 1; c += 1
-                        j = p + 1 + c
-                        i = j + tt
+                        e = TRAIL[8 * p - p * (p + 1) // 2 + t]
+                        i, j = e >> 4, e & 15
                         assert p < j <= i <= 7 and not (i == p + 1 and j == p + 1)
                         C = (PB * i + R) * MLD + PB * j + 2 * Q
                         Ao = (PB * i + R) * MLD + PB * p
@@ -151,15 +145,32 @@ def run(A):
                         Mnew[C] = c0; Mnew[C + 1] = c1
                     t0 += 3 * TB
             assert len(done) == ntile, (p, sorted(done), ntile)
+            gseen = []
+            for w3 in range(3):
+                for u in range(3):
+                    ig = p + 1 + w3 + 3 * u
+                    if ig >= 8:
+                        continue
+                    gseen.append(ig)
+                    Lr = (PB * ig + R) * MLD + PB * p
+                    e0, e1 = dmma(z, z, M[Lr + Q], g0)
+                    e0, e1 = dmma(e0, e1, M[Lr + 4 + Q], g1)
+                    Mnew[(PB * p + 2 * Q) * MLD + PB * ig + R] = e0
+                    Mnew[(PB * p + 2 * Q + 1) * MLD + PB * ig + R] = e1
+            assert sorted(gseen) == list(range(p + 1, 8))
         M = Mnew
         factor(M, V, rinv, p + 1)
-    # factor back
-    for idx in range(NB * NB // 2):
-        row, c2 = idx >> 5, idx & 31
-        if 2 * c2 + 1 <= row:
-            Aout[row, 2 * c2: 2 * c2 + 2] = M[row * MLD + 2 * c2: row * MLD + 2 * c2 + 2]
-        if 2 * c2 == row:
-            Aout[row, row] = M[row * MLD + row]
+    def store_l_column(pc):
+        v0, v1 = M[(PB * pc + R) * MLD + PB * pc + 2 * Q], M[(PB * pc + R) * MLD + PB * pc + 2 * Q + 1]
+        for lane in range(32):
+            r, q = R[lane], Q[lane]
+            if 2 * q + 1 <= r:
+                Aout[PB * pc + r, PB * pc + 2 * q] = v0[lane]; Aout[PB * pc + r, PB * pc + 2 * q + 1] = v1[lane]
+            elif 2 * q == r:
+                Aout[PB * pc + r, PB * pc + 2 * q] = v0[lane]
+        for i in range(pc + 1, 8):
+            Aout[PB * i + R, PB * pc + 2 * Q] = M[(PB * i + R) * MLD + PB * pc + 2 * Q]
+            Aout[PB * i + R, PB * pc + 2 * Q + 1] = M[(PB * i + R) * MLD + PB * pc + 2 * Q + 1]
 
     def store_w(i, j, c0, c1):
         W[(PB * i + R) * NB + PB * j + 2 * Q] = c0
@@ -167,34 +178,31 @@ def run(A):
         WT[(PB * j + 2 * Q) * NB + PB * i + R] = c0
         WT[(PB * j + 2 * Q + 1) * NB + PB * i + R] = c1
 
-    def inverse_rows(IA, IB):
-        na, nb = {}, {}
-        for j in range(IA + 1, 8):
-            store_w(IA, j, z, z)
-        for j in range(IB + 1, 8):
-            store_w(IB, j, z, z)
-        store_w(IA, IA, V[IA * 64 + R * 8 + 2 * Q], V[IA * 64 + R * 8 + 2 * Q + 1])
-        store_w(IB, IB, V[IB * 64 + R * 8 + 2 * Q], V[IB * 64 + R * 8 + 2 * Q + 1])
-        na[IA] = (-V[IA * 64 + R * 8 + Q], -V[IA * 64 + R * 8 + 4 + Q])
-        nb[IB] = (-V[IB * 64 + R * 8 + Q], -V[IB * 64 + R * 8 + 4 + Q])
-        for t in range(1, IA + 1):
-            for (I, n) in ((IA, na), (IB, nb)):
-                j = I - t
-                if j < 0:
-                    continue
-                so0, so1 = z, z
-                for k in range(I, j + 1, -1):
-                    gt = (PB * j + R) * MLD + PB * k
-                    so0, so1 = dmma(so0, so1, n[k][0], M[gt + Q])
-                    so0, so1 = dmma(so0, so1, n[k][1], M[gt + 4 + Q])
-                gt = (PB * j + R) * MLD + PB * (j + 1)
-                s0, s1 = dmma(z, z, n[j + 1][0], M[gt + Q])
-                s0, s1 = dmma(s0, s1, n[j + 1][1], M[gt + 4 + Q])
-                s0, s1 = s0 + so0, s1 + so1
-                store_w(I, j, s0, s1)
-                if j > 0:
-                    n[j] = cfrag_to_neg_afrag(s0, s1)
-    inverse_rows(7, 0); inverse_rows(6, 1); inverse_rows(5, 2); inverse_rows(4, 3)
+    def inverse_row(I):
+        n = {}
+        store_w(I, I, V[I * 64 + R * 8 + 2 * Q], V[I * 64 + R * 8 + 2 * Q + 1])
+        n[I] = (-V[I * 64 + R * 8 + Q], -V[I * 64 + R * 8 + 4 + Q])
+        for t in range(1, I + 1):
+            j = I - t
+            so0, so1, sp0, sp1 = z, z, z, z
+            for k in range(I, j + 1, -1):
+                gt = (PB * j + R) * MLD + PB * k
+                so0, so1 = dmma(so0, so1, n[k][0], M[gt + Q])
+                sp0, sp1 = dmma(sp0, sp1, n[k][1], M[gt + 4 + Q])
+            gt = (PB * j + R) * MLD + PB * (j + 1)
+            s0, s1 = dmma(z, z, n[j + 1][0], M[gt + Q])
+            s0, s1 = dmma(s0, s1, n[j + 1][1], M[gt + 4 + Q])
+            s0, s1 = s0 + so0 + sp0, s1 + so1 + sp1
+            if j > 0:
+                n[j] = cfrag_to_neg_afrag(s0, s1)
+            store_w(I, j, s0, s1)
+
+    # (the kernel issues column / row p inside step p; the data they read is final by then -- here simply afterwards)
+    for pc in range(8):
+        store_l_column(pc)
+        inverse_row(pc)
+        for j in range(pc + 1, 8):
+            store_w(pc, j, z, z)
     # statistics as the kernel forms them
     lg = sum(-np.log((rinv[4 * l] * rinv[4 * l + 1]) * (rinv[4 * l + 2] * rinv[4 * l + 3])) for l in range(16))
     return Aout, W.reshape(NB, NB), WT.reshape(NB, NB), rinv, 2.0 * lg
