@@ -23,6 +23,7 @@ constexpr int NB = kNB;          // 64
 using tile::LDS;
 using tile::TILE_THREADS;
 using tile::load_tile;
+using tile::load_tiles2;
 using tile::warp_mma;
 constexpr size_t TILE_SMEM = 2ull * NB * LDS * sizeof(double);
 
@@ -54,7 +55,9 @@ __device__ __forceinline__ void tri_decode(int t, int& a, int& b) {
   b = t - a * (a + 1) / 2;
 }
 
-template <int MODE>
+// CHAIN: the launch sits on the critical chain of a large factorisation with a handful of CTAs: round trips, not bytes or
+// occupancy, are its time (both operands in one global round trip, 64 more registers)
+template <int MODE, bool CHAIN = false>
 __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
   extern __shared__ __align__(16) double smem[];
   double* SA = smem;
@@ -103,8 +106,12 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
     const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * 2 * NB * NB;   // slot 0: W_kk
     const double* srcA = (ai < 0) ? Dm : Am + ((long)ai * NB) * g.ld + (long)aj * NB;
     const double* srcB = (bi < 0) ? Dm : Am + ((long)bi * NB) * g.ld + (long)bj * NB;
-    load_tile(SA, srcA, ai < 0 ? NB : g.ld);
-    load_tile(SB, srcB, bi < 0 ? NB : g.ld);
+    if (CHAIN) {
+      load_tiles2(SA, srcA, ai < 0 ? NB : g.ld, SB, srcB, bi < 0 ? NB : g.ld);
+    } else {
+      load_tile(SA, srcA, ai < 0 ? NB : g.ld);
+      load_tile(SB, srcB, bi < 0 ? NB : g.ld);
+    }
     __syncthreads();
 
     double acc[4][4][2];
@@ -187,21 +194,38 @@ __global__ void __launch_bounds__(TILE_THREADS) syrk_wide_kernel(EngineArgs g, i
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
+    const int r = lane >> 2, c = 2 * (lane & 3);
+    // !TRI = the few-tile launches on the critical chain (in-panel and NEXT updates): the C tile is fetched under the
+    // products and both operands of a k-block come in one global round trip; TRI (the bulk update) keeps its registers for
+    // occupancy
+    double2 cpre[TRI ? 1 : 4][TRI ? 1 : 4];
+    if (!TRI) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          cpre[TRI ? 0 : a][TRI ? 0 : b] = *reinterpret_cast<const double2*>(C + (long)(m0 + 8 * a + r) * g.ld + n0 + 8 * b + c);
+    }
     for (int kb = 0; kb < nkb; ++kb) {
-      load_tile(SA, Am + ((long)i * NB) * g.ld + (long)(kb0 + kb) * NB, g.ld);
-      load_tile(SB, Am + ((long)j * NB) * g.ld + (long)(kb0 + kb) * NB, g.ld);
+      const double* pa = Am + ((long)i * NB) * g.ld + (long)(kb0 + kb) * NB;
+      const double* pb = Am + ((long)j * NB) * g.ld + (long)(kb0 + kb) * NB;
+      if (!TRI) {
+        load_tiles2(SA, pa, g.ld, SB, pb, g.ld);
+      } else {
+        load_tile(SA, pa, g.ld);
+        load_tile(SB, pb, g.ld);
+      }
       __syncthreads();
       warp_mma<true, true>(SA, SB, m0, n0, acc);
       __syncthreads();
     }
-    double* C = Am + ((long)i * NB) * g.ld + (long)j * NB;
-    const int r = lane >> 2, c = 2 * (lane & 3);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         double2* p = reinterpret_cast<double2*>(C + (long)(m0 + 8 * a + r) * g.ld + n0 + 8 * b + c);
-        double2 v = *p;
+        double2 v = TRI ? *p : cpre[TRI ? 0 : a][TRI ? 0 : b];
         v.x -= acc[a][b][0];
         v.y -= acc[a][b][1];
         *p = v;
@@ -243,12 +267,12 @@ __global__ void __launch_bounds__(NB) trsm_panel_kernel(EngineArgs g) {
   }
 }
 
-template <int MODE>
+template <int MODE, bool CHAIN = false>
 int launch_tiles(const EngineArgs& g, int ntiles, cudaStream_t st, long* launches) {
   if (ntiles <= 0 || g.batch <= 0) return 0;
-  NMGP_SMEM_ATTR_PER_DEVICE(tile_kernel<MODE>, TILE_SMEM);
+  NMGP_SMEM_ATTR_PER_DEVICE((tile_kernel<MODE, CHAIN>), TILE_SMEM);
   dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
-  tile_kernel<MODE><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g);
+  tile_kernel<MODE, CHAIN><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g);
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -264,8 +288,9 @@ EngineArgs make_args(const BlockBatch& b) {
 }  // namespace
 
 namespace {
-int launch_panel(const BlockBatch& b, const EngineArgs& g, int r, bool stable_panel, cudaStream_t st, long* launches) {
-  if (!stable_panel) return launch_tiles<POTRF_PANEL>(g, r, st, launches);
+int launch_panel(const BlockBatch& b, const EngineArgs& g, int r, bool stable_panel, cudaStream_t st, long* launches,
+                 bool chain = false) {
+  if (!stable_panel) return chain ? launch_tiles<POTRF_PANEL, true>(g, r, st, launches) : launch_tiles<POTRF_PANEL>(g, r, st, launches);
   if (r <= 0) return 0;
   dim3 pg(r, b.batch < 65535 ? b.batch : 65535);
   constexpr size_t kTrsmSmem = 2ull * NB * (NB + 1) * sizeof(double);
@@ -356,7 +381,7 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
         continue;
       }
       if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
-      if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches))) break;
+      if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches, true))) break;
       if (k + 1 < p1) rc = launch_syrk_wide<false>(g, k + 1, p1, k, 1, crit, launches);   // rest of this panel, rank 64
       ++k;
     }

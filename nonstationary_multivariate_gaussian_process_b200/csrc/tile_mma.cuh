@@ -20,6 +20,27 @@ __device__ __forceinline__ void load_tile(double* __restrict__ S, const double* 
   }
 }
 
+// Two tiles with ALL 32 loads of a thread in flight before the first shared-memory store: ONE global round trip instead of
+// the eight of two load_tile calls (4 loads in flight each).  For the small launches on the critical chain of a large
+// factorisation, where the round trips, not the bytes, are the time; costs 64 transient registers.
+__device__ __forceinline__ void load_tiles2(double* __restrict__ SA, const double* __restrict__ srcA, int lda,
+                                            double* __restrict__ SB, const double* __restrict__ srcB, int ldb) {
+  constexpr int V2 = NB / 2, PER = NB * V2 / TILE_THREADS;   // 16 double2 per thread and tile
+  double2 va[PER], vb[PER];
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    const int idx = threadIdx.x + it * TILE_THREADS, r = idx / V2, c2 = idx % V2;
+    va[it] = *reinterpret_cast<const double2*>(srcA + (long)r * lda + 2 * c2);
+    vb[it] = *reinterpret_cast<const double2*>(srcB + (long)r * ldb + 2 * c2);
+  }
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    const int idx = threadIdx.x + it * TILE_THREADS, r = idx / V2, c2 = idx % V2;
+    *reinterpret_cast<double2*>(SA + r * LDS + 2 * c2) = va[it];
+    *reinterpret_cast<double2*>(SB + r * LDS + 2 * c2) = vb[it];
+  }
+}
+
 // acc(32x32 per warp) += opA(32 x NB) * opB(32 x NB)^T.   KM: S[row][k],  MM: S[k][row].
 template <bool A_KM, bool B_KM>
 __device__ __forceinline__ void warp_mma(const double* __restrict__ SA, const double* __restrict__ SB, int m0, int n0,

@@ -115,3 +115,47 @@ def test_a_failed_subject_does_not_poison_later_evaluations(S, cuda_device):
     plan.close()
     assert int(i1.abs().sum()) == 0
     assert torch.equal(v1, v0) and torch.equal(g1, g0)
+
+
+@pytest.mark.parametrize("j", [0, 7, 8, 36, 63, 64, 71, 130, 199])
+def test_diagonal_block_kernel_reports_the_exact_pivot(j, cuda_device):
+    """Diagonal matrices: pivot j IS entry j, so info must name it exactly wherever it sits in the 8 x 8 tile grid of the
+    64 x 64 diagonal-block kernel (csrc/diag.cu:diag64_mma_kernel / factor_tile); a subnormal pivot counts as a failure."""
+    from nonstationary_multivariate_gaussian_process_b200 import _lib
+    lib = _lib.load_library()
+    n = 200
+    d = np.linspace(0.5, 3.0, n)
+    S = np.stack([np.diag(d), np.diag(d), np.diag(d)])
+    S[0, j, j] = -1.0
+    S[2, j, j] = 1e-310
+    A = torch.from_numpy(S.copy()).cuda()
+    logdet = torch.empty(3, dtype=torch.float64, device="cuda")
+    info = torch.empty(3, dtype=torch.int32, device="cuda")
+    _lib.check(lib.nmgp_potrf_batched(A.data_ptr(), n, 3, logdet.data_ptr(), info.data_ptr(), None), "potrf")
+    torch.cuda.synchronize()
+    assert info.cpu().tolist() == [j + 1, 0, j + 1]
+    assert abs(logdet[1].item() - np.log(d).sum()) < 1e-12 * n
+    assert np.allclose(np.diagonal(A[1].cpu().numpy()), np.sqrt(d), rtol=1e-15, atol=0)
+
+
+def test_diagonal_block_kernel_log_determinant_of_badly_scaled_pivots(cuda_device):
+    """The kernel takes one logarithm per four reciprocal pivots: pivots between 1e-70 and 1e+70 must not overflow the
+    product, and the factor / inverse of a graded matrix stay accurate."""
+    from nonstationary_multivariate_gaussian_process_b200 import _lib
+    lib = _lib.load_library()
+    n = 128
+    rng = np.random.RandomState(5)
+    s = 10.0 ** rng.uniform(-70, 70, size=n)
+    Q = _spd(n, 1, 11)[0]
+    S = (s[:, None] * Q * s[None, :])[None]
+    A = torch.from_numpy(S.copy()).cuda()
+    logdet = torch.empty(1, dtype=torch.float64, device="cuda")
+    info = torch.empty(1, dtype=torch.int32, device="cuda")
+    _lib.check(lib.nmgp_potrf_batched(A.data_ptr(), n, 1, logdet.data_ptr(), info.data_ptr(), None), "potrf")
+    torch.cuda.synchronize()
+    assert int(info[0]) == 0
+    ref = np.linalg.slogdet(Q)[1] + 2.0 * np.log(s).sum()
+    assert abs(logdet[0].item() - ref) < 1e-11 * abs(ref) + 1e-9
+    L = np.tril(A[0].cpu().numpy())
+    Lq = L / s[:, None]                       # chol(D Q D) = D chol(Q)
+    assert np.abs(Lq - np.linalg.cholesky(Q)).max() < 1e-11

@@ -56,16 +56,6 @@ int main() {
     cudaMemcpy(c.A, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     for (int m = 0; m < batch; ++m) cudaMemcpy(c.A + (size_t)m * n * n, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     for (int m = 0; m < batch; ++m) cudaMemcpy(c.A + (size_t)m * n * n, A.data(), n * n * 8, cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(diag64_mma_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM_BYTES);
-    diag64_mma_ws_kernel<<<1, MMA_THREADS, MMA_SMEM_BYTES>>>(g);
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(st, g_diag_prof, sizeof(st));
-    {
-      double ld; cudaMemcpy(&ld, c.logdet + 7, 8, cudaMemcpyDeviceToHost);
-      printf("warp-specialised kernel, warm: load %lld  factorisation (all 8 tile columns) %lld  tail (row 7, statistics) %lld  total %lld  logdet %.6f (%s)\n",
-             st[1] - st[0], st[2] - st[1], st[9] - st[2], st[9] - st[0], ld, cudaGetErrorString(cudaGetLastError()));
-    }
-    for (int m = 0; m < batch; ++m) cudaMemcpy(c.A + (size_t)m * n * n, A.data(), n * n * 8, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(diag64_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     diag64_kernel<false, true><<<1, 2 * THREADS, SMEM_BYTES>>>(g);
     cudaDeviceSynchronize();
