@@ -461,7 +461,7 @@ def ours(a):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_source,
                 "kernel": "panel_gemm_kernel<mode> / inverse_kernel<mode> (left-looking potrf + guarded Takahashi / W^T W inverse: 64x64 "
-                          "DMMA.8x8x4 tiles fed by TMA, cp.async.bulk.tensor + 128B swizzle + mbarrier ring) + diag64_kernel; "
+                          "DMMA.8x8x4 tiles fed by TMA, cp.async.bulk.tensor + 128B swizzle + mbarrier ring) + diag64_mma_kernel (64x64 diagonal blocks on DMMA); "
                           "achieved = S*n^3 flop / (t_potrf + t_potri), phase times from CUDA events inside nmgp_logpost_grad_profile",
                 "peak_source": peak_source, "peak_clocks": peak_clk,
                 "algorithmic_flops_per_eval": f_potrf + f_potri,
