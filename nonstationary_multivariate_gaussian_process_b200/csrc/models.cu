@@ -210,16 +210,16 @@ __global__ void __launch_bounds__(32 * PWB) prior_solve_warp_kernel(const double
       const int k0 = o * 32;
       __syncwarp();
       if (TRANS) {   // rows k0.. (the solved x[r]), columns r0..r0+31 of L:  Ls[rr][kk] = L[k0+rr][r0+kk]
-#pragma unroll 8
+#pragma unroll 16
         for (int rr = 0; rr < 32; ++rr)
           Ls[rr * 34 + lane] = (k0 + rr < N) ? L[(long)(k0 + rr) * N + r0 + lane] : 0.0;   // r0 + lane < k0 <= N
       } else {       // rows r0..r0+31, columns k0..k0+31 (solved x[k]) of L, transposed:  Ls[kk][rr] = L[r0+rr][k0+kk]
-#pragma unroll 8
+#pragma unroll 16
         for (int rr = 0; rr < 32; ++rr)
           Ls[lane * 34 + rr] = (r0 + rr < N) ? L[(long)(r0 + rr) * N + k0 + lane] : 0.0;
       }
       __syncwarp();
-#pragma unroll 4
+#pragma unroll 8
       for (int kk = 0; kk < 32; ++kk) {
         const double xk = (vok && k0 + kk < N) ? Xc[(long)(k0 + kk) * nv + v] : 0.0;
         const double* row = Ls + kk * 34;
@@ -234,11 +234,11 @@ __global__ void __launch_bounds__(32 * PWB) prior_solve_warp_kernel(const double
     // ---- diagonal block
     __syncwarp();
     if (TRANS) {
-#pragma unroll 8
+#pragma unroll 16
       for (int rr = 0; rr < 32; ++rr)
         Ls[rr * 34 + lane] = (r0 + rr < N && r0 + lane < N) ? L[(long)(r0 + rr) * N + r0 + lane] : (rr == lane ? 1.0 : 0.0);
     } else {
-#pragma unroll 8
+#pragma unroll 16
       for (int rr = 0; rr < 32; ++rr)
         Ls[lane * 34 + rr] = (r0 + rr < N && r0 + lane < N) ? L[(long)(r0 + rr) * N + r0 + lane] : (rr == lane ? 1.0 : 0.0);
     }
