@@ -367,6 +367,15 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
     return rc == 0;
   };
   if (rc == 0) { cu(cudaEventRecord(ev0, st)); cu(cudaStreamWaitEvent(crit, ev0, 0)); }   // after whatever built the matrices
+  // the updates A(i,j) -= sum_c A(i,c) A(j,c)^T, ja <= j < jb, i >= j: on the TMA-ring kernel of engine_ll.cu where the batch has
+  // (or can build) tensor maps -- n = 16 384: potrf 53.0 -> 48.8 ms with the bulk update there (27 -> 30 TFLOP/s) -- else the plain
+  // tile kernels.  NMGP_REST_LL: 0 = plain kernels, 1 = bulk update only, 2 (default) = chain updates too.
+  static const int upd_ll = getenv("NMGP_REST_LL") ? atoi(getenv("NMGP_REST_LL")) : 2;
+  const bool can_ll = !stable_panel && (b.maps || (b.Dinv && b.Pbuf));
+  auto update = [&](int ja, int jb, int kb0, int nkb, cudaStream_t s, bool bulk) -> int {
+    if (can_ll && upd_ll >= (bulk ? 1 : 2)) return engine_syrk_update_ll(b, ja, jb, kb0, nkb, s, launches);
+    return bulk ? launch_syrk_wide<true>(g, ja, jb, kb0, nkb, s, launches) : launch_syrk_wide<false>(g, ja, jb, kb0, nkb, s, launches);
+  };
   bool rest_pending = false;
   int last_e = -1, panel = 0;
   for (int p0 = 0; rc == 0 && p0 < Kt; p0 += W, ++panel) {
@@ -382,7 +391,7 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
       }
       if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
       if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches, true))) break;
-      if (k + 1 < p1) rc = launch_syrk_wide<false>(g, k + 1, p1, k, 1, crit, launches);   // rest of this panel, rank 64
+      if (k + 1 < p1) rc = update(k + 1, p1, k, 1, crit, false);                          // rest of this panel, rank 64
       ++k;
     }
     if (rc != 0 || !cu(cudaEventRecord(evP[e], crit))) break;
@@ -391,10 +400,10 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
     if (rest_pending && !cu(cudaStreamWaitEvent(crit, evR[e ^ 1], 0))) break;              // REST(P-1) done
     rest_pending = false;
     const int n1 = p1 + W < Kt ? p1 + W : Kt;
-    if ((rc = launch_syrk_wide<false>(g, p1, n1, p0, p1 - p0, crit, launches))) break;     // NEXT: the next panel's columns
+    if ((rc = update(p1, n1, p0, p1 - p0, crit, false))) break;                           // NEXT: the next panel's columns
     if (n1 < Kt) {
       if (!cu(cudaStreamWaitEvent(st, evP[e], 0))) break;
-      if ((rc = launch_syrk_wide<true>(g, n1, Kt, p0, p1 - p0, st, launches))) break;      // REST
+      if ((rc = update(n1, Kt, p0, p1 - p0, st, true))) break;                              // REST: the bulk of the update
       if (!cu(cudaEventRecord(evR[e], st))) break;
       rest_pending = true;
     }

@@ -65,6 +65,10 @@ int engine_potri_ll_stable(const BlockBatch& b, cudaStream_t st, long* launches)
 // Same result with W = L^-1 formed level by level (two launches of independent long-K tiles per level): for a few large
 // matrices.  Accepts the factor of either potrf engine.  Requires b.A2 and b.Pbuf (tensor maps).
 int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launches);
+// Trailing update A(i,j) -= sum_{c in [kb0, kb0+nkb)} A(i,c) A(j,c)^T over the lower tiles i >= j, ja <= j < jb (jb = 0: all
+// remaining block columns) on the TMA-ring kernel: the updates of the right-looking potrf.  Needs b.maps or the buffers to
+// build them (A, Dinv, Pbuf).
+int engine_syrk_update_ll(const BlockBatch& b, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches);
 // TMA descriptors of a workspace, built once (the maps cover the whole workspace, so they serve every sub-batch of it).
 // `out` receives nullptr when the batch has no panel buffer.  engine_*_ll build a temporary set when b.maps is null.
 int engine_maps_create(const BlockBatch& b, void** out);

@@ -72,6 +72,9 @@ struct LLArgs {
   const double* pivmin;
   const double* pivmax;
   int* sched;   // [2] {next item, CTAs out of work}, zero between launches (the kernel resets them); nullptr = static grid
+  // SYRK_UPD: updated tiles (i, j), i >= j, ua <= j < ujb (ujb = 0: up to Kt, the whole trailing triangle), k-block range
+  // [ukb0, ukb0 + unkb)
+  int ua = 0, ujb = 0, ukb0 = 0, unkb = 0;
 };
 
 __device__ __forceinline__ bool guard_skips(const LLArgs& g, int mat) {
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(PG_THREADS, PG_CTAS) panel_gemm_kernel(const _
 //   REC_W   W(i,j)  = -sum_{c=b..i} W(i,c) T(c,j)     b = first block of the second half
 //                     -> lower tile (i,j) of A (over L21) and transposed -> upper tile (j,i) of A2 (operand of LAUUM)
 // 2 log2(Kt) launches instead of a 3 Kt sweep, every tile a long-K accumulation in registers.
-enum InvMode : int { PANEL_ALL = 0, TRTRI_ROW = 1, LAUUM = 2, REC_T = 3, REC_W = 4 };
+enum InvMode : int { PANEL_ALL = 0, TRTRI_ROW = 1, LAUUM = 2, REC_T = 3, REC_W = 4, SYRK_UPD = 5 };
 
 struct Tile {
   int i, j, nch;
@@ -457,6 +460,17 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
       t.i = base + hs + a; t.j = base + b;
       if (MODE == REC_T) { t.c0 = t.j; t.nch = (hs - b) * CPB; }          // c = j .. base+hs-1
       else { t.c0 = t.i; t.nch = (a + 1) * CPB; }                          // c = i .. base+hs (descending)
+    } else if (MODE == SYRK_UPD) {    // lower pairs incl. diagonal of the trailing triangle [ua, Kt); k-blocks ukb0 .. ukb0 + unkb - 1
+      if (g.ujb == 0) {
+        int a, b;
+        tri_decode(blockIdx.x + tt * gridDim.x, a, b);
+        t.i = g.ua + a; t.j = g.ua + b;
+      } else {                        // a few block columns: column by column, Kt - j tiles each
+        int tl = blockIdx.x + tt * gridDim.x, jj = g.ua;
+        while (jj < g.ujb - 1 && tl >= Kt - jj) { tl -= Kt - jj; ++jj; }
+        t.i = jj + tl; t.j = jj;
+      }
+      t.c0 = g.ukb0; t.nch = g.unkb * CPB;
     } else {                          // lower pairs incl. diagonal; k-blocks c = i .. last, the last one ragged
       tri_decode(blockIdx.x + tt * gridDim.x, t.i, t.j);
       t.nch = (last - t.i) * CPB + ragged_chunks;
@@ -506,6 +520,10 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
         if (cb == t.i) tma_load_chunk(SA, &mapD, kcol, 0, dbase + 2 * t.i, bar);
         else tma_load_chunk(SA, &mapA, cb * NB + kcol, t.i * NB, mat, bar);
         tma_load_chunk(SB, &mapA, cb * NB + kcol, t.j * NB, mat, bar);
+      } else if (MODE == SYRK_UPD) {     // A(i,cb) . A(j,cb)^T,  cb = ukb0 ..         (panel tiles of the factor)
+        const int cb = t.c0 + kb;
+        tma_load_chunk(SA, &mapA, cb * NB + kcol, t.i * NB, mat, bar);
+        tma_load_chunk(SB, &mapA, cb * NB + kcol, t.j * NB, mat, bar);
       } else {                           // W(cb,i)^T . W(cb,j),  cb = i .. last       (upper tiles (i,cb), (j,cb) of A2)
         const int cb = t.i + kb;
         if (cb == t.i) tma_load_chunk(SA, &mapD, kcol, 0, dbase + 2 * t.i + 1, bar);
@@ -531,7 +549,7 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
       const Tile t = tile_at(tt);
       const int rows_valid = (t.i == last) ? vlast : NB;
       const int cols_valid = (t.j == last) ? vlast : NB;
-      const bool diag_tile = (MODE == LAUUM) && t.i == t.j;
+      const bool diag_tile = (MODE == LAUUM || MODE == SYRK_UPD) && t.i == t.j;   // only the lower triangle is needed
       const bool active = (m0 < rows_valid) && (n0 < cols_valid) && !(diag_tile && m0 == 0 && n0 == NB / 2);
       for (int qq = 0; qq < t.nch; ++qq, ++gq) {
         const int slot = gq % STAGES;
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
         }
         // chunks of the first k-block that only meet structural zeros of the triangular diagonal inverse
         bool zero = false;
-        if (qq < CPB) {
+        if (qq < CPB && MODE != SYRK_UPD) {
           if (MODE == PANEL_ALL || MODE == REC_T) zero = (n0 == NB / 2 && qq < HALF);   // W_jj[k][n] = 0 for n > k
           else if (MODE == TRTRI_ROW || MODE == REC_W) zero = (m0 == 0 && qq >= HALF);  // W_ii[m][k] = 0 for k > m
           else zero = (m0 == NB / 2 && qq < HALF) || (diag_tile && n0 == NB / 2 && qq < HALF);   // W_ii[k][m] = 0 for m > k
@@ -567,6 +585,12 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
             if (MODE == PANEL_ALL || MODE == REC_T) {   // Lh(i,j)^T / T(i,j)^T -> upper tile (j,i) of A
               U[(long)col * g.ld + row] = acc[a][b][0];
               U[(long)(col + 1) * g.ld + row] = acc[a][b][1];
+            } else if (MODE == SYRK_UPD) {   // A(i,j) -= sum
+              double2* pp = reinterpret_cast<double2*>(C + (long)row * g.ld + col);
+              double2 v = *pp;
+              v.x -= acc[a][b][0];
+              v.y -= acc[a][b][1];
+              *pp = v;
             } else if (MODE == TRTRI_ROW || MODE == REC_W) {   // W(i,j) -> lower tile of A, W(i,j)^T -> upper tile of A2
               double2 v; v.x = -acc[a][b][0]; v.y = -acc[a][b][1];
               *reinterpret_cast<double2*>(C + (long)row * g.ld + col) = v;
@@ -744,6 +768,14 @@ int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launch
     const int full = Kt / (2 * hs), rest = Kt - full * 2 * hs;
     ntiles = full * hs * hs + (rest > hs ? (rest - hs) * hs : 0);
     g.step = hs;
+  } else if (MODE == SYRK_UPD) {
+    if (g.ujb == 0) {
+      const int T = Kt - g.ua;
+      ntiles = T * (T + 1) / 2;
+    } else {
+      ntiles = 0;
+      for (int jj = g.ua; jj < g.ujb; ++jj) ntiles += Kt - jj;
+    }
   } else {
     ntiles = MODE == PANEL_ALL ? Kt * (Kt - 1) / 2 : (MODE == TRTRI_ROW ? Kt - 1 : Kt * (Kt + 1) / 2);
   }
@@ -830,6 +862,20 @@ int engine_potri_ll_guarded(const BlockBatch& b, cudaStream_t st, long* launches
   NMGP_TRY(launch_inv<TRTRI_ROW>(*ms, g, st, launches));
   NMGP_TRY(launch_inv<LAUUM>(*ms, g, st, launches));
   return 0;
+}
+
+// Trailing update of the right-looking potrf on the TMA-ring kernel:  A(i,j) -= sum_{kb0 <= c < kb0+nkb} A(i,c) A(j,c)^T for
+// the lower tiles i >= j, ja <= j < jb (jb = 0 or Kt: the whole trailing triangle; the diagonal tiles' strictly-upper quarter
+// is not touched).  Replaces engine.cu's
+// syrk_wide_kernel<true> (single-buffered loads, 27 TFLOP/s at n = 16 384) wherever the batch has TMA descriptors or the
+// buffers to build them.
+int engine_syrk_update_ll(const BlockBatch& b, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches) {
+  if (b.batch <= 0 || ja >= b.Kt || nkb <= 0 || (jb != 0 && jb <= ja)) return 0;
+  MapRef mr;
+  NMGP_TRY(mr.init(b));
+  LLArgs g = make_ll(b);
+  g.ua = ja; g.ujb = jb >= b.Kt ? 0 : jb; g.ukb0 = kb0; g.unkb = nkb;
+  return launch_inv<SYRK_UPD>(*mr.ms, g, st, launches);
 }
 
 int engine_maps_create(const BlockBatch& b, void** out) {
