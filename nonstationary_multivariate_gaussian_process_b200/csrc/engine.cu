@@ -421,7 +421,8 @@ int engine_potrf(const BlockBatch& b, cudaStream_t st, long* launches, bool stab
   if (b.batch <= 0) return 0;
   if (b.NB != NB || b.nP != b.Kt * NB) { set_last_error("engine_potrf: bad block layout"); return -1; }
   // look-ahead pays when a block step does not fill the GPU for long: few matrices, several block columns
-  if (b.Kt >= 8 && ((long)b.batch * b.Kt < 2048 || getenv("NMGP_FORCE_LOOKAHEAD"))) return potrf_lookahead(b, st, launches, stable_panel);
+  if (b.Kt >= 8 && ((long)b.batch * b.Kt < 2048 || (b.batch < 96 && b.Kt >= 32) || getenv("NMGP_FORCE_LOOKAHEAD")))
+    return potrf_lookahead(b, st, launches, stable_panel);
   EngineArgs g = make_args(b);
   for (int k = 0; k < b.Kt; ++k) {
     g.step = k;

@@ -84,12 +84,14 @@ int engine_potri_ll_guarded(const BlockBatch& b, cudaStream_t st, long* launches
 constexpr int kTakahashiMaxBlocks = 16;
 
 // Heuristic: the left-looking path launches (Kt - k) * batch CTAs per block column, each a long K loop; it needs a few
-// waves of them (148 SMs x 4 resident CTAs) to keep the tensor pipes busy.  Below that the right-looking path with panels and
-// look-ahead (engine.cu) is ahead.  Measured on B200, potrf only (profiles/r01_potrf_panel_width.txt): n = 16 384: batch 8
-// equal (404 ms), batch 4 right-looking 206 vs 236 ms, batch 1 54 ms; n = 4096 batch 16: 16.7 vs 17.2 ms; n = 2048 batch 64:
-// left-looking 7.9 vs 9.0 ms.
+// waves of them (148 SMs x 4 resident CTAs) to keep the tensor pipes busy: thousands of mid-size matrices.  For a few dozen
+// LARGE matrices the right-looking path with panels and look-ahead (engine.cu), whose updates run on the same TMA-ring kernel
+// since the end of round 2, is ahead.  Measured on B200, potrf only, right- vs left-looking (profiles/r02_potrf_crossover.txt):
+// n = 2048 x 64: 7.2 vs 8.0 ms; n = 4096 x 32: 25.9 vs 29.5, x 64: 50.9 vs 51.4; n = 8192 x 16: 91 vs 111; n = 16 384 x 8:
+// 355 vs 431, x 23: 1022 vs 1067 ms.  (Round 1, before that kernel: n = 16 384 batch 8 equal, n = 2048 batch 64 left-looking
+// 7.9 vs 9.0 ms -- profiles/r01_potrf_panel_width.txt.)
 inline bool prefer_left_looking(const BlockBatch& b) {
-  return b.Pbuf != nullptr && (b.batch >= 96 || (long)b.batch * b.Kt >= 2048);
+  return b.Pbuf != nullptr && (b.batch >= 96 || (b.Kt < 32 && (long)b.batch * b.Kt >= 2048));
 }
 
 }  // namespace nmgp
