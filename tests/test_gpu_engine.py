@@ -159,3 +159,48 @@ def test_diagonal_block_kernel_log_determinant_of_badly_scaled_pivots(cuda_devic
     L = np.tril(A[0].cpu().numpy())
     Lq = L / s[:, None]                       # chol(D Q D) = D chol(Q)
     assert np.abs(Lq - np.linalg.cholesky(Q)).max() < 1e-11
+
+
+_SWITCH_SCRIPT = r"""
+import json, sys
+import numpy as np, torch
+from nonstationary_multivariate_gaussian_process_b200 import synth
+from nonstationary_multivariate_gaussian_process_b200.batched import LogPosteriorPlan
+N, M, S = 150, 8, 2          # n = 1200: 19 block columns, right-looking look-ahead potrf (batch * Kt < 2048)
+hyper = {"mu_tilde_l": 0.0, "alpha_tilde_l": 10.0, "beta_tilde_l": 1.0, "mu_L": 0.0, "alpha_L": 1.0, "beta_L": 1.0, "a": 1e-2, "b": 1e-2}
+xs, Ys, ps = [], [], []
+for s in range(S):
+    x, Y, _ = synth.sample_subject(N, M, 500 + s)
+    xs.append(x); Ys.append(Y); ps.append(synth.start_point("nonseparable", N, M, 500 + s, 0.05))
+plan = LogPosteriorPlan("nonseparable", np.stack(xs), np.stack(Ys), hyper)
+plan.set_engine("right")
+v, g, i = plan.value_and_grad(torch.from_numpy(np.stack(ps)).cuda())
+torch.cuda.synchronize()
+print(json.dumps({"v": v.cpu().numpy().tolist(), "g": g.cpu().numpy().tolist(), "info": int(i.abs().sum())}))
+"""
+
+
+def test_potrf_variants_behind_environment_switches_agree(cuda_device):
+    """The A/B switches are read once per process, so each variant runs in its own interpreter: the tensor-pipe diagonal block
+    against the FMA kernels (NMGP_DIAG_MMA), the updates of the right-looking potrf on the TMA-ring kernel against the plain tile
+    kernels (NMGP_REST_LL), the 128-wide diagonal step (NMGP_DIAG128).  Same factor up to rounding: values to 1e-12, gradients
+    to 1e-10."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for name, env in {"default": {}, "fma_diag": {"NMGP_DIAG_MMA": "0"}, "plain_updates": {"NMGP_REST_LL": "0"},
+                      "diag128": {"NMGP_DIAG128": "1"}}.items():
+        e = dict(os.environ, **env)
+        e["PYTHONPATH"] = root + os.pathsep + e.get("PYTHONPATH", "")
+        r = subprocess.run([sys.executable, "-c", _SWITCH_SCRIPT], env=e, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+        assert out[name]["info"] == 0
+    v0, g0 = np.array(out["default"]["v"]), np.array(out["default"]["g"])
+    for name in ("fma_diag", "plain_updates", "diag128"):
+        v, g = np.array(out[name]["v"]), np.array(out[name]["g"])
+        assert np.abs(v[:, 1] - v0[:, 1]).max() / np.abs(v0[:, 1]).max() < 1e-12, name
+        assert (np.linalg.norm(g - g0, axis=1) / np.linalg.norm(g0, axis=1)).max() < 1e-10, name
