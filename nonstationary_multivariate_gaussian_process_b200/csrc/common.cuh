@@ -43,6 +43,29 @@ constexpr int kMaxDevices = 64;
     }                                                                                                             \
   } while (0)
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_kernel_pdl(.., pdl = true) may be scheduled while
+// the previous kernel of its stream still runs; it must call pdl_wait() before touching anything that kernel (or any earlier
+// one) wrote.  pdl_launch_dependents() lets the NEXT kernel be scheduled early.  Both are no-ops for ordinary launches.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // number of SMs of the current device (148 on B200; never hard-coded in grid sizing)
 inline int sm_count() {
   static std::atomic<int> cached[kMaxDevices];

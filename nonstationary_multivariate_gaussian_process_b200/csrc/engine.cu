@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(EngineArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (warp >> 1) * 32, n0 = (warp & 1) * 32;
 
+  if (CHAIN) {   // may be a programmatic dependent of the diagonal-block kernel (common.cuh)
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   for (int mat = blockIdx.y; mat < g.batch; mat += gridDim.y) {
     double* Am = g.A + (long)mat * g.strideA;
     const double* Dm = g.Dinv + (long)mat * g.strideD + (long)s * 2 * NB * NB;   // slot 0: W_kk
@@ -268,11 +272,11 @@ __global__ void __launch_bounds__(NB) trsm_panel_kernel(EngineArgs g) {
 }
 
 template <int MODE, bool CHAIN = false>
-int launch_tiles(const EngineArgs& g, int ntiles, cudaStream_t st, long* launches) {
+int launch_tiles(const EngineArgs& g, int ntiles, cudaStream_t st, long* launches, bool pdl = false) {
   if (ntiles <= 0 || g.batch <= 0) return 0;
   NMGP_SMEM_ATTR_PER_DEVICE((tile_kernel<MODE, CHAIN>), TILE_SMEM);
   dim3 grid(ntiles, g.batch < 65535 ? g.batch : 65535);
-  tile_kernel<MODE, CHAIN><<<grid, TILE_THREADS, TILE_SMEM, st>>>(g);
+  NMGP_CUDA_TRY(launch_kernel_pdl(tile_kernel<MODE, CHAIN>, grid, dim3(TILE_THREADS), TILE_SMEM, st, pdl && CHAIN, g));
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -289,8 +293,8 @@ EngineArgs make_args(const BlockBatch& b) {
 
 namespace {
 int launch_panel(const BlockBatch& b, const EngineArgs& g, int r, bool stable_panel, cudaStream_t st, long* launches,
-                 bool chain = false) {
-  if (!stable_panel) return chain ? launch_tiles<POTRF_PANEL, true>(g, r, st, launches) : launch_tiles<POTRF_PANEL>(g, r, st, launches);
+                 bool chain = false, bool pdl = false) {
+  if (!stable_panel) return chain ? launch_tiles<POTRF_PANEL, true>(g, r, st, launches, pdl) : launch_tiles<POTRF_PANEL>(g, r, st, launches);
   if (r <= 0) return 0;
   dim3 pg(r, b.batch < 65535 ? b.batch : 65535);
   constexpr size_t kTrsmSmem = 2ull * NB * (NB + 1) * sizeof(double);
@@ -372,8 +376,16 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
   // tile kernels.  NMGP_REST_LL: 0 = plain kernels, 1 = bulk update only, 2 (default) = chain updates too.
   static const int upd_ll = getenv("NMGP_REST_LL") ? atoi(getenv("NMGP_REST_LL")) : 2;
   const bool can_ll = !stable_panel && (b.maps || (b.Dinv && b.Pbuf));
-  auto update = [&](int ja, int jb, int kb0, int nkb, cudaStream_t s, bool bulk) -> int {
-    if (can_ll && upd_ll >= (bulk ? 1 : 2)) return engine_syrk_update_ll(b, ja, jb, kb0, nkb, s, launches);
+  // The kernels of the chain as programmatic dependents of one another (scheduled while their predecessor still runs,
+  // griddepcontrol.wait before they read: common.cuh): hides most of the launch gap between the three dependent launches of a
+  // block column.  Measured (profiles/r02_potrf_crossover.txt): it pays where the chain IS the time -- one matrix of n = 3000:
+  // 1.63 -> 1.37 ms, n = 5000: 3.07 -> 2.87 ms -- and costs 2-6 % where a bulk update runs beside the chain (n = 8000: 7.48 ->
+  // 7.62 ms, n = 16 384: 47.0 -> 48.4 ms, 4 x n = 4096: 4.03 -> 4.28 ms: the early-scheduled CTAs wait in slots the update
+  // could use).  Hence: batch * Kt <= 96.  NMGP_PDL = 0 / 1 forces it off / on.
+  static const int want_pdl = getenv("NMGP_PDL") ? atoi(getenv("NMGP_PDL")) : -1;
+  const bool pdl = can_ll && upd_ll >= 2 && !stable_panel && (want_pdl >= 0 ? want_pdl != 0 : (long)b.batch * Kt <= 96);
+  auto update = [&](int ja, int jb, int kb0, int nkb, cudaStream_t s, bool bulk, bool dep = false) -> int {
+    if (can_ll && upd_ll >= (bulk ? 1 : 2)) return engine_syrk_update_ll(b, ja, jb, kb0, nkb, s, launches, dep && pdl);
     return bulk ? launch_syrk_wide<true>(g, ja, jb, kb0, nkb, s, launches) : launch_syrk_wide<false>(g, ja, jb, kb0, nkb, s, launches);
   };
   bool rest_pending = false;
@@ -389,9 +401,11 @@ int potrf_lookahead(const BlockBatch& b, cudaStream_t st, long* launches, bool s
         k += 2;
         continue;
       }
-      if ((rc = engine_diag_step(b, k, crit, launches, stable_panel))) break;
-      if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches, true))) break;
-      if (k + 1 < p1) rc = update(k + 1, p1, k, 1, crit, false);                          // rest of this panel, rank 64
+      // (the first diagonal block follows the caller's work, the one after a panel boundary follows NEXT: a kernel either way,
+      //  but the very first launch of the chain has an event wait in front of it)
+      if ((rc = engine_diag_step(b, k, crit, launches, stable_panel, pdl && k > 0))) break;
+      if ((rc = launch_panel(b, g, Kt - k - 1, stable_panel, crit, launches, true, pdl))) break;
+      if (k + 1 < p1) rc = update(k + 1, p1, k, 1, crit, false, true);                    // rest of this panel, rank 64
       ++k;
     }
     if (rc != 0 || !cu(cudaEventRecord(evP[e], crit))) break;

@@ -48,7 +48,8 @@ int engine_trtri(const BlockBatch& b, cudaStream_t st, long* launches);
 int engine_potri(const BlockBatch& b, cudaStream_t st, long* launches);
 
 // One diagonal-block step (factor A(k,k), W_kk = L_kk^-1 into Dinv, log det, info) -- shared by both engines.
-int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches, bool accurate = false);
+// pdl: programmatic dependent launch behind the previous kernel of `st` (common.cuh); only the tensor-pipe kernel honours it
+int engine_diag_step(const BlockBatch& b, int k, cudaStream_t st, long* launches, bool accurate = false, bool pdl = false);
 
 // 128-wide diagonal step for a handful of large matrices: blocks k and k+1 in ONE launch (both diagonal factorisations, the
 // tile between them, W21 of the 128 x 128 inverse into Pbuf slot k) followed by the panel below both block columns.
@@ -68,7 +69,8 @@ int engine_potri_ll_recursive(const BlockBatch& b, cudaStream_t st, long* launch
 // Trailing update A(i,j) -= sum_{c in [kb0, kb0+nkb)} A(i,c) A(j,c)^T over the lower tiles i >= j, ja <= j < jb (jb = 0: all
 // remaining block columns) on the TMA-ring kernel: the updates of the right-looking potrf.  Needs b.maps or the buffers to
 // build them (A, Dinv, Pbuf).
-int engine_syrk_update_ll(const BlockBatch& b, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches);
+int engine_syrk_update_ll(const BlockBatch& b, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches,
+                          bool pdl = false);
 // TMA descriptors of a workspace, built once (the maps cover the whole workspace, so they serve every sub-batch of it).
 // `out` receives nullptr when the batch has no panel buffer.  engine_*_ll build a temporary set when b.maps is null.
 int engine_maps_create(const BlockBatch& b, void** out);

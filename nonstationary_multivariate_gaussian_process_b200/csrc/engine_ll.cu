@@ -482,6 +482,10 @@ __global__ void __launch_bounds__(THREADS, 4) inverse_kernel(const __grid_consta
     for (int st = 0; st < STAGES; ++st) mbar_init(&full[st], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (MODE == SYRK_UPD) {   // the chain launches of the look-ahead potrf may be programmatic dependents (common.cuh)
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   __syncthreads();
   int gq = 0;
 
@@ -759,7 +763,7 @@ int engine_potrf_ll(const BlockBatch& b, cudaStream_t st, long* launches) {
 
 namespace {
 template <int MODE>
-int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launches, int hs = 0) {
+int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launches, int hs = 0, bool pdl = false) {
   if (g0.batch <= 0) return 0;
   LLArgs g = g0;
   const int Kt = g.Kt;
@@ -791,7 +795,7 @@ int launch_inv(const MapSet& ms, const LLArgs& g0, cudaStream_t st, long* launch
     if (gx < 1) gx = 1;
   }
   dim3 grid(gx, gy);
-  inverse_kernel<MODE><<<grid, THREADS, LL_SMEM, st>>>(ms.mA, ms.mA2, ms.mD, g);
+  NMGP_CUDA_TRY(launch_kernel_pdl(inverse_kernel<MODE>, grid, dim3(THREADS), LL_SMEM, st, pdl, ms.mA, ms.mA2, ms.mD, g));
   NMGP_CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -869,13 +873,13 @@ int engine_potri_ll_guarded(const BlockBatch& b, cudaStream_t st, long* launches
 // is not touched).  Replaces engine.cu's
 // syrk_wide_kernel<true> (single-buffered loads, 27 TFLOP/s at n = 16 384) wherever the batch has TMA descriptors or the
 // buffers to build them.
-int engine_syrk_update_ll(const BlockBatch& b, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches) {
+int engine_syrk_update_ll(const BlockBatch& b, int ja, int jb, int kb0, int nkb, cudaStream_t st, long* launches, bool pdl) {
   if (b.batch <= 0 || ja >= b.Kt || nkb <= 0 || (jb != 0 && jb <= ja)) return 0;
   MapRef mr;
   NMGP_TRY(mr.init(b));
   LLArgs g = make_ll(b);
   g.ua = ja; g.ujb = jb >= b.Kt ? 0 : jb; g.ukb0 = kb0; g.unkb = nkb;
-  return launch_inv<SYRK_UPD>(*mr.ms, g, st, launches);
+  return launch_inv<SYRK_UPD>(*mr.ms, g, st, launches, 0, pdl);
 }
 
 int engine_maps_create(const BlockBatch& b, void** out) {
